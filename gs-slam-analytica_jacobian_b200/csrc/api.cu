@@ -1,0 +1,234 @@
+// C-ABI of gsr_b200 (declared in include/gsr_b200.h).  Thin host layer: argument checks, workspace
+// carve-up, stream plumbing; no torch types, no global state beyond a thread-local error string.
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../include/gsr_b200.h"
+#include "gsr_params.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "")
+{
+	snprintf(g_err, sizeof(g_err), fmt, detail);
+	return code;
+}
+
+int check_cuda(const char* where)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", where, cudaGetErrorString(e));
+		return GSR_ERR_CUDA;
+	}
+	return GSR_OK;
+}
+
+int debug_sync(const gsr_scene* s, cudaStream_t st, const char* where)
+{
+	if (!s->debug) return check_cuda(where);
+	cudaError_t e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		snprintf(g_err, sizeof(g_err), "CUDA error after %s: %s", where, cudaGetErrorString(e));
+		return GSR_ERR_CUDA;
+	}
+	return check_cuda(where);
+}
+
+int make_scene(const gsr_scene* a, gsr::Scene& s)
+{
+	if (!a) return fail(GSR_ERR_ARG, "null scene");
+	if (a->P < 0 || a->W <= 0 || a->H <= 0) return fail(GSR_ERR_ARG, "bad P/W/H");
+	if (a->W > 16 * 65535 || a->H > 16 * 65535 || ((a->W + 15) / 16) * (long long)((a->H + 15) / 16) > 65535)
+		return fail(GSR_ERR_ARG, "image too large: tile ids are 16-bit (max 65535 tiles)");
+	if (a->P > 0) {
+		if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->background)
+			return fail(GSR_ERR_ARG, "means3D, opacities, viewmatrix, projmatrix and background are required");
+		if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
+			return fail(GSR_ERR_ARG, "Please provide excatly one of either SHs or precomputed colors!");
+		const bool sr = a->scales != nullptr && a->rotations != nullptr;
+		if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
+		    ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
+			return fail(GSR_ERR_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+		(void)sr;
+		if (a->shs && (a->M <= 0 || a->M > 16 || (a->D + 1) * (a->D + 1) > a->M || a->D < 0 || a->D > 3))
+			return fail(GSR_ERR_ARG, "SH degree / coefficient count mismatch");
+		if (a->shs && !a->campos) return fail(GSR_ERR_ARG, "campos is required with SHs");
+		if (a->rotations && ((size_t)a->rotations & 15)) return fail(GSR_ERR_ARG, "rotations must be 16-byte aligned");
+	}
+	s.P = a->P; s.D = a->D; s.M = a->shs ? a->M : 0; s.W = a->W; s.H = a->H;
+	s.background = a->background; s.means3D = a->means3D; s.shs = a->shs; s.colors_precomp = a->colors_precomp;
+	s.opacities = a->opacities; s.scales = a->scales; s.rotations = a->rotations; s.cov3D_precomp = a->cov3D_precomp;
+	s.viewmatrix = a->viewmatrix; s.projmatrix = a->projmatrix; s.projmatrix_raw = a->projmatrix_raw; s.campos = a->campos;
+	s.scale_modifier = a->scale_modifier; s.tan_fovx = a->tan_fovx; s.tan_fovy = a->tan_fovy;
+	// focal lengths are derived, not passed (rasterizer_impl.cu:272-273)
+	s.focal_y = a->H / (2.0f * a->tan_fovy);
+	s.focal_x = a->W / (2.0f * a->tan_fovx);
+	s.grid_x = (a->W + GSR_TILE - 1) / GSR_TILE;
+	s.grid_y = (a->H + GSR_TILE - 1) / GSR_TILE;
+	s.prefiltered = a->prefiltered;
+	return GSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gsr_error_string(void) { return g_err; }
+int gsr_version(void) { return 100; }
+
+size_t gsr_geometry_bytes(int P) { return gsr::geom_bytes((size_t)(P > 0 ? P : 0)); }
+size_t gsr_image_bytes(int W, int H) { return gsr::image_bytes((size_t)W, (size_t)H); }
+size_t gsr_binning_bytes(int P, long long cap)
+{
+	return gsr::binning_bytes((size_t)(P > 0 ? P : 0), (size_t)(cap > 0 ? cap : 0));
+}
+
+int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* radii, int* n_touched, void* stream)
+{
+	gsr::Scene s;
+	int rc = make_scene(a, s);
+	if (rc) return rc;
+	if (!geom || geom_bytes < gsr::geom_bytes(s.P)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
+	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
+	cudaStream_t st = (cudaStream_t)stream;
+	gsr::GeomView g = gsr::geom_view(geom, s.P);
+	gsr::launch_preprocess_forward(s, g, radii, n_touched, st);
+	return debug_sync(a, st, "preprocess");
+}
+
+int gsr_forward_num_rendered(void* geom, void* stream, long long* out)
+{
+	if (!geom || !out) return fail(GSR_ERR_ARG, "null argument");
+	gsr::GeomView g = gsr::geom_view(geom, 0);
+	unsigned int r = 0;
+	cudaError_t e = cudaMemcpyAsync(&r, &g.hdr->num_rendered, sizeof(r), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+	if (e != cudaSuccess) return fail(GSR_ERR_CUDA, "reading num_rendered: %s", cudaGetErrorString(e));
+	*out = (long long)r;
+	return GSR_OK;
+}
+
+int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t binning_bytes, long long capacity,
+                       long long R_host, void* image, size_t image_bytes, float* out_color, float* out_depth,
+                       float* out_opacity, int* n_touched, void* stream)
+{
+	gsr::Scene s;
+	int rc = make_scene(a, s);
+	if (rc) return rc;
+	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
+	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
+	if (capacity >= (1ll << 30)) return fail(GSR_ERR_ARG, "more than 2^30 tile instances are not supported");
+	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
+	if (!binning || binning_bytes < gsr::binning_bytes(s.P, (size_t)capacity)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	if (!out_color || !out_depth || !out_opacity || (s.P > 0 && !n_touched)) return fail(GSR_ERR_ARG, "null output");
+	cudaStream_t st = (cudaStream_t)stream;
+	gsr::GeomView g = gsr::geom_view(geom, s.P);
+	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
+	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
+	gsr::launch_binning(s, g, b, im, (size_t)capacity, (size_t)(R_host >= 0 ? R_host : capacity), st);
+	rc = debug_sync(a, st, "binning");
+	if (rc) return rc;
+	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, st);
+	return debug_sync(a, st, "render");
+}
+
+int gsr_forward_overflowed(void* geom, void* stream, int* overflowed, long long* needed)
+{
+	if (!geom || !overflowed) return fail(GSR_ERR_ARG, "null argument");
+	gsr::GeomView g = gsr::geom_view(geom, 0);
+	unsigned int h[2] = {0, 0};
+	cudaError_t e = cudaMemcpyAsync(h, g.hdr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+	if (e != cudaSuccess) return fail(GSR_ERR_CUDA, "reading overflow flag: %s", cudaGetErrorString(e));
+	*overflowed = h[1] != 0;
+	if (needed) *needed = h[0];
+	return GSR_OK;
+}
+
+int gsr_rasterize_gaussians(const gsr_scene* a, void* geom, size_t geom_bytes, void* image, size_t image_bytes,
+                            gsr_alloc_fn alloc, void* user, void** binning_out, long long* R_out, float* out_color,
+                            float* out_depth, float* out_opacity, int* radii, int* n_touched, void* stream)
+{
+	if (!alloc || !binning_out || !R_out) return fail(GSR_ERR_ARG, "null argument");
+	int rc = gsr_forward_plan(a, geom, geom_bytes, radii, n_touched, stream);
+	if (rc) return rc;
+	long long R = 0;
+	rc = gsr_forward_num_rendered(geom, stream, &R);
+	if (rc) return rc;
+	const size_t bytes = gsr_binning_bytes(a->P, R);
+	void* bin = alloc(user, bytes);
+	if (!bin) return fail(GSR_ERR_WORKSPACE, "binning allocator returned null");
+	*binning_out = bin;
+	*R_out = R;
+	return gsr_forward_render(a, geom, bin, bytes, R, R, image, image_bytes, out_color, out_depth, out_opacity, n_touched, stream);
+}
+
+int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void* geom, void* binning, long long capacity,
+                                     void* image, const float* dL_dout_color, const float* dL_dout_depth,
+                                     float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors,
+                                     float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                                     float* dL_dtau, void* stream)
+{
+	gsr::Scene s;
+	int rc = make_scene(a, s);
+	if (rc) return rc;
+	if (!dL_dtau) return fail(GSR_ERR_ARG, "dL_dtau output is required");
+	cudaStream_t st = (cudaStream_t)stream;
+	if (s.P == 0) {
+		cudaMemsetAsync(dL_dtau, 0, 6 * sizeof(float), st);
+		return check_cuda("backward(P=0)");
+	}
+	if (!geom || !binning || !image || !radii) return fail(GSR_ERR_ARG, "null workspace");
+	if (!dL_dout_color || !dL_dout_depth) return fail(GSR_ERR_ARG, "null upstream gradient");
+	if (!s.projmatrix_raw) return fail(GSR_ERR_ARG, "projmatrix_raw is required by the backward");
+	if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacity) return fail(GSR_ERR_ARG, "null gradient output");
+	if (s.shs && !dL_dsh) return fail(GSR_ERR_ARG, "dL_dsh is required with SHs");
+	if (s.scales && (!dL_dscales || !dL_drotations)) return fail(GSR_ERR_ARG, "dL_dscales / dL_drotations required");
+	if (dL_drotations && ((size_t)dL_drotations & 15)) return fail(GSR_ERR_ARG, "dL_drotations must be 16-byte aligned");
+	gsr::GeomView g = gsr::geom_view(geom, s.P);
+	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
+	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
+	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, st);
+	rc = debug_sync(a, st, "render backward");
+	if (rc) return rc;
+	gsr::launch_preprocess_backward(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
+	                                dL_drotations, dL_dcov3D, dL_dtau, st);
+	return debug_sync(a, st, "preprocess backward");
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream)
+{
+	(void)projmatrix;   // the reference's test only uses the view matrix (auxiliary.h:152-154)
+	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSR_ERR_ARG, "bad argument");
+	gsr::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+	return check_cuda("mark_visible");
+}
+
+int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long capacity, void* image,
+                       unsigned long long* out)
+{
+	if (!geom || !out) return fail(GSR_ERR_ARG, "null argument");
+	gsr::GeomView g = gsr::geom_view(geom, P);
+	out[0] = (unsigned long long)g.rec;
+	out[1] = (unsigned long long)g.tiles_touched;
+	out[2] = (unsigned long long)g.clamped;
+	out[3] = out[4] = out[5] = out[6] = 0;
+	if (binning) {
+		gsr::BinView b = gsr::bin_view(binning, P, (size_t)capacity);
+		out[3] = (unsigned long long)b.point_list;
+	}
+	if (image) {
+		gsr::ImageView im = gsr::image_view(image, W, H);
+		out[4] = (unsigned long long)im.ranges;
+		out[5] = (unsigned long long)im.final_T;
+		out[6] = (unsigned long long)im.n_contrib;
+	}
+	out[7] = (unsigned long long)g.hdr;
+	return GSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// gsr_b200: B200-native (sm_100a) differentiable Gaussian-splatting rasterizer.
+// Shared layouts and device helpers.  See DESIGN.md for the data layout in HBM.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define GSR_TILE 16            // tile edge in pixels (reference config.h:16-17 BLOCK_X/BLOCK_Y)
+#define GSR_TILE_PIX 256
+#define GSR_ALIGN 256          // carve-up alignment inside workspaces
+
+namespace gsr {
+
+// ---------------------------------------------------------------------------------------------
+// Per-Gaussian render record: 48 B, three 16-byte words, written once by the forward preprocess,
+// gathered (3 x LDG.128 / cp.async 16) by both render kernels and read by the backward preprocess.
+//   q0 = { mean2D.x, mean2D.y, conic.xx, conic.xy }
+//   q1 = { conic.yy, opacity, view-space depth, red }
+//   q2 = { green, blue, rect (4 x u16: min.x, min.y, max.x, max.y packed in 2 words) }
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) GaussRec {
+	float4 q0, q1, q2;
+};
+
+// Per-Gaussian accumulator of the render backward (48 B): what the reference keeps in five
+// zero-filled tensors (rasterize_points.cu:176-180).
+//   a0 = { dL/dmean2D.x, dL/dmean2D.y (NDC units), dL/dconic.xx, dL/dconic.xy }
+//   a1 = { dL/dconic.yy, dL/dopacity, dL/ddepth, dL/dred }
+//   a2 = { dL/dgreen, dL/dblue, 0, 0 }
+struct alignas(16) GaussAcc {
+	float4 a0, a1, a2;
+};
+
+// Header at the start of the geometry workspace (device memory, 256 B)
+struct GeomHeader {
+	unsigned int num_rendered;   // R = sum of tiles touched
+	unsigned int overflow;       // set when R exceeded the binning capacity handed to stage B
+	unsigned int num_visible;    // Gaussians with radii > 0
+	unsigned int ticket[8];      // dynamic tile tickets of the sort / emit passes
+	unsigned int bwd_blocks_done;
+	unsigned int pad[64 - 12];
+};
+static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a = GSR_ALIGN) { return (v + a - 1) / a * a; }
+
+// Geometry workspace (one per forward call, kept for the backward):
+struct GeomView {
+	GeomHeader* hdr;
+	GaussRec* rec;           // [P]
+	GaussAcc* acc;           // [P]   zeroed by the forward preprocess, consumed+cleared by backward
+	uint32_t* tiles_touched; // [P]
+	uint32_t* depth_key;     // [P]   float bits of view depth, 0x7F800000 when culled
+	uint8_t* clamped;        // [P]   bit ch set when SH colour channel ch was clamped at 0
+	float* tau_partial;      // [ceil(P/256) * 8] per-block pose-gradient partials
+};
+
+__host__ __device__ inline size_t geom_bytes(size_t P)
+{
+	size_t s = sizeof(GeomHeader);
+	s += align_up(P * sizeof(GaussRec));
+	s += align_up(P * sizeof(GaussAcc));
+	s += align_up(P * 4);
+	s += align_up(P * 4);
+	s += align_up(P);
+	s += align_up(((P + 255) / 256) * 8 * sizeof(float));
+	return s + GSR_ALIGN;
+}
+
+__host__ __device__ inline GeomView geom_view(void* base, size_t P)
+{
+	char* p = (char*)align_up((size_t)base);
+	GeomView g;
+	g.hdr = (GeomHeader*)p; p += sizeof(GeomHeader);
+	g.rec = (GaussRec*)p; p += align_up(P * sizeof(GaussRec));
+	g.acc = (GaussAcc*)p; p += align_up(P * sizeof(GaussAcc));
+	g.tiles_touched = (uint32_t*)p; p += align_up(P * 4);
+	g.depth_key = (uint32_t*)p; p += align_up(P * 4);
+	g.clamped = (uint8_t*)p; p += align_up(P);
+	g.tau_partial = (float*)p;
+	return g;
+}
+
+// Image workspace: final transmittance, last contributor, per-tile ranges.
+struct ImageView {
+	float* final_T;      // [H*W]
+	uint32_t* n_contrib; // [H*W]
+	uint2* ranges;       // [tiles]
+};
+__host__ __device__ inline size_t image_bytes(size_t W, size_t H)
+{
+	size_t tiles = ((W + 15) / 16) * ((H + 15) / 16);
+	return align_up(W * H * 4) * 2 + align_up(tiles * 8) + GSR_ALIGN;
+}
+__host__ __device__ inline ImageView image_view(void* base, size_t W, size_t H)
+{
+	char* p = (char*)align_up((size_t)base);
+	ImageView v;
+	v.final_T = (float*)p; p += align_up(W * H * 4);
+	v.n_contrib = (uint32_t*)p; p += align_up(W * H * 4);
+	v.ranges = (uint2*)p;
+	return v;
+}
+
+// Binning workspace.  point_list[R] is the product (kept for the backward); the rest is scratch.
+#define GSR_SORT_THREADS 256
+#define GSR_SORT_ITEMS 8
+#define GSR_SORT_TILE (GSR_SORT_THREADS * GSR_SORT_ITEMS)
+
+struct BinView {
+	uint32_t* point_list;     // [R]  Gaussian ids sorted by (tile, depth)        <- kept
+	uint32_t* inst_val_alt;   // [R]  ping-pong partner of point_list
+	uint16_t* inst_tile;      // [R]  tile id of every instance (ping)
+	uint16_t* inst_tile_alt;  // [R]  (pong)
+	uint32_t* gkey_alt;       // [P]  depth-key pong
+	uint32_t* order;          // [P]  Gaussian ids in depth order (ping)
+	uint32_t* order_alt;      // [P]
+	uint32_t* hist;           // [6][256] global digit histograms: 4 depth passes, 2 tile passes
+	uint32_t* lookback;       // decoupled look-back status words, zeroed every forward
+	size_t lookback_words;
+	uint32_t* emit_status;    // [ceil(P/256)] look-back words of the scan+emit kernel (part of lookback block)
+};
+__host__ __device__ inline size_t sort_tiles(size_t n) { return (n + GSR_SORT_TILE - 1) / GSR_SORT_TILE; }
+__host__ __device__ inline size_t lookback_words(size_t P, size_t R)
+{
+	// 4 depth passes + 2 tile passes, 256 words per sort tile, + emit status + histograms
+	return 4 * sort_tiles(P) * 256 + 2 * sort_tiles(R) * 256 + align_up((P + 255) / 256, 64) + 6 * 256;
+}
+__host__ __device__ inline size_t binning_bytes(size_t P, size_t R)
+{
+	size_t s = 0;
+	s += 2 * align_up(R * 4) + 2 * align_up(R * 2) + 3 * align_up(P * 4);
+	s += align_up(lookback_words(P, R) * 4);
+	return s + GSR_ALIGN;
+}
+__host__ __device__ inline BinView bin_view(void* base, size_t P, size_t R)
+{
+	char* p = (char*)align_up((size_t)base);
+	BinView b;
+	b.point_list = (uint32_t*)p; p += align_up(R * 4);
+	b.inst_val_alt = (uint32_t*)p; p += align_up(R * 4);
+	b.inst_tile = (uint16_t*)p; p += align_up(R * 2);
+	b.inst_tile_alt = (uint16_t*)p; p += align_up(R * 2);
+	b.gkey_alt = (uint32_t*)p; p += align_up(P * 4);
+	b.order = (uint32_t*)p; p += align_up(P * 4);
+	b.order_alt = (uint32_t*)p; p += align_up(P * 4);
+	b.lookback_words = lookback_words(P, R);
+	b.hist = (uint32_t*)p;                 // first 6*256 words of the zeroed block
+	b.emit_status = b.hist + 6 * 256;
+	b.lookback = b.emit_status + align_up((P + 255) / 256, 64);
+	return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// vector reduction to global memory: one 16-byte RED instead of four scalar atomics (sm_90+)
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+	             : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// cp.async 16-byte global->shared (LDGSTS), used to stage gathered Gaussian records
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+	unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+}  // namespace gsr

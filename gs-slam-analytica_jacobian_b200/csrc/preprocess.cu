@@ -1,0 +1,295 @@
+// Forward per-Gaussian preprocess: EWA projection of the 3D covariance to a 2D conic, SH -> RGB,
+// radius and tile bounds.  Replaces reference preprocessCUDA (cuda_rasterizer/forward.cu:157-401)
+// and checkFrustum (rasterizer_impl.cu:54-66).
+//
+// Arithmetic contract: radii, tile rectangles and depth keys must be bit-identical to the reference,
+// so the fp32 expression trees that feed them (view/clip transform, cov3D = (S R)^T (S R),
+// cov2D = (W J)^T Vrk^T (W J), eigenvalue radius, double-precision ndc2Pix, getRect) are written
+// with the same association order as the reference + glm 0.9.9 (type_mat3x3.inl:486-518), and are
+// compiled with the same default -fmad contraction.
+#include "gsr_params.h"
+
+namespace gsr {
+
+namespace {
+
+struct M3 {            // column-major 3x3: m[c][r], same indexing as glm::mat3
+	float m[3][3];
+};
+__device__ __forceinline__ M3 m3_mul(const M3& A, const M3& B)
+{
+	M3 R;
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+			R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+	return R;
+}
+__device__ __forceinline__ M3 m3_transpose(const M3& A)
+{
+	M3 R;
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+	return R;
+}
+
+__device__ const float kSH_C0 = 0.28209479177387814f;
+__device__ const float kSH_C1 = 0.4886025119029199f;
+__device__ const float kSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float kSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                   -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+// Block-cooperative vectorised load of a [P,3] fp32 array slice (256 rows) into shared memory.
+__device__ __forceinline__ void load_rows3(const float* __restrict__ g, int row0, int P, float* s, bool vec_ok)
+{
+	const int n = min(256, P - row0) * 3;
+	const float* src = g + (size_t)row0 * 3;
+	if (vec_ok) {
+		const int n4 = n >> 2;
+		const float4* src4 = reinterpret_cast<const float4*>(src);
+		for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(s)[i] = __ldg(src4 + i);
+		for (int i = (n4 << 2) + threadIdx.x; i < n; i += 256) s[i] = __ldg(src + i);
+	} else {
+		for (int i = threadIdx.x; i < n; i += 256) s[i] = __ldg(src + i);
+	}
+}
+
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 pos, float3 campos, unsigned& clamped)
+{
+	float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
+	float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+	dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
+	float res[3];
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) res[ch] = kSH_C0 * sh[ch];
+	if (deg > 0) {
+		const float x = dir.x, y = dir.y, z = dir.z;
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++)
+			res[ch] = res[ch] - kSH_C1 * y * sh[3 + ch] + kSH_C1 * z * sh[6 + ch] - kSH_C1 * x * sh[9 + ch];
+		if (deg > 1) {
+			const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++)
+				res[ch] = res[ch] + kSH_C2[0] * xy * sh[12 + ch] + kSH_C2[1] * yz * sh[15 + ch] +
+				          kSH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + ch] + kSH_C2[3] * xz * sh[21 + ch] +
+				          kSH_C2[4] * (xx - yy) * sh[24 + ch];
+			if (deg > 2) {
+#pragma unroll
+				for (int ch = 0; ch < 3; ch++)
+					res[ch] = res[ch] + kSH_C3[0] * y * (3.0f * xx - yy) * sh[27 + ch] + kSH_C3[1] * xy * z * sh[30 + ch] +
+					          kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
+					          kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
+					          kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + ch] + kSH_C3[5] * z * (xx - yy) * sh[42 + ch] +
+					          kSH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + ch];
+			}
+		}
+	}
+	clamped = 0;
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) {
+		res[ch] += 0.5f;
+		if (res[ch] < 0.0f) clamped |= 1u << ch;
+		res[ch] = fmaxf(res[ch], 0.0f);
+	}
+	return make_float3(res[0], res[1], res[2]);
+}
+
+__global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomView g, int* __restrict__ radii,
+                                                                 int* __restrict__ n_touched, int vec_mask)
+{
+	__shared__ __align__(16) float s_mean[768];
+	__shared__ __align__(16) float s_scale[768];
+	__shared__ __align__(16) float s_col[768];
+	__shared__ float s_view[16], s_proj[16];
+	__shared__ unsigned s_red[16];
+
+	const int row0 = blockIdx.x * 256;
+	const int idx = row0 + threadIdx.x;
+	if (threadIdx.x < 16) {
+		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
+		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
+	}
+	load_rows3(s.means3D, row0, s.P, s_mean, vec_mask & 1);
+	if (s.scales) load_rows3(s.scales, row0, s.P, s_scale, vec_mask & 2);
+	const bool dc_only = (s.colors_precomp != nullptr) || (s.M == 1);
+	if (dc_only) load_rows3(s.colors_precomp ? s.colors_precomp : s.shs, row0, s.P, s_col, vec_mask & 4);
+	__syncthreads();
+
+	unsigned my_tiles = 0, my_vis = 0;
+	if (idx < s.P) {
+		int out_radius = 0;
+		uint32_t key = 0x7F800000u;
+		GaussRec rec;
+		rec.q0 = make_float4(0.f, 0.f, 0.f, 0.f); rec.q1 = rec.q0; rec.q2 = rec.q0;
+		unsigned clamped = 0;
+		const float3 p_orig = {s_mean[3 * threadIdx.x], s_mean[3 * threadIdx.x + 1], s_mean[3 * threadIdx.x + 2]};
+		const float* vm = s_view;
+		const float* pm = s_proj;
+		// transformPoint4x4 / 4x3 (auxiliary.h:58-77)
+		const float hx = pm[0] * p_orig.x + pm[4] * p_orig.y + pm[8] * p_orig.z + pm[12];
+		const float hy = pm[1] * p_orig.x + pm[5] * p_orig.y + pm[9] * p_orig.z + pm[13];
+		const float hw = pm[3] * p_orig.x + pm[7] * p_orig.y + pm[11] * p_orig.z + pm[15];
+		const float p_w = 1.0f / (hw + 0.0000001f);
+		const float projx = hx * p_w, projy = hy * p_w;
+		float3 t;
+		t.x = vm[0] * p_orig.x + vm[4] * p_orig.y + vm[8] * p_orig.z + vm[12];
+		t.y = vm[1] * p_orig.x + vm[5] * p_orig.y + vm[9] * p_orig.z + vm[13];
+		t.z = vm[2] * p_orig.x + vm[6] * p_orig.y + vm[10] * p_orig.z + vm[14];
+		const float depth = t.z;
+		if (!(depth <= 0.2f)) {   // near-plane cull only (auxiliary.h:154)
+			float cov3D[6];
+			if (s.cov3D_precomp) {
+#pragma unroll
+				for (int i = 0; i < 6; i++) cov3D[i] = __ldg(s.cov3D_precomp + (size_t)idx * 6 + i);
+			} else {
+				// computeCov3D (forward.cu:120-154): quaternion used un-normalised
+				const float mod = s.scale_modifier;
+				M3 S;
+#pragma unroll
+				for (int c = 0; c < 3; c++)
+#pragma unroll
+					for (int r = 0; r < 3; r++) S.m[c][r] = (c == r) ? 1.0f : 0.0f;
+				S.m[0][0] = mod * s_scale[3 * threadIdx.x];
+				S.m[1][1] = mod * s_scale[3 * threadIdx.x + 1];
+				S.m[2][2] = mod * s_scale[3 * threadIdx.x + 2];
+				const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
+				const float r = q.x, x = q.y, y = q.z, z = q.w;
+				M3 R;
+				R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+				R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+				R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+				const M3 Mm = m3_mul(S, R);
+				const M3 Sigma = m3_mul(m3_transpose(Mm), Mm);
+				cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
+				cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
+			}
+			// computeCov2D (forward.cu:76-115)
+			const float limx = 1.3f * s.tan_fovx;
+			const float limy = 1.3f * s.tan_fovy;
+			const float txtz = t.x / t.z;
+			const float tytz = t.y / t.z;
+			t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+			t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+			M3 J;
+			J.m[0][0] = s.focal_x / t.z; J.m[0][1] = 0.0f; J.m[0][2] = -(s.focal_x * t.x) / (t.z * t.z);
+			J.m[1][0] = 0.0f; J.m[1][1] = s.focal_y / t.z; J.m[1][2] = -(s.focal_y * t.y) / (t.z * t.z);
+			J.m[2][0] = 0.0f; J.m[2][1] = 0.0f; J.m[2][2] = 0.0f;
+			M3 Wm;
+			Wm.m[0][0] = vm[0]; Wm.m[0][1] = vm[4]; Wm.m[0][2] = vm[8];
+			Wm.m[1][0] = vm[1]; Wm.m[1][1] = vm[5]; Wm.m[1][2] = vm[9];
+			Wm.m[2][0] = vm[2]; Wm.m[2][1] = vm[6]; Wm.m[2][2] = vm[10];
+			const M3 T = m3_mul(Wm, J);
+			M3 Vrk;
+			Vrk.m[0][0] = cov3D[0]; Vrk.m[0][1] = cov3D[1]; Vrk.m[0][2] = cov3D[2];
+			Vrk.m[1][0] = cov3D[1]; Vrk.m[1][1] = cov3D[3]; Vrk.m[1][2] = cov3D[4];
+			Vrk.m[2][0] = cov3D[2]; Vrk.m[2][1] = cov3D[4]; Vrk.m[2][2] = cov3D[5];
+			M3 cov = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+			cov.m[0][0] += 0.3f;
+			cov.m[1][1] += 0.3f;
+			const float cx = cov.m[0][0], cy = cov.m[0][1], cz = cov.m[1][1];
+			const float det = (cx * cz - cy * cy);
+			if (det != 0.0f) {
+				const float det_inv = 1.f / det;
+				const float3 conic = {cz * det_inv, -cy * det_inv, cx * det_inv};
+				const float mid = 0.5f * (cx + cz);
+				const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+				const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+				const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+				// ndc2Pix in double (auxiliary.h:41-44)
+				const float pix_x = ((projx + 1.0) * s.W - 1.0) * 0.5;
+				const float pix_y = ((projy + 1.0) * s.H - 1.0) * 0.5;
+				// getRect (auxiliary.h:46-56), int max_radius
+				const int mr = (int)my_radius;
+				const unsigned gx = (unsigned)s.grid_x, gy = (unsigned)s.grid_y;
+				const unsigned rminx = min(gx, (unsigned)max((int)0, (int)((pix_x - mr) / GSR_TILE)));
+				const unsigned rminy = min(gy, (unsigned)max((int)0, (int)((pix_y - mr) / GSR_TILE)));
+				const unsigned rmaxx = min(gx, (unsigned)max((int)0, (int)((pix_x + mr + GSR_TILE - 1) / GSR_TILE)));
+				const unsigned rmaxy = min(gy, (unsigned)max((int)0, (int)((pix_y + mr + GSR_TILE - 1) / GSR_TILE)));
+				const unsigned area = (rmaxx - rminx) * (rmaxy - rminy);
+				if (area != 0) {
+					float3 rgb;
+					if (s.colors_precomp) {
+						rgb = make_float3(s_col[3 * threadIdx.x], s_col[3 * threadIdx.x + 1], s_col[3 * threadIdx.x + 2]);
+					} else if (s.M == 1) {
+						const float3 campos = {__ldg(s.campos), __ldg(s.campos + 1), __ldg(s.campos + 2)};
+						rgb = sh_to_rgb(s.D, &s_col[3 * threadIdx.x], p_orig, campos, clamped);
+					} else {
+						const float3 campos = {__ldg(s.campos), __ldg(s.campos + 1), __ldg(s.campos + 2)};
+						rgb = sh_to_rgb(s.D, s.shs + (size_t)idx * s.M * 3, p_orig, campos, clamped);
+					}
+					out_radius = mr;
+					my_tiles = area;
+					my_vis = 1;
+					key = __float_as_uint(depth);
+					rec.q0 = make_float4(pix_x, pix_y, conic.x, conic.y);
+					rec.q1 = make_float4(conic.z, __ldg(s.opacities + idx), depth, rgb.x);
+					rec.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(rminx | (rminy << 16)),
+					                     __uint_as_float(rmaxx | (rmaxy << 16)));
+				}
+			}
+		} else if (s.prefiltered) {
+			__trap();   // auxiliary.h:156-160
+		}
+		radii[idx] = out_radius;
+		if (n_touched) n_touched[idx] = 0;
+		g.rec[idx] = rec;
+		GaussAcc z;
+		z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0;
+		g.acc[idx] = z;
+		g.tiles_touched[idx] = my_tiles;
+		g.depth_key[idx] = key;
+		g.clamped[idx] = (uint8_t)clamped;
+	}
+	// block totals -> header (integer atomics: deterministic)
+	unsigned wt = my_tiles, wv = my_vis;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		wt += __shfl_xor_sync(0xffffffffu, wt, o);
+		wv += __shfl_xor_sync(0xffffffffu, wv, o);
+	}
+	if (lane_id() == 0) { s_red[threadIdx.x >> 5] = wt; s_red[8 + (threadIdx.x >> 5)] = wv; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned a = 0, b = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) { a += s_red[w]; b += s_red[8 + w]; }
+		if (a) atomicAdd(&g.hdr->num_rendered, a);
+		if (b) atomicAdd(&g.hdr->num_visible, b);
+	}
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ vm,
+                                    unsigned char* __restrict__ present)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	const float x = means[3 * idx], y = means[3 * idx + 1], z = means[3 * idx + 2];
+	const float pz = vm[2] * x + vm[6] * y + vm[10] * z + vm[14];
+	present[idx] = !(pz <= 0.2f);
+}
+
+}  // namespace
+
+static inline bool aligned16(const void* p) { return ((size_t)p & 15) == 0; }
+
+void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream)
+{
+	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), stream);
+	if (s.P == 0) return;
+	int vec_mask = (aligned16(s.means3D) ? 1 : 0) | (aligned16(s.scales) ? 2 : 0) |
+	               (aligned16(s.colors_precomp ? s.colors_precomp : s.shs) ? 4 : 0);
+	preprocess_forward_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, g, radii, n_touched, vec_mask);
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present, cudaStream_t stream)
+{
+	if (P == 0) return;
+	mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+}
+
+}  // namespace gsr

@@ -1,0 +1,370 @@
+// Fused per-Gaussian backward: conic -> cov2D -> (cov3D, mean, pose), NDC mean -> (mean, pose),
+// depth -> (mean, pose), SH -> (coefficients, mean, pose), cov3D -> (scale, rotation), plus the
+// analytic SE(3) pose gradient dL/dtau of the GS-SLAM paper reduced to ONE 6-vector per view.
+// Replaces reference computeCov2DCUDA (cuda_rasterizer/backward.cu:150-345), preprocessCUDA
+// (:494-624), computeColorFromSH (:21-145), computeCov3D (:426-489) and the torch.sum over the
+// [P,6] buffer (diff_gaussian_rasterization/__init__.py:162-164): two kernels + eleven zero-filled
+// tensors + a reduction there, one kernel and no memset here.  Every output row is written
+// (zeros for culled Gaussians), so the caller allocates with torch.empty.
+// dL/dtau: warp shuffle -> shared memory -> one partial per CTA -> the last CTA to finish sums the
+// partials in index order, so the result is deterministic (the reference's is not needed to be:
+// it sums a [P,6] tensor).
+#include "gsr_params.h"
+
+namespace gsr {
+
+namespace {
+
+__device__ const float bSH_C0 = 0.28209479177387814f;
+__device__ const float bSH_C1 = 0.4886025119029199f;
+__device__ const float bSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float bSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                   -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+// SH backward for one Gaussian (backward.cu:21-145).  dRGB already masked by the clamp flags.
+// Writes dL_dsh[0..M) (zeros above the active degree), returns dL/dmean through the view direction.
+__device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __restrict__ sh, float3 pos, float3 campos,
+                                              const float dRGB[3], float* __restrict__ dL_dsh)
+{
+	const float3 dir_o = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
+	const float len = sqrtf(dir_o.x * dir_o.x + dir_o.y * dir_o.y + dir_o.z * dir_o.z);
+	const float x = dir_o.x / len, y = dir_o.y / len, z = dir_o.z / len;
+	float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+	float w[16];
+	w[0] = bSH_C0;
+	int ncoef = 1;
+	float xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
+	if (deg > 0) {
+		w[1] = -bSH_C1 * y; w[2] = bSH_C1 * z; w[3] = -bSH_C1 * x;
+		ncoef = 4;
+		if (deg > 1) {
+			xx = x * x; yy = y * y; zz = z * z; xy = x * y; yz = y * z; xz = x * z;
+			w[4] = bSH_C2[0] * xy; w[5] = bSH_C2[1] * yz; w[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+			w[7] = bSH_C2[3] * xz; w[8] = bSH_C2[4] * (xx - yy);
+			ncoef = 9;
+			if (deg > 2) {
+				w[9] = bSH_C3[0] * y * (3.f * xx - yy); w[10] = bSH_C3[1] * xy * z;
+				w[11] = bSH_C3[2] * y * (4.f * zz - xx - yy); w[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+				w[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); w[14] = bSH_C3[5] * z * (xx - yy);
+				w[15] = bSH_C3[6] * x * (xx - 3.f * yy);
+				ncoef = 16;
+			}
+		}
+	}
+	for (int i = 0; i < M; i++) {
+		const float wi = i < ncoef ? w[i] : 0.f;
+		dL_dsh[3 * i + 0] = wi * dRGB[0];
+		dL_dsh[3 * i + 1] = wi * dRGB[1];
+		dL_dsh[3 * i + 2] = wi * dRGB[2];
+	}
+	if (deg > 0) {
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) {
+#define SHC(i) sh[3 * (i) + ch]
+			float dx = -bSH_C1 * SHC(3), dy = -bSH_C1 * SHC(1), dz = bSH_C1 * SHC(2);
+			if (deg > 1) {
+				dx += bSH_C2[0] * y * SHC(4) + bSH_C2[2] * 2.f * -x * SHC(6) + bSH_C2[3] * z * SHC(7) + bSH_C2[4] * 2.f * x * SHC(8);
+				dy += bSH_C2[0] * x * SHC(4) + bSH_C2[1] * z * SHC(5) + bSH_C2[2] * 2.f * -y * SHC(6) + bSH_C2[4] * 2.f * -y * SHC(8);
+				dz += bSH_C2[1] * y * SHC(5) + bSH_C2[2] * 2.f * 2.f * z * SHC(6) + bSH_C2[3] * x * SHC(7);
+				if (deg > 2) {
+					dx += bSH_C3[0] * SHC(9) * 3.f * 2.f * xy + bSH_C3[1] * SHC(10) * yz + bSH_C3[2] * SHC(11) * -2.f * xy +
+					      bSH_C3[3] * SHC(12) * -3.f * 2.f * xz + bSH_C3[4] * SHC(13) * (-3.f * xx + 4.f * zz - yy) +
+					      bSH_C3[5] * SHC(14) * 2.f * xz + bSH_C3[6] * SHC(15) * 3.f * (xx - yy);
+					dy += bSH_C3[0] * SHC(9) * 3.f * (xx - yy) + bSH_C3[1] * SHC(10) * xz +
+					      bSH_C3[2] * SHC(11) * (-3.f * yy + 4.f * zz - xx) + bSH_C3[3] * SHC(12) * -3.f * 2.f * yz +
+					      bSH_C3[4] * SHC(13) * -2.f * xy + bSH_C3[5] * SHC(14) * -2.f * yz + bSH_C3[6] * SHC(15) * -3.f * 2.f * xy;
+					dz += bSH_C3[1] * SHC(10) * xy + bSH_C3[2] * SHC(11) * 4.f * 2.f * yz +
+					      bSH_C3[3] * SHC(12) * 3.f * (2.f * zz - xx - yy) + bSH_C3[4] * SHC(13) * 4.f * 2.f * xz +
+					      bSH_C3[5] * SHC(14) * (xx - yy);
+				}
+			}
+#undef SHC
+			ddx += dx * dRGB[ch]; ddy += dy * dRGB[ch]; ddz += dz * dRGB[ch];
+		}
+	}
+	// dnormvdv (auxiliary.h:107-117)
+	const float sum2 = dir_o.x * dir_o.x + dir_o.y * dir_o.y + dir_o.z * dir_o.z;
+	const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+	float3 dm;
+	dm.x = ((+sum2 - dir_o.x * dir_o.x) * ddx - dir_o.y * dir_o.x * ddy - dir_o.z * dir_o.x * ddz) * inv32;
+	dm.y = (-dir_o.x * dir_o.y * ddx + (sum2 - dir_o.y * dir_o.y) * ddy - dir_o.z * dir_o.y * ddz) * inv32;
+	dm.z = (-dir_o.x * dir_o.z * ddx - dir_o.y * dir_o.z * ddy + (sum2 - dir_o.z * dir_o.z) * ddz) * inv32;
+	return dm;
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, float* __restrict__ dL_dmeans3D,
+                           float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
+                           float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
+                           float* __restrict__ dL_dcov3D_out, float* __restrict__ dL_dtau)
+{
+	__shared__ float s_view[16], s_proj[16], s_raw[16];
+	__shared__ float s_tau[8][6];
+	__shared__ bool s_last;
+	if (threadIdx.x < 16) {
+		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
+		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
+		s_raw[threadIdx.x] = s.projmatrix_raw[threadIdx.x];
+	}
+	__syncthreads();
+	const float* vm = s_view;
+	const float* pj = s_proj;
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	float tau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+	if (idx < s.P) {
+		float dmean[3] = {0.f, 0.f, 0.f};
+		float dm2x = 0.f, dm2y = 0.f, dopac = 0.f;
+		float dcol[3] = {0.f, 0.f, 0.f};
+		float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+		float dscale[3] = {0.f, 0.f, 0.f};
+		float drot[4] = {0.f, 0.f, 0.f, 0.f};
+		const bool visible = radii[idx] > 0;
+		if (visible) {
+			const GaussAcc a = g.acc[idx];
+			GaussAcc z;
+			z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0;
+			g.acc[idx] = z;   // consumed: ready for the next backward without a memset
+			dm2x = a.a0.x; dm2y = a.a0.y;
+			const float dcx = a.a0.z, dcy = a.a0.w, dcz = a.a1.x;
+			dopac = a.a1.y;
+			const float ddepth = a.a1.z;
+			dcol[0] = a.a1.w; dcol[1] = a.a2.x; dcol[2] = a.a2.y;
+
+			const float mx = s.means3D[3 * idx], my = s.means3D[3 * idx + 1], mz = s.means3D[3 * idx + 2];
+			// ---- 3D covariance (recomputed; reference re-reads geomState.cov3D) ----
+			float c3[6];
+			float sc[3] = {0.f, 0.f, 0.f};
+			float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+			float Rq[3][3];
+			if (s.cov3D_precomp) {
+#pragma unroll
+				for (int i = 0; i < 6; i++) c3[i] = s.cov3D_precomp[(size_t)idx * 6 + i];
+			} else {
+				q = reinterpret_cast<const float4*>(s.rotations)[idx];
+				const float r = q.x, x = q.y, y = q.z, zq = q.w;
+				Rq[0][0] = 1.f - 2.f * (y * y + zq * zq); Rq[0][1] = 2.f * (x * y - r * zq); Rq[0][2] = 2.f * (x * zq + r * y);
+				Rq[1][0] = 2.f * (x * y + r * zq); Rq[1][1] = 1.f - 2.f * (x * x + zq * zq); Rq[1][2] = 2.f * (y * zq - r * x);
+				Rq[2][0] = 2.f * (x * zq - r * y); Rq[2][1] = 2.f * (y * zq + r * x); Rq[2][2] = 1.f - 2.f * (x * x + y * y);
+#pragma unroll
+				for (int i = 0; i < 3; i++) sc[i] = s.scale_modifier * s.scales[3 * idx + i];
+				float Sg[3][3];
+#pragma unroll
+				for (int aa = 0; aa < 3; aa++)
+#pragma unroll
+					for (int bb = 0; bb < 3; bb++) {
+						float accv = 0.f;
+#pragma unroll
+						for (int i = 0; i < 3; i++) accv += (sc[i] * Rq[aa][i]) * (sc[i] * Rq[bb][i]);
+						Sg[aa][bb] = accv;
+					}
+				c3[0] = Sg[0][0]; c3[1] = Sg[0][1]; c3[2] = Sg[0][2]; c3[3] = Sg[1][1]; c3[4] = Sg[1][2]; c3[5] = Sg[2][2];
+			}
+			// ---- cov2D forward recompute (backward.cu:171-206) ----
+			float t[3];
+#pragma unroll
+			for (int r = 0; r < 3; r++) t[r] = vm[r] * mx + vm[4 + r] * my + vm[8 + r] * mz + vm[12 + r];
+			const float pCx = t[0], pCy = t[1];   // unclamped camera-space mean
+			const float limx = 1.3f * s.tan_fovx, limy = 1.3f * s.tan_fovy;
+			const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+			t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+			t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+			const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+			const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+			const float hx = s.focal_x, hy = s.focal_y;
+			const float J00 = hx / t[2], J11 = hy / t[2];
+			const float J02 = -(hx * t[0]) / (t[2] * t[2]), J12 = -(hy * t[1]) / (t[2] * t[2]);
+			float A0[3], A1[3];   // rows of J * R_cw
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				A0[k] = J00 * vm[4 * k + 0] + J02 * vm[4 * k + 2];
+				A1[k] = J11 * vm[4 * k + 1] + J12 * vm[4 * k + 2];
+			}
+			const float V[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+			float VA0[3], VA1[3];
+#pragma unroll
+			for (int i = 0; i < 3; i++) {
+				VA0[i] = V[i][0] * A0[0] + V[i][1] * A0[1] + V[i][2] * A0[2];
+				VA1[i] = V[i][0] * A1[0] + V[i][1] * A1[1] + V[i][2] * A1[2];
+			}
+			const float ca = A0[0] * VA0[0] + A0[1] * VA0[1] + A0[2] * VA0[2] + 0.3f;
+			const float cb = A0[0] * VA1[0] + A0[1] * VA1[1] + A0[2] * VA1[2];
+			const float cc = A1[0] * VA1[0] + A1[1] * VA1[1] + A1[2] * VA1[2] + 0.3f;
+			const float denom = ca * cc - cb * cb;
+			float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+			const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+			if (denom2inv != 0.f) {
+				dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+				dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+				dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+				dcov[0] = A0[0] * A0[0] * dL_da + A0[0] * A1[0] * dL_db + A1[0] * A1[0] * dL_dc;
+				dcov[3] = A0[1] * A0[1] * dL_da + A0[1] * A1[1] * dL_db + A1[1] * A1[1] * dL_dc;
+				dcov[5] = A0[2] * A0[2] * dL_da + A0[2] * A1[2] * dL_db + A1[2] * A1[2] * dL_dc;
+				dcov[1] = 2 * A0[0] * A0[1] * dL_da + (A0[0] * A1[1] + A0[1] * A1[0]) * dL_db + 2 * A1[0] * A1[1] * dL_dc;
+				dcov[2] = 2 * A0[0] * A0[2] * dL_da + (A0[0] * A1[2] + A0[2] * A1[0]) * dL_db + 2 * A1[0] * A1[2] * dL_dc;
+				dcov[4] = 2 * A0[2] * A0[1] * dL_da + (A0[1] * A1[2] + A0[2] * A1[1]) * dL_db + 2 * A1[1] * A1[2] * dL_dc;
+			}
+			float dT0[3], dT1[3];
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				dT0[k] = 2 * VA0[k] * dL_da + VA1[k] * dL_db;
+				dT1[k] = 2 * VA1[k] * dL_dc + VA0[k] * dL_db;
+			}
+			float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				dJ00 += vm[4 * j + 0] * dT0[j];
+				dJ02 += vm[4 * j + 2] * dT0[j];
+				dJ11 += vm[4 * j + 1] * dT1[j];
+				dJ12 += vm[4 * j + 2] * dT1[j];
+			}
+			const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+			const float gx = x_grad_mul * -hx * tz2 * dJ02;
+			const float gy = y_grad_mul * -hy * tz2 * dJ12;
+			const float gz = -hx * tz2 * dJ00 - hy * tz2 * dJ11 + (2 * hx * t[0]) * tz3 * dJ02 + (2 * hy * t[1]) * tz3 * dJ12;
+			// pose through t: [I | -t^x] with the clamped t (backward.cu:275-290)
+			tau[0] += gx; tau[1] += gy; tau[2] += gz;
+			tau[3] += t[1] * gz - t[2] * gy;
+			tau[4] += t[2] * gx - t[0] * gz;
+			tau[5] += t[0] * gy - t[1] * gx;
+			// mean through t (assignment in the reference, :299)
+#pragma unroll
+			for (int c = 0; c < 3; c++) dmean[c] = vm[4 * c + 0] * gx + vm[4 * c + 1] * gy + vm[4 * c + 2] * gz;
+			// pose through W: dtheta = sum_k R[:,k] x dL/dR[:,k]  (backward.cu:301-345)
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				const float dW0 = J00 * dT0[k], dW1 = J11 * dT1[k], dW2 = J02 * dT0[k] + J12 * dT1[k];
+				const float c0 = vm[4 * k + 0], c1 = vm[4 * k + 1], c2 = vm[4 * k + 2];
+				tau[3] += c1 * dW2 - c2 * dW1;
+				tau[4] += c2 * dW0 - c0 * dW2;
+				tau[5] += c0 * dW1 - c1 * dW0;
+			}
+			// ---- NDC mean (backward.cu:522-597) ----
+			const float mhx = pj[0] * mx + pj[4] * my + pj[8] * mz + pj[12];
+			const float mhy = pj[1] * mx + pj[5] * my + pj[9] * mz + pj[13];
+			const float mhw = pj[3] * mx + pj[7] * my + pj[11] * mz + pj[15];
+			const float m_w = 1.0f / (mhw + 0.0000001f);
+			const float mul1 = mhx * m_w * m_w, mul2 = mhy * m_w * m_w;
+#pragma unroll
+			for (int k = 0; k < 3; k++)
+				dmean[k] += (pj[4 * k] * m_w - pj[4 * k + 3] * mul1) * dm2x + (pj[4 * k + 1] * m_w - pj[4 * k + 3] * mul2) * dm2y;
+			{
+				const float al = m_w, be = -mhx * m_w * m_w, ga = -mhy * m_w * m_w;
+				const float pa = s_raw[0], pb = s_raw[5], pe = s_raw[11];
+				const float pC[3] = {pCx, pCy, t[2]};
+				const float v1[3] = {al * pa, 0.f, be * pe}, v2[3] = {0.f, al * pb, ga * pe};
+				const float c1[3] = {pC[1] * v1[2] - pC[2] * v1[1], pC[2] * v1[0] - pC[0] * v1[2], pC[0] * v1[1] - pC[1] * v1[0]};
+				const float c2[3] = {pC[1] * v2[2] - pC[2] * v2[1], pC[2] * v2[0] - pC[0] * v2[2], pC[0] * v2[1] - pC[1] * v2[0]};
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+					tau[i] += dm2x * v1[i] + dm2y * v2[i];
+					tau[3 + i] += dm2x * c1[i] + dm2y * c2[i];
+				}
+				// ---- depth (backward.cu:603-613) ----
+				dmean[0] += ddepth * vm[2]; dmean[1] += ddepth * vm[6]; dmean[2] += ddepth * vm[10];
+				tau[2] += ddepth;
+				tau[3] += ddepth * pC[1];
+				tau[4] += ddepth * -pC[0];
+			}
+			// ---- SH (backward.cu:618-619) ----
+			if (s.shs) {
+				const unsigned cl = g.clamped[idx];
+				const float dRGB[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
+				const float3 campos = {s.campos[0], s.campos[1], s.campos[2]};
+				const float3 dm = sh_backward(s.D, s.M, s.shs + (size_t)idx * s.M * 3, make_float3(mx, my, mz), campos, dRGB,
+				                              dL_dsh + (size_t)idx * s.M * 3);
+				dmean[0] += dm.x; dmean[1] += dm.y; dmean[2] += dm.z;
+				tau[0] += -dm.x; tau[1] += -dm.y; tau[2] += -dm.z;
+			}
+			// ---- cov3D -> scale / rotation (backward.cu:426-489) ----
+			if (s.scales) {
+				float Mm[3][3];   // M = S * Rq^T
+#pragma unroll
+				for (int i = 0; i < 3; i++)
+#pragma unroll
+					for (int j = 0; j < 3; j++) Mm[i][j] = sc[i] * Rq[j][i];
+				const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+				                        {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+				                        {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+				float Gm[3][3];
+#pragma unroll
+				for (int i = 0; i < 3; i++) {
+					float dM[3];
+#pragma unroll
+					for (int j = 0; j < 3; j++) dM[j] = 2.0f * (Mm[i][0] * dS[0][j] + Mm[i][1] * dS[1][j] + Mm[i][2] * dS[2][j]);
+					dscale[i] = Rq[0][i] * dM[0] + Rq[1][i] * dM[1] + Rq[2][i] * dM[2];
+#pragma unroll
+					for (int j = 0; j < 3; j++) Gm[i][j] = sc[i] * dM[j];
+				}
+				const float r = q.x, x = q.y, y = q.z, zq = q.w;
+				drot[0] = 2 * zq * (Gm[0][1] - Gm[1][0]) + 2 * y * (Gm[2][0] - Gm[0][2]) + 2 * x * (Gm[1][2] - Gm[2][1]);
+				drot[1] = 2 * y * (Gm[1][0] + Gm[0][1]) + 2 * zq * (Gm[2][0] + Gm[0][2]) + 2 * r * (Gm[1][2] - Gm[2][1]) - 4 * x * (Gm[2][2] + Gm[1][1]);
+				drot[2] = 2 * x * (Gm[1][0] + Gm[0][1]) + 2 * r * (Gm[2][0] - Gm[0][2]) + 2 * zq * (Gm[1][2] + Gm[2][1]) - 4 * y * (Gm[2][2] + Gm[0][0]);
+				drot[3] = 2 * r * (Gm[0][1] - Gm[1][0]) + 2 * x * (Gm[2][0] + Gm[0][2]) + 2 * y * (Gm[1][2] + Gm[2][1]) - 4 * zq * (Gm[1][1] + Gm[0][0]);
+			}
+		} else if (s.shs) {
+			for (int i = 0; i < s.M * 3; i++) dL_dsh[(size_t)idx * s.M * 3 + i] = 0.f;
+		}
+		dL_dmeans3D[3 * idx] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
+		dL_dmeans2D[3 * idx] = dm2x; dL_dmeans2D[3 * idx + 1] = dm2y; dL_dmeans2D[3 * idx + 2] = 0.f;
+		dL_dopacity[idx] = dopac;
+		if (dL_dcolors) { dL_dcolors[3 * idx] = dcol[0]; dL_dcolors[3 * idx + 1] = dcol[1]; dL_dcolors[3 * idx + 2] = dcol[2]; }
+		if (s.scales) {
+			dL_dscales[3 * idx] = dscale[0]; dL_dscales[3 * idx + 1] = dscale[1]; dL_dscales[3 * idx + 2] = dscale[2];
+			reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+		}
+		if (dL_dcov3D_out) {
+#pragma unroll
+			for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] = dcov[i];
+		}
+	}
+
+	// ---- block-level 6-vector reduction of the pose gradient ----
+#pragma unroll
+	for (int i = 0; i < 6; i++) tau[i] = warp_sum(tau[i]);
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int i = 0; i < 6; i++) s_tau[threadIdx.x >> 5][i] = tau[i];
+	}
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		float v = 0.f;
+#pragma unroll
+		for (int w = 0; w < 8; w++) v += s_tau[w][threadIdx.x];
+		g.tau_partial[(size_t)blockIdx.x * 8 + threadIdx.x] = v;
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(&g.hdr->bwd_blocks_done, 1u) == gridDim.x - 1);
+	__syncthreads();
+	if (s_last) {
+		__threadfence();
+		// deterministic final sum: 6 warps, one component each, fixed strided order + shuffle tree
+		const int comp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+		if (comp < 6) {
+			float v = 0.f;
+			for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&g.tau_partial[(size_t)b * 8 + comp]);
+			v = warp_sum(v);
+			if (lane == 0) dL_dtau[comp] = v;
+		}
+		if (threadIdx.x == 0) g.hdr->bwd_blocks_done = 0;
+	}
+}
+
+}  // namespace
+
+void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,
+                                float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
+                                float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dtau,
+                                cudaStream_t stream)
+{
+	if (s.P == 0) {
+		cudaMemsetAsync(dL_dtau, 0, 6 * sizeof(float), stream);
+		return;
+	}
+	preprocess_backward_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
+	                                                                  dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dtau);
+}
+
+}  // namespace gsr

@@ -1,0 +1,131 @@
+/*
+ * gsr_b200 -- C-ABI of the B200-native differentiable Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary for the hot path of notu97/GS-SLAM-Analytica_Jacobian: these entry points are
+ * what the reference's native binding for this path exports through pybind
+ * (submodules/diff-gaussian-rasterization/ext.cpp:15-19):
+ *
+ *   reference `rasterize_gaussians`           rasterize_points.h:18-39,  rasterize_points.cu:35-137
+ *       -> gsr_rasterize_gaussians            (one call, same outputs, same "returns num_rendered")
+ *          = gsr_forward_plan + gsr_forward_num_rendered + gsr_forward_render  (split so a caller
+ *            can skip the reference's blocking D2H read of num_rendered, rasterizer_impl.cu:331)
+ *   reference `rasterize_gaussians_backward`  rasterize_points.h:41-65,  rasterize_points.cu:139-226
+ *       -> gsr_rasterize_gaussians_backward
+ *   reference `mark_visible`                  rasterize_points.h:67-70,  rasterize_points.cu:228-247
+ *       -> gsr_mark_visible
+ *   reference scratch growth through std::function<char*(size_t)> resize callbacks
+ *       (rasterize_points.cu:27-33, rasterizer_impl.cu:275-276,288-289,333-334)
+ *       -> gsr_geometry_bytes / gsr_image_bytes / gsr_binning_bytes size queries + caller-owned
+ *          buffers, and a gsr_alloc_fn callback for the one size that is data dependent.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless it is
+ * named *_host.  All arrays are fp32, contiguous, laid out as the reference documents them
+ * (means3D[P,3], shs[P,M,3], opacities[P], scales[P,3], rotations[P,4] (w,x,y,z),
+ * cov3D_precomp[P,6], 4x4 matrices as 16 floats column-major).  A null pointer selects the
+ * alternative path exactly like the reference's empty tensors (forward.cu:207,382).
+ * All work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream).  Functions return
+ * GSR_OK or a negative error code and never throw; gsr_error_string() explains the last failure
+ * of the calling thread.  The library holds no global mutable state besides that string.
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_OK 0
+#define GSR_ERR_ARG -1        /* inconsistent arguments (mirrors the Python-side exceptions / AT_ERROR) */
+#define GSR_ERR_CUDA -2       /* a CUDA call failed */
+#define GSR_ERR_WORKSPACE -3  /* a caller-provided workspace is too small */
+#define GSR_ERR_OVERFLOW -4   /* num_rendered exceeded the binning capacity (no-sync mode) */
+
+typedef struct gsr_scene {
+	int P;                       /* number of Gaussians */
+	int D;                       /* active SH degree                      (settings.sh_degree) */
+	int M;                       /* SH coefficients per Gaussian, 0 if shs is null */
+	int W, H;                    /* image_width, image_height */
+	const float* background;     /* [3] */
+	const float* means3D;        /* [P,3] */
+	const float* shs;            /* [P,M,3] or null */
+	const float* colors_precomp; /* [P,3]  or null  (exactly one of shs / colors_precomp) */
+	const float* opacities;      /* [P] */
+	const float* scales;         /* [P,3]  or null */
+	const float* rotations;      /* [P,4]  or null */
+	const float* cov3D_precomp;  /* [P,6]  or null  (exactly one of scales+rotations / cov3D_precomp) */
+	const float* viewmatrix;     /* [16] */
+	const float* projmatrix;     /* [16] */
+	const float* projmatrix_raw; /* [16] (only read by the backward) */
+	const float* campos;         /* [3] */
+	float scale_modifier;
+	float tan_fovx, tan_fovy;
+	int prefiltered;
+	int debug;                   /* synchronise + check after every stage (reference CHECK_CUDA) */
+} gsr_scene;
+
+/* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
+typedef void* (*gsr_alloc_fn)(void* user, size_t bytes);
+
+/* ---- workspace sizes (reference: required<GeometryState/ImageState/BinningState>) ---- */
+size_t gsr_geometry_bytes(int P);
+size_t gsr_image_bytes(int W, int H);
+size_t gsr_binning_bytes(int P, long long num_rendered_capacity);
+
+/* ---- forward ---- */
+/* Stage A: per-Gaussian preprocess (+ tile counts, depth keys).  Writes radii[P] and zero-fills
+ * n_touched[P]; leaves num_rendered in the geometry workspace on the device. */
+int gsr_forward_plan(const gsr_scene* s, void* geom, size_t geom_bytes, int* radii, int* n_touched, void* stream);
+/* Blocks until stage A is done and returns num_rendered (the reference's only host sync). */
+int gsr_forward_num_rendered(void* geom, void* stream, long long* num_rendered_host);
+/* Stage B: binning + compositing.  `num_rendered_host` >= 0: the exact count read with
+ * gsr_forward_num_rendered;  < 0: unknown -- the kernels read it from the device and the call needs no
+ * host synchronisation at all; gsr_forward_overflowed() must then be checked before results are used. */
+int gsr_forward_render(const gsr_scene* s, void* geom, void* binning, size_t binning_bytes,
+                       long long binning_capacity, long long num_rendered_host, void* image, size_t image_bytes,
+                       float* out_color /*[3,H,W]*/, float* out_depth /*[1,H,W]*/, float* out_opacity /*[1,H,W]*/,
+                       int* n_touched /*[P]*/, void* stream);
+/* Synchronises and reports whether the last no-sync forward ran out of binning capacity
+ * (*needed_host receives the required capacity). */
+int gsr_forward_overflowed(void* geom, void* stream, int* overflowed_host, long long* needed_host);
+
+/* One-call forward with the reference's semantics: allocates the binning workspace through
+ * `binning_alloc` once num_rendered is known, returns it in *num_rendered_host and the buffer in
+ * *binning_out (keep both for the backward). */
+int gsr_rasterize_gaussians(const gsr_scene* s, void* geom, size_t geom_bytes, void* image, size_t image_bytes,
+                            gsr_alloc_fn binning_alloc, void* alloc_user, void** binning_out,
+                            long long* num_rendered_host, float* out_color, float* out_depth, float* out_opacity,
+                            int* radii, int* n_touched, void* stream);
+
+/* ---- backward ---- */
+/* Consumes dL/dcolor[3,H,W] and dL/ddepth[1,H,W] only (the reference drops the gradient of the
+ * opacity image, __init__.py:114,139-140).  Every output row is written; outputs need no zero fill.
+ * Null outputs: dL_dsh when shs is null, dL_dcolors optional, dL_dscales/dL_drotations when scales is
+ * null, dL_dcov3D optional.  dL_dtau[6] = [rho(3), theta(3)], already summed over Gaussians
+ * (reference: torch.sum of a [P,6] buffer, __init__.py:162-164). */
+int gsr_rasterize_gaussians_backward(const gsr_scene* s, const int* radii, void* geom, void* binning,
+                                     long long binning_capacity, void* image, const float* dL_dout_color,
+                                     const float* dL_dout_depth, float* dL_dmeans3D /*[P,3]*/,
+                                     float* dL_dmeans2D /*[P,3]*/, float* dL_dsh /*[P,M,3]*/, float* dL_dcolors /*[P,3]*/,
+                                     float* dL_dopacity /*[P,1]*/, float* dL_dscales /*[P,3]*/,
+                                     float* dL_drotations /*[P,4]*/, float* dL_dcov3D /*[P,6]*/, float* dL_dtau /*[6]*/,
+                                     void* stream);
+
+/* ---- markVisible ---- */
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present /*[P] bool*/, void* stream);
+
+/* ---- introspection (tests / parity): device pointers into the workspaces of the last forward ---- */
+/* out[0]=records (48 B each: x,y,conic.xx,conic.xy | conic.yy,opacity,depth,r | g,b,rect_min,rect_max)
+ * out[1]=tiles_touched u32[P]  out[2]=clamped u8[P]  out[3]=point_list u32[R]  out[4]=ranges u32[2*tiles]
+ * out[5]=final_T f32[HW]  out[6]=n_contrib u32[HW]  out[7]=header (u32: num_rendered, overflow, num_visible) */
+int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long binning_capacity, void* image,
+                       unsigned long long* out);
+
+const char* gsr_error_string(void);
+int gsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */
