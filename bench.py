@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: "fwd+bwd raster iters/s incl. pose
+dL/dtau; % of HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C1_tum_tracking]
+
+A *step* is one tracking iteration of the C1 workload (TUM fr1/desk shape, 640x480,
+100 000 Gaussians, one view): forward rasterization + backward incl. dL/dtau at a pose that changes every
+step; the loss is excluded (dL/dpixel tensors are pre-generated, seed 1).  With N > 1 every rank runs its
+own independent pose stream on the same map (pose-parallel batched tracking, weak scaling, no data-path
+collective -- SURVEY.md §8(e)); value = total iterations of all ranks / max-over-ranks device time.
+
+  value     device-timed (CUDA events per step, L2 flushed between steps) with everything resident in HBM
+  e2e       same step driven from HOST buffers: pinned camera block + pinned dL/dpixel images are copied
+            H2D and dL/dtau + the forward header are copied D2H inside the timed region, host blocks on
+            every step (the next pose depends on dL/dtau)
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (oracle/gs_oracle.c, OpenMP) on one iteration of the same workload
+--impl reference: the reference's own implementation of the path on this box.  The reference path has no
+CPU implementation (it IS a CUDA extension), so this arm drives the UNMODIFIED reference kernels compiled
+for sm_100a (oracle/_ref/libgsref.so) on the GPU, including the zero-fills and the torch.sum its binding
+performs; if that library is absent it times the CPU oracle port instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "fwd+bwd raster iters/s incl. pose dL/dtau"
+UNIT = "iters/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(name, steps_total, rank, device):
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+
+    cfg = S.CONFIGS[name]
+    sc = S.make_scene(name, seed=0)
+    W, H = cfg["W"], cfg["H"]
+    # pose perturbed every iteration: Exp(noise) * base, seeded per rank (pose seed 2)
+    poses = S.noisy_poses(steps_total, sigma_rho=0.01, sigma_theta=np.radians(0.5), seed=2 + 1000 * rank)
+    cams = []
+    for w2c in poses:
+        cam = S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c)
+        blk = np.zeros(52, np.float32)
+        blk[0:16] = cam["viewmatrix"].reshape(-1)
+        blk[16:32] = cam["projmatrix"].reshape(-1)
+        blk[32:48] = cam["projmatrix_raw"].reshape(-1)
+        blk[48:51] = cam["campos"]
+        cams.append(blk)
+    cams = np.stack(cams)
+    dc, dd = S.make_pixel_grads(W, H, seed=1)
+    return cfg, sc, cams, dc, dd
+
+
+def l2_flusher(device):
+    buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def flush():
+        buf.fill_(1)
+    return flush
+
+
+def roofline_bytes(P, R, HW):
+    """Algorithmic bytes per stage (SH degree 0)."""
+    return {
+        "preprocess": (56 + 8 + 44) * P,
+        "binning": 44 * R,
+        "render_forward": 44 * R + 28 * HW,
+        "render_backward": (44 + 40) * R + 24 * HW + 40 * P,
+        "preprocess_backward": (60 + 40 + 68) * P,
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_oracle_iters_per_s(sc, dc, dd, max_seconds=30.0):
+    from oracle.gs_oracle import Oracle
+
+    o = Oracle(np.float32)
+    o.forward(dict(sc, means3D=sc["means3D"][:2000], scales=sc["scales"][:2000], rotations=sc["rotations"][:2000],
+                   opacities=sc["opacities"][:2000], shs=sc["shs"][:2000]))   # warm the library
+    n, t0 = 0, time.perf_counter()
+    while True:
+        st = o.forward(sc)
+        o.backward(st, dc, dd)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > 10.0 or n >= 3 or el + el / n > max_seconds:
+            break
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return n / el, threads, "%d full fwd+bwd iteration(s) of the same workload (P=%d, %dx%d), fp32 oracle, OpenMP" % (
+        n, sc["means3D"].shape[0], sc["image_width"], sc["image_height"])
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, device):
+    from diff_gaussian_rasterization import _cabi
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+
+    L = _cabi.load()
+    K, Wm = args.steps, args.warmup
+    cfg, sc, cams, dc, dd = build_workload(args.workload, K + Wm, rank, device)
+    t = S.to_torch(sc, device)
+    eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                       cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
+    cams_dev = torch.from_numpy(cams).to(device)
+    cams_pin = torch.from_numpy(cams).pin_memory()
+    dc_pin, dd_pin = torch.from_numpy(dc).pin_memory(), torch.from_numpy(dd).pin_memory()
+    eng.dL_dcolor.copy_(dc_pin)
+    eng.dL_ddepth.copy_(dd_pin)
+    # exact instance counts over all poses -> capacity that cannot overflow
+    Rs = []
+    for i in range(K + Wm):
+        eng.set_camera(cams_dev[i])
+        Rs.append(eng.calibrate())
+    eng.capture()
+    flush = l2_flusher(device)
+    stream = torch.cuda.current_stream(device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------- value: device timed, inputs resident ----------------
+    l0 = L.gsr_kernel_launch_count()
+    eng.set_camera(cams_dev[0])
+    eng.step(use_graph=False)
+    torch.cuda.synchronize(device)
+    launches_per_step = int(L.gsr_kernel_launch_count() - l0)
+    for i in range(Wm):
+        flush()
+        eng.set_camera(cams_dev[i])
+        eng.step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device())
+    barrier()
+    sampler.start()
+    for i in range(K):
+        flush()
+        ev[i][0].record(stream)
+        eng.set_camera(cams_dev[Wm + i])
+        eng.step()
+        ev[i][1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(step_ms))
+    R_last, overflow = eng.header()
+    assert not overflow, "binning capacity overflow inside the timed region"
+    tau_check = eng.g_tau.cpu().numpy().copy()
+
+    # ---------------- e2e: host buffers, copies inside the timed region ----------------
+    copy_stream = torch.cuda.Stream(device)
+    tau_pin = torch.empty(6, dtype=torch.float32).pin_memory()
+    hdr_pin = torch.empty(2, dtype=torch.int32).pin_memory()
+    hdr_dev = torch.as_tensor(_RawView(eng.geom.data_ptr(), 8), device=device).view(torch.int32)
+    up_done = torch.cuda.Event()
+
+    def e2e_step(i):
+        eng.cam.copy_(cams_pin[i], non_blocking=True)                    # H2D pose (208 B)
+        with torch.cuda.stream(copy_stream):                              # H2D dL/dpixel, overlaps the forward
+            eng.dL_dcolor.copy_(dc_pin, non_blocking=True)
+            eng.dL_ddepth.copy_(dd_pin, non_blocking=True)
+            up_done.record(copy_stream)
+        eng.graph_fwd.replay()
+        stream.wait_event(up_done)
+        eng.graph_bwd.replay()
+        tau_pin.copy_(eng.g_tau, non_blocking=True)                      # D2H result
+        hdr_pin.copy_(hdr_dev, non_blocking=True)
+        stream.synchronize()                                              # the next pose depends on dL/dtau
+        copy_stream.wait_stream(stream)
+
+    for i in range(Wm):
+        flush()
+        torch.cuda.synchronize(device)
+        e2e_step(i)
+    barrier()
+    e2e_s = 0.0
+    for i in range(K):
+        flush()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        e2e_step(Wm + i)
+        e2e_s += time.perf_counter() - t0
+        assert hdr_pin[1].item() == 0
+    barrier()
+    assert np.allclose(tau_pin.numpy(), tau_check, rtol=1e-3, atol=1e-9), "e2e path disagrees with the resident path"
+    h2d = 52 * 4 + dc.nbytes + dd.nbytes
+    d2h = 6 * 4 + 8
+
+    # ---------------- per-stage CUDA-event timing (roofline) ----------------
+    L.gsr_stage_timing(1)
+    stage = np.zeros(5)
+    out5 = (C.c_float * 5)()
+    nst = max(3, min(K, 20))
+    for i in range(nst):
+        flush()
+        eng.set_camera(cams_dev[Wm + (i % K)])
+        eng.step(use_graph=False)
+        _cabi.check(L.gsr_stage_times_ms(out5), "stage_times")
+        stage += np.array(list(out5))
+    stage /= nst
+    L.gsr_stage_timing(0)
+    names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
+    R_mean = float(np.mean(Rs[Wm:]))
+    HW = cfg["W"] * cfg["H"]
+    rb = roofline_bytes(cfg["P"], R_mean, HW)
+    peak, peak_src = peaks()
+    dom = int(np.argmax([stage[2], stage[3]])) + 2       # dominant single kernel: one of the two composite kernels
+    achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9
+    stages = {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]), "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
+              for n, ms in zip(names, stage)}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(names[dom])
+
+    # ---------------- reductions over ranks ----------------
+    tmax, emax = dev_ms, e2e_s
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        tmax, emax = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return None
+    line = {
+        "metric": METRIC, "value": world * K / (tmax * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": tmax / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload + ": %dx%d, P=%d Gaussians, SH deg %d, 1 view/step, pose perturbed every step"
+                   % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"]),
+                   "num_rendered_mean": R_mean, "tiles": ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16),
+                   "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
+                   "parallelism": "pose-parallel x%d (one independent tracking stream per GPU, no collective)" % world,
+                   "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d" % eng.capacity},
+        "e2e": {"value": world * K / emax, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": emax / K * 1e3,
+                "what": "pinned pose block + pinned dL/dcolor,dL/ddepth H2D, dL/dtau + header D2H, host sync every step"},
+        "gpu_launches": launches_per_step * K,
+        "launches_per_step": {"kernels": launches_per_step, "graph_launches": 1},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
+                     "whole_step": {"alg_bytes": int(sum(rb.values())), "frac": round(sum(rb.values()) / (tmax / K * 1e-3) / 1e9 / peak, 4)},
+                     "stages": stages},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    return line
+
+
+class _RawView:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world, device):
+    """The reference arm (rank 0 only)."""
+    from diff_gaussian_rasterization import scenes as S
+
+    K, Wm = args.steps, args.warmup
+    cfg, sc, cams, dc, dd = build_workload(args.workload, K + Wm, 0, device)
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libgsref.so")
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload + ": %dx%d, P=%d Gaussians, SH deg %d, 1 view/step, pose perturbed every step"
+                       % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"])}}
+    if not (os.path.exists(ref_so) and torch.cuda.is_available()):
+        v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd)
+        base.update(value=v, ms_per_step=1e3 / v,
+                    cpu_baseline={"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        return base
+    Lr = C.CDLL(ref_so)
+    Lr.gsref_create.restype = C.c_void_p
+    h = C.c_void_p(Lr.gsref_create())
+    t = S.to_torch(sc, device)
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    f32 = dict(dtype=torch.float32, device=device)
+    cams_dev = torch.from_numpy(cams).to(device)
+    cam = torch.zeros(52, **f32)
+    gc, gd = torch.from_numpy(dc).to(device), torch.from_numpy(dd).to(device)
+    out = dict(color=torch.empty((3, H, W), **f32), depth=torch.empty((1, H, W), **f32), opacity=torch.empty((1, H, W), **f32),
+               radii=torch.empty((P,), dtype=torch.int32, device=device), n_touched=torch.empty((P,), dtype=torch.int32, device=device))
+    gshape = dict(m2d=(P, 3), conic=(P, 2, 2), opac=(P, 1), col=(P, 3), dep=(P, 1), m3d=(P, 3), cov=(P, 6), sh=(P, 1, 3),
+                  sc=(P, 3), rot=(P, 4), tau=(P, 6))
+    g = {k: torch.empty(s, **f32) for k, s in gshape.items()}
+    p = lambda x: C.c_void_p(x.data_ptr())
+    cp = cam.data_ptr()
+    view, proj, praw, campos = C.c_void_p(cp), C.c_void_p(cp + 64), C.c_void_p(cp + 128), C.c_void_p(cp + 192)
+
+    def step(i):
+        cam.copy_(cams_dev[i])
+        for v in out.values():          # torch::full(0) of the binding, rasterize_points.cu:84-88
+            v.zero_()
+        R = Lr.gsref_forward(h, P, 0, 1, p(t["bg"]), W, H, p(t["means3D"]), p(t["shs"]), None, p(t["opacities"]), p(t["scales"]),
+                             C.c_float(1.0), p(t["rotations"]), None, view, proj, campos, C.c_float(sc["tanfovx"]),
+                             C.c_float(sc["tanfovy"]), 0, p(out["color"]), p(out["depth"]), p(out["opacity"]), p(out["radii"]),
+                             p(out["n_touched"]), 0)
+        for v in g.values():            # torch::zeros of the binding, rasterize_points.cu:175-185
+            v.zero_()
+        Lr.gsref_backward(h, P, 0, 1, R, p(t["bg"]), W, H, p(t["means3D"]), p(t["shs"]), None, p(t["scales"]), C.c_float(1.0),
+                          p(t["rotations"]), None, view, proj, praw, campos, C.c_float(sc["tanfovx"]), C.c_float(sc["tanfovy"]),
+                          p(out["radii"]), p(gc), p(gd), p(g["m2d"]), p(g["conic"]), p(g["opac"]), p(g["col"]), p(g["dep"]),
+                          p(g["m3d"]), p(g["cov"]), p(g["sh"]), p(g["sc"]), p(g["rot"]), p(g["tau"]), 0)
+        return torch.sum(g["tau"].view(-1, 6), dim=0)     # __init__.py:162-164
+
+    flush = l2_flusher(device)
+    stream = torch.cuda.current_stream(device)
+    for i in range(Wm):
+        flush()
+        step(i)
+    torch.cuda.synchronize(device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    for i in range(K):
+        flush()
+        ev[i][0].record(stream)
+        tau = step(Wm + i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop()
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    v = K / (ms * 1e-3)
+    Lr.gsref_destroy(h)
+    base.update(value=v, ms_per_step=ms / K, clocks=clocks,
+                cpu_baseline={"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "device": "cuda",
+                              "sample": "all %d steps of the workload; the reference path has no CPU implementation, so its own "
+                                        "CUDA kernels (unmodified sources, sm_100a) run on the B200, driven by one host thread" % K},
+                e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                check={"dL_dtau_last": [float(x) for x in tau.cpu().numpy()]})
+    base["config"]["l2"] = "flushed between steps (256 MiB fill, outside the per-step events)"
+    return base
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C1_tum_tracking")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        device = "cuda:%d" % local if torch.cuda.is_available() else "cpu"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        print(json.dumps(run_reference(args, rank, world, device)), flush=True)
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
+    torch.cuda.set_device(local)
+    device = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    line = run_ours(args, rank, world, device)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

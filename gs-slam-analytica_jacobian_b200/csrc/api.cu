@@ -1,5 +1,6 @@
 // C-ABI of gsr_b200 (declared in include/gsr_b200.h).  Thin host layer: argument checks, workspace
 // carve-up, stream plumbing; no torch types, no global state beyond a thread-local error string.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -9,6 +10,14 @@
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py: gpu_launches)
+// optional stage timing (bench.py roofline): CUDA events recorded on the launching stream between stages
+bool g_timing = false;
+cudaEvent_t g_ev[7];
+void stage_mark(int i, cudaStream_t st)
+{
+	if (g_timing) cudaEventRecord(g_ev[i], st);
+}
 
 int fail(int code, const char* fmt, const char* detail = "")
 {
@@ -95,7 +104,10 @@ int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* rad
 	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
 	cudaStream_t st = (cudaStream_t)stream;
 	gsr::GeomView g = gsr::geom_view(geom, s.P);
+	stage_mark(0, st);
 	gsr::launch_preprocess_forward(s, g, radii, n_touched, st);
+	stage_mark(1, st);
+	if (s.P > 0) g_launches += 1;
 	return debug_sync(a, st, "preprocess");
 }
 
@@ -128,10 +140,13 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 	gsr::GeomView g = gsr::geom_view(geom, s.P);
 	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
-	gsr::launch_binning(s, g, b, im, (size_t)capacity, (size_t)(R_host >= 0 ? R_host : capacity), st);
+	g_launches += gsr::launch_binning(s, g, b, im, (size_t)capacity, (size_t)(R_host >= 0 ? R_host : capacity), st);
+	stage_mark(2, st);
 	rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
 	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, st);
+	stage_mark(3, st);
+	g_launches += 1;
 	return debug_sync(a, st, "render");
 }
 
@@ -191,11 +206,15 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 	gsr::GeomView g = gsr::geom_view(geom, s.P);
 	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
+	stage_mark(4, st);
 	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, st);
+	stage_mark(5, st);
+	g_launches += 2;
 	rc = debug_sync(a, st, "render backward");
 	if (rc) return rc;
 	gsr::launch_preprocess_backward(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
 	                                dL_drotations, dL_dcov3D, dL_dtau, st);
+	stage_mark(6, st);
 	return debug_sync(a, st, "preprocess backward");
 }
 
@@ -206,6 +225,31 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSR_ERR_ARG, "bad argument");
 	gsr::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 	return check_cuda("mark_visible");
+}
+
+unsigned long long gsr_kernel_launch_count(void) { return g_launches.load(); }
+
+int gsr_stage_timing(int enable)
+{
+	if (enable && !g_timing) {
+		for (int i = 0; i < 7; i++)
+			if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GSR_ERR_CUDA, "cudaEventCreate failed");
+		g_timing = true;
+	} else if (!enable && g_timing) {
+		g_timing = false;
+		for (int i = 0; i < 7; i++) cudaEventDestroy(g_ev[i]);
+	}
+	return GSR_OK;
+}
+
+int gsr_stage_times_ms(float* out5)
+{
+	if (!g_timing || !out5) return fail(GSR_ERR_ARG, "stage timing is not enabled");
+	if (cudaEventSynchronize(g_ev[6]) != cudaSuccess) return fail(GSR_ERR_CUDA, "event sync failed");
+	const int a[5] = {0, 1, 2, 4, 5}, b[5] = {1, 2, 3, 5, 6};
+	for (int i = 0; i < 5; i++)
+		if (cudaEventElapsedTime(&out5[i], g_ev[a[i]], g_ev[b[i]]) != cudaSuccess) return fail(GSR_ERR_CUDA, "elapsed time failed");
+	return GSR_OK;
 }
 
 int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long capacity, void* image,

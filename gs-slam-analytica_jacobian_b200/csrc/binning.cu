@@ -111,21 +111,29 @@ onesweep_kernel(const KeyT* __restrict__ kin, KeyT* __restrict__ kout, const uin
 			if (w < warp) woff += s_wsum[w];
 		const uint32_t gbase = woff + inc - gh;
 
+		// Decoupled look-back.  Flag and value share one 32-bit word, so relaxed gpu-scope accesses suffice;
+		// four predecessors are polled per round trip to shorten the latency chain.
 		uint32_t excl = 0;
 		uint32_t* my = lookback + (size_t)tile * 256 + d;
 		if (tile == 0) {
-			st_release_u32(my, LB_PREFIX | total);
+			st_relaxed_u32(my, LB_PREFIX | total);
 		} else {
-			st_release_u32(my, LB_AGG | total);
+			st_relaxed_u32(my, LB_AGG | total);
 			int t = (int)tile - 1;
-			while (true) {
-				const uint32_t w = ld_acquire_u32(lookback + (size_t)t * 256 + d);
-				if ((w >> 30) == 0) continue;
-				excl += w & LB_MASK;
-				if ((w >> 30) == 2) break;
-				t--;
+			bool stop = false;
+			while (!stop) {
+				uint32_t w[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) w[k] = (t - k >= 0) ? ld_relaxed_u32(lookback + (size_t)(t - k) * 256 + d) : LB_PREFIX;
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					if (stop || (w[k] >> 30) == 0) break;
+					excl += w[k] & LB_MASK;
+					t--;
+					if ((w[k] >> 30) == 2) stop = true;
+				}
 			}
-			st_release_u32(my, LB_PREFIX | (excl + total));
+			st_relaxed_u32(my, LB_PREFIX | (excl + total));
 		}
 		s_base[d] = gbase + excl;
 	}
@@ -182,23 +190,32 @@ scan_emit_kernel(const uint32_t* __restrict__ order, int P, const GaussRec* __re
 		if (w < warp) woff += s_w[w];
 		btotal += s_w[w];
 	}
-	if (tid == 0) {
+	if (warp == 0) {
+		// warp-parallel decoupled look-back: 32 predecessors per round trip
 		uint32_t excl = 0;
 		if (blk == 0) {
-			st_release_u32(status, LB_PREFIX | btotal);
+			if (lane == 0) st_relaxed_u32(status, LB_PREFIX | btotal);
 		} else {
-			st_release_u32(status + blk, LB_AGG | btotal);
-			int t = (int)blk - 1;
+			if (lane == 0) st_relaxed_u32(status + blk, LB_AGG | btotal);
+			int base = (int)blk - 1;
 			while (true) {
-				const uint32_t w = ld_acquire_u32(status + t);
-				if ((w >> 30) == 0) continue;
-				excl += w & LB_MASK;
-				if ((w >> 30) == 2) break;
-				t--;
+				const int t = base - lane;
+				const uint32_t w = (t >= 0) ? ld_relaxed_u32(status + t) : LB_PREFIX;
+				const unsigned ready = __ballot_sync(0xffffffffu, (w >> 30) != 0);
+				const unsigned pref = __ballot_sync(0xffffffffu, (w >> 30) == 2);
+				const int p = pref ? __ffs(pref) - 1 : 31;          // nearest predecessor holding a prefix
+				const unsigned need = (p >= 31) ? 0xffffffffu : ((2u << p) - 1u);
+				if ((ready & need) != need) continue;                // someone in the window is not published yet
+				uint32_t v = (lane <= p) ? (w & LB_MASK) : 0u;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+				excl += v;
+				if (pref) break;
+				base -= 32;
 			}
-			st_release_u32(status + blk, LB_PREFIX | (excl + btotal));
+			if (lane == 0) st_relaxed_u32(status + blk, LB_PREFIX | (excl + btotal));
 		}
-		s_blockbase = excl;
+		if (lane == 0) s_blockbase = excl;
 	}
 	__syncthreads();
 	const uint32_t off = s_blockbase + woff + inc - ntiles;
@@ -257,12 +274,13 @@ tile_ranges_kernel(const uint16_t* __restrict__ tiles, const unsigned* __restric
 
 // R_capacity: instance capacity of the binning workspace (layout key);  R_bound: host-known upper bound of
 // the instance count used to size grids (== R when the caller synchronised, == R_capacity otherwise).
-void launch_binning(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, size_t R_capacity,
-                    size_t R_bound, cudaStream_t stream)
+int launch_binning(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, size_t R_capacity,
+                   size_t R_bound, cudaStream_t stream)
 {
+	int launches = 0;
 	const int tiles = s.grid_x * s.grid_y;
 	cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), stream);
-	if (s.P == 0) return;
+	if (s.P == 0) return 0;
 	cudaMemsetAsync(b.hist, 0, b.lookback_words * 4, stream);
 	const int P = s.P;
 	uint32_t* h = b.hist;
@@ -282,6 +300,7 @@ void launch_binning(const Scene& s, const GeomView& g, const BinView& b, const I
 		onesweep_kernel<uint32_t, false, true><<<nt, GSR_SORT_THREADS, 0, stream>>>(kA, kB, b.order_alt, b.order, nullptr, P, 16, 255, h + 512, lb, &g.hdr->ticket[2]);
 		lb += (size_t)nt * 256;
 		onesweep_kernel<uint32_t, false, false><<<nt, GSR_SORT_THREADS, 0, stream>>>(kB, kA, b.order, b.order_alt, nullptr, P, 24, 255, h + 768, lb, &g.hdr->ticket[3]);
+		launches += 5;
 	}
 	// 2. scan + emit (depth order -> instances)
 	int tile_bits = 1;
@@ -291,6 +310,7 @@ void launch_binning(const Scene& s, const GeomView& g, const BinView& b, const I
 	uint32_t* V1 = npass == 2 ? b.inst_val_alt : b.point_list;
 	scan_emit_kernel<<<(P + 255) / 256, 256, 0, stream>>>(b.order_alt, P, g.rec, s.grid_x, b.inst_tile, V0, (unsigned)R_capacity,
 	                                                     b.emit_status, h + 1024, g.hdr);
+	launches += 1;
 	// 3. tile sort
 	if (R_bound > 0) {
 		const unsigned nt = (unsigned)sort_tiles(R_bound);
@@ -308,7 +328,9 @@ void launch_binning(const Scene& s, const GeomView& g, const BinView& b, const I
 		int rb = (int)((R_bound + 256 * 8 - 1) / (256 * 8));
 		if (rb > 148 * 8) rb = 148 * 8;
 		tile_ranges_kernel<<<rb, 256, 0, stream>>>(sorted_tiles, &g.hdr->num_rendered, (unsigned)R_capacity, im.ranges);
+		launches += npass + 1;
 	}
+	return launches;
 }
 
 }  // namespace gsr

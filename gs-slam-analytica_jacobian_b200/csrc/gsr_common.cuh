@@ -169,6 +169,16 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 	             : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
 	uint32_t v;

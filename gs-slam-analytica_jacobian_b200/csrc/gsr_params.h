@@ -25,8 +25,8 @@ struct Scene {
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
-void launch_binning(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, size_t R_capacity,
-                    size_t R_bound, cudaStream_t stream);
+int launch_binning(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, size_t R_capacity,
+                   size_t R_bound, cudaStream_t stream);   // returns the number of kernels launched
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, cudaStream_t stream);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,

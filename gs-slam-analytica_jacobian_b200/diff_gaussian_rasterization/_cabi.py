@@ -17,7 +17,8 @@ GSR_ERR_ARG, GSR_ERR_CUDA, GSR_ERR_WORKSPACE, GSR_ERR_OVERFLOW = -1, -2, -3, -4
 EXPORTS = (
     "gsr_geometry_bytes", "gsr_image_bytes", "gsr_binning_bytes", "gsr_forward_plan", "gsr_forward_num_rendered",
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
-    "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version",
+    "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
+    "gsr_stage_timing", "gsr_stage_times_ms",
 )
 
 
@@ -77,6 +78,9 @@ def load():
     lib.gsr_mark_visible.argtypes = [ip, vp, vp, vp, vp, vp]
     lib.gsr_debug_pointers.argtypes = [ip, ip, ip, vp, vp, ll, vp, C.POINTER(C.c_ulonglong)]
     lib.gsr_error_string.restype = C.c_char_p
+    lib.gsr_kernel_launch_count.restype = C.c_ulonglong
+    lib.gsr_stage_timing.argtypes = [ip]
+    lib.gsr_stage_times_ms.argtypes = [C.POINTER(C.c_float)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

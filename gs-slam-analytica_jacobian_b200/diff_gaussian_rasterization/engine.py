@@ -1,0 +1,198 @@
+"""RasterEngine: the launch-lean way to drive the hot path for SLAM loops.
+
+The reference calls the rasterizer once per view through autograd, allocates every scratch/grad tensor
+per call and blocks on a D2H read of num_rendered in every forward (rasterizer_impl.cu:331).  A tracking
+loop (utils/slam_frontend.py:163, 100 iterations on one frozen map) or a mapping window iteration
+(utils/slam_backend.py:168-232) repeats the same shapes, so the engine
+  * owns persistent workspaces (geometry / binning / image) and output + gradient buffers,
+  * runs forward and backward WITHOUT any host synchronisation: the binning capacity is calibrated once
+    (exact run) with head-room, the kernels read num_rendered on the device, and an overflow flag is
+    read back with the results (overflow -> the step is re-run exactly, never silently wrong),
+  * captures forward(+backward) into CUDA graphs: one launch per step instead of ~14,
+  * takes the camera as four small device tensors whose contents are replaced in place per step.
+All compute goes through the C-ABI (include/gsr_b200.h); torch only owns memory and streams.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import GsrScene
+
+_L = _cabi.load()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class RasterEngine:
+    def __init__(self, gaussians, image_width, image_height, tanfovx, tanfovy, bg, sh_degree=0, scale_modifier=1.0,
+                 device="cuda", headroom=1.25):
+        """gaussians: dict with means3D[P,3], opacities[P,1], shs[P,M,3] or colors_precomp[P,3],
+        scales[P,3]+rotations[P,4] or cov3D_precomp[P,6] (fp32 tensors on `device`)."""
+        self.dev = torch.device(device)
+        f = lambda k: (gaussians[k].to(self.dev, torch.float32).contiguous() if gaussians.get(k) is not None else None)
+        self.g = {k: f(k) for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp")}
+        if self.g["colors_precomp"] is not None:
+            self.g["shs"] = None
+        if self.g["cov3D_precomp"] is not None:
+            self.g["scales"] = self.g["rotations"] = None
+        self.P = int(self.g["means3D"].shape[0])
+        self.M = int(self.g["shs"].shape[1]) if self.g["shs"] is not None else 0
+        self.W, self.H = int(image_width), int(image_height)
+        self.headroom = float(headroom)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        u8 = dict(dtype=torch.uint8, device=self.dev)
+        self.bg = torch.as_tensor(bg, dtype=torch.float32).to(self.dev).contiguous()
+        # camera block: view(16) | proj(16) | proj_raw(16) | campos(4)  -- one 208-byte H2D per pose
+        self.cam = torch.zeros(52, **f32)
+        # outputs
+        P, W, H, M = self.P, self.W, self.H, self.M
+        self.color = torch.empty((3, H, W), **f32)
+        self.depth = torch.empty((1, H, W), **f32)
+        self.opacity = torch.empty((1, H, W), **f32)
+        self.radii = torch.empty((P,), **i32)
+        self.n_touched = torch.empty((P,), **i32)
+        # upstream gradients + gradients
+        self.dL_dcolor = torch.zeros((3, H, W), **f32)
+        self.dL_ddepth = torch.zeros((1, H, W), **f32)
+        self.g_means3D = torch.empty((P, 3), **f32)
+        self.g_means2D = torch.empty((P, 3), **f32)
+        self.g_opacity = torch.empty((P, 1), **f32)
+        self.g_sh = torch.empty((P, M, 3), **f32) if self.g["shs"] is not None else None
+        self.g_colors = torch.empty((P, 3), **f32) if self.g["colors_precomp"] is not None else None
+        self.g_scales = torch.empty((P, 3), **f32) if self.g["scales"] is not None else None
+        self.g_rot = torch.empty((P, 4), **f32) if self.g["scales"] is not None else None
+        self.g_cov = torch.empty((P, 6), **f32) if self.g["cov3D_precomp"] is not None else None
+        self.g_tau = torch.zeros((6,), **f32)
+        # workspaces
+        self.geom_bytes = _L.gsr_geometry_bytes(P)
+        self.img_bytes = _L.gsr_image_bytes(W, H)
+        self.geom = torch.empty((self.geom_bytes,), **u8)
+        self.img = torch.empty((self.img_bytes,), **u8)
+        self.capacity = 0
+        self.bin_bytes = 0
+        self.binning = None
+        s = GsrScene()
+        s.P, s.D, s.M, s.W, s.H = P, int(sh_degree), M, W, H
+        s.background = self.bg.data_ptr()
+        for k in ("means3D", "shs", "colors_precomp", "opacities", "scales", "rotations", "cov3D_precomp"):
+            setattr(s, k, self.g[k].data_ptr() if self.g[k] is not None else None)
+        base = self.cam.data_ptr()
+        s.viewmatrix, s.projmatrix, s.projmatrix_raw, s.campos = base, base + 64, base + 128, base + 192
+        s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
+        s.prefiltered, s.debug = 0, 0
+        self.scene = s
+        self.graph_fwd = self.graph_bwd = self.graph_all = None
+        self.last_num_rendered = None
+
+    # ---- camera ---------------------------------------------------------------------------------------
+    @staticmethod
+    def pack_camera(viewmatrix, projmatrix, projmatrix_raw, campos, out=None):
+        """Pack the four settings tensors (any device) into the 52-float camera block layout."""
+        out = torch.empty(52, dtype=torch.float32) if out is None else out
+        out[0:16] = viewmatrix.reshape(-1)
+        out[16:32] = projmatrix.reshape(-1)
+        out[32:48] = projmatrix_raw.reshape(-1)
+        out[48:51] = campos.reshape(-1)
+        out[51] = 0
+        return out
+
+    def set_camera(self, packed, non_blocking=True):
+        self.cam.copy_(packed, non_blocking=non_blocking)
+
+    # ---- capacity -------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def ensure_capacity(self, num_rendered):
+        need = int(num_rendered * self.headroom) + 4096
+        if need > self.capacity:
+            self.capacity = need
+            self.bin_bytes = _L.gsr_binning_bytes(self.P, self.capacity)
+            self.binning = torch.empty((self.bin_bytes,), dtype=torch.uint8, device=self.dev)
+            self.graph_fwd = self.graph_bwd = self.graph_all = None   # pointers changed
+        return self.capacity
+
+    def calibrate(self):
+        """One exact (synchronising) forward at the current camera to size the binning workspace."""
+        with torch.cuda.device(self.dev):
+            _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
+                                            _p(self.n_touched), self._stream()), "forward_plan")
+            R = C.c_longlong(0)
+            _cabi.check(_L.gsr_forward_num_rendered(_p(self.geom), self._stream(), C.byref(R)), "num_rendered")
+        self.last_num_rendered = int(R.value)
+        self.ensure_capacity(R.value)
+        return int(R.value)
+
+    # ---- un-synchronised launches ---------------------------------------------------------------------
+    def launch_forward(self):
+        st = self._stream()
+        _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
+                                        _p(self.n_touched), st), "forward_plan")
+        _cabi.check(_L.gsr_forward_render(C.byref(self.scene), _p(self.geom), _p(self.binning), self.bin_bytes,
+                                          self.capacity, -1, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
+                                          _p(self.opacity), _p(self.n_touched), st), "forward_render")
+
+    def launch_backward(self):
+        _cabi.check(_L.gsr_rasterize_gaussians_backward(
+            C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
+            _p(self.dL_dcolor), _p(self.dL_ddepth), _p(self.g_means3D), _p(self.g_means2D), _p(self.g_sh), _p(self.g_colors),
+            _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov), _p(self.g_tau), self._stream()), "backward")
+
+    def capture(self):
+        """Capture forward, backward and forward+backward CUDA graphs over the persistent buffers."""
+        if self.binning is None:
+            self.calibrate()
+        with torch.cuda.device(self.dev):
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self.launch_forward()
+                self.launch_backward()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            self.graph_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fwd):
+                self.launch_forward()
+            self.graph_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_bwd):
+                self.launch_backward()
+            self.graph_all = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_all):
+                self.launch_forward()
+                self.launch_backward()
+
+    def step(self, use_graph=True):
+        """forward + backward at the current camera / upstream gradients; no host synchronisation."""
+        if use_graph:
+            if self.graph_all is None:
+                self.capture()
+            self.graph_all.replay()
+        else:
+            if self.binning is None:
+                self.calibrate()
+            with torch.cuda.device(self.dev):
+                self.launch_forward()
+                self.launch_backward()
+
+    def header(self):
+        """(num_rendered, overflow) of the last forward -- synchronises."""
+        ov, need = C.c_int(0), C.c_longlong(0)
+        with torch.cuda.device(self.dev):
+            _cabi.check(_L.gsr_forward_overflowed(_p(self.geom), self._stream(), C.byref(ov), C.byref(need)), "overflowed")
+        self.last_num_rendered = int(need.value)
+        return int(need.value), bool(ov.value)
+
+    def step_checked(self, use_graph=True):
+        """step() + overflow validation; an overflowing step is re-run with a larger workspace."""
+        self.step(use_graph)
+        R, ov = self.header()
+        if ov:
+            self.ensure_capacity(R)
+            self.step(use_graph)
+            R, ov = self.header()
+            assert not ov
+        return R

@@ -122,6 +122,14 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long binning_capacity, void* image,
                        unsigned long long* out);
 
+/* ---- measurement hooks (bench.py) ---- */
+/* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
+unsigned long long gsr_kernel_launch_count(void);
+/* enable/disable CUDA-event stage timing; gsr_stage_times_ms returns the durations of the last
+ * forward+backward: {preprocess, binning, render_forward, render_backward, preprocess_backward} */
+int gsr_stage_timing(int enable);
+int gsr_stage_times_ms(float* out5);
+
 const char* gsr_error_string(void);
 int gsr_version(void);
 
