@@ -21,13 +21,15 @@ struct alignas(16) GaussRec {
 	float4 q0, q1, q2;
 };
 
-// Per-Gaussian accumulator of the render backward (48 B): what the reference keeps in five
-// zero-filled tensors (rasterize_points.cu:176-180).
-//   a0 = { dL/dmean2D.x, dL/dmean2D.y (NDC units), dL/dconic.xx, dL/dconic.xy }
-//   a1 = { dL/dconic.yy, dL/dopacity, dL/ddepth, dL/dred }
-//   a2 = { dL/dgreen, dL/dblue, 0, 0 }
+// Per-Gaussian accumulator of the render backward (64 B = two 32-byte sectors): what the reference
+// keeps in five zero-filled tensors (rasterize_points.cu:176-180).  Four 16-byte words, each the target
+// of ONE vector RED (red.global.add.v4.f32) per (warp, Gaussian):
+//   a0 = { dL/dmean2D.x, dL/dmean2D.y (NDC units), dL/dconic.xx, 0 }
+//   a1 = { dL/dconic.xy, dL/dconic.yy, 0, 0 }
+//   a2 = { dL/dopacity, dL/ddepth, dL/dred, 0 }
+//   a3 = { dL/dgreen, dL/dblue, 0, 0 }
 struct alignas(16) GaussAcc {
-	float4 a0, a1, a2;
+	float4 a0, a1, a2, a3;
 };
 
 // Header at the start of the geometry workspace (device memory, 256 B)

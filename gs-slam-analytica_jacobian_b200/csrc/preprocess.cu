@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		if (n_touched) n_touched[idx] = 0;
 		g.rec[idx] = rec;
 		GaussAcc z;
-		z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0;
+		z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
 		g.acc[idx] = z;
 		g.tiles_touched[idx] = my_tiles;
 		g.depth_key[idx] = key;

@@ -124,13 +124,13 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 		if (visible) {
 			const GaussAcc a = g.acc[idx];
 			GaussAcc z;
-			z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0;
+			z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
 			g.acc[idx] = z;   // consumed: ready for the next backward without a memset
 			dm2x = a.a0.x; dm2y = a.a0.y;
-			const float dcx = a.a0.z, dcy = a.a0.w, dcz = a.a1.x;
-			dopac = a.a1.y;
-			const float ddepth = a.a1.z;
-			dcol[0] = a.a1.w; dcol[1] = a.a2.x; dcol[2] = a.a2.y;
+			const float dcx = a.a0.z, dcy = a.a1.x, dcz = a.a1.y;
+			dopac = a.a2.x;
+			const float ddepth = a.a2.y;
+			dcol[0] = a.a2.z; dcol[1] = a.a3.x; dcol[2] = a.a3.y;
 
 			const float mx = s.means3D[3 * idx], my = s.means3D[3 * idx + 1], mz = s.means3D[3 * idx + 2];
 			// ---- 3D covariance (recomputed; reference re-reads geomState.cov3D) ----

@@ -3,24 +3,33 @@
 // renderCUDA (cuda_rasterizer/backward.cu:648-872).
 //
 // One CTA per 16x16 tile, one thread per pixel; each warp owns an 8x4 pixel block.  Batches of 256
-// list entries are gathered as 48-byte records (3 x 16 B, cp.async / LDGSTS) into shared memory.
+// list entries are gathered as 48-byte records (3 x 16 B, cp.async / LDGSTS, double buffered) into
+// shared memory.
 //
 // Work skipping that does not change results: a (pixel, Gaussian) pair only matters when
 // alpha = min(0.99, o*exp(-q)) >= 1/255, i.e. q <= ln(255 o).  For every chunk of 32 list entries the
 // 32 lanes test one entry each against the warp's pixel block (exact minimum of the convex quadratic q
 // over the 8x4 rectangle, with a conservative margin) and ballot; the warp then evaluates only the
-// survivors (typically < 1/3 of the entries), with exactly the reference's per-pair arithmetic.
+// survivors (typically < 1/3 of the entries) with the reference's per-pair decisions.
 // Every per-pair decision is predicated, so the warp stays converged and can (a) vote its own early
-// termination, (b) aggregate the n_touched integer atomics to one RED per warp, and in the backward
-// (c) reduce the ten per-Gaussian gradient terms with a transposing butterfly of 12 register shuffles
-// instead of the reference's 256-thread shared-memory tree (backward.cu:626-644, ~12 __syncthreads per
-// (tile, Gaussian)), accumulate them per CTA in shared memory and flush them with three 16-byte vector
-// REDs per (tile, Gaussian) instead of ten scalar global atomics (backward.cu:859-868).
+// termination, (b) aggregate the n_touched integer atomics to one RED per chunk and warp, and in the
+// backward (c) reduce the ten per-Gaussian gradient terms with a transposing butterfly of 12 register
+// shuffles instead of the reference's 256-thread shared-memory tree (backward.cu:626-644, ~12
+// __syncthreads per (tile, Gaussian)) and flush them with four 16-byte vector REDs per (warp, Gaussian)
+// instead of ten scalar global atomics behind a CTA-wide tree (backward.cu:859-868).
 #include "gsr_params.h"
 
 namespace gsr {
 
 namespace {
+
+#ifndef GSR_ACCURATE_EXP
+// ex2.approx(x * log2 e): relative error ~2^-21 + |x| * 2^-23 (|x| < 6 where it matters); accurate expf costs 8
+// more instructions per (pixel, Gaussian) pair in issue-bound kernels.
+__device__ __forceinline__ float gsr_exp(float x) { return __expf(x); }
+#else
+__device__ __forceinline__ float gsr_exp(float x) { return expf(x); }
+#endif
 
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
 {
@@ -31,7 +40,7 @@ __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px,
 
 // Conservative test: can the Gaussian (mean q0.xy, conic q0.z q0.w q1.x, opacity q1.y) reach
 // alpha >= 1/255 at any pixel centre inside [x0,x1] x [y0,y1] ?  Returns false only when the exact
-// per-pixel test (fp32, reference arithmetic) is guaranteed to reject every pixel of the block.
+// per-pixel test (fp32) is guaranteed to reject every pixel of the block.
 __device__ __forceinline__ bool may_touch(const float4 q0, const float4 q1, float x0, float y0, float x1, float y1)
 {
 	const float mx = q0.x, my = q0.y, A = q0.z, B = q0.w, Cc = q1.x, o = q1.y;
@@ -70,7 +79,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched)
 {
-	__shared__ float4 s_q0[2][256], s_q1[2][256], s_q2[2][256];
+	__shared__ GaussRec s_rec[2][256];
 	__shared__ uint32_t s_id[2][256];
 
 	const int tile = blockIdx.x;
@@ -89,6 +98,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 	bool done = !inside;
 	float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
 	uint32_t last_contributor = 0;
+	// n_touched counts pixels whose transmittance after the blend is still > 0.5 (forward.cu:511-514).
+	// T only decreases, so once no live lane of the warp is above 0.5 the bookkeeping is skipped for good.
+	bool warp_hi_T = __any_sync(0xffffffffu, inside);
 
 	auto stage = [&](int b, int buf) {
 		const int i = b * 256 + threadIdx.x;
@@ -96,9 +108,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 			const uint32_t id = __ldg(point_list + range.x + i);
 			s_id[buf][threadIdx.x] = id;
 			const GaussRec* r = rec + id;
-			cp_async16(&s_q0[buf][threadIdx.x], &r->q0);
-			cp_async16(&s_q1[buf][threadIdx.x], &r->q1);
-			cp_async16(&s_q2[buf][threadIdx.x], &r->q2);
+			cp_async16(&s_rec[buf][threadIdx.x].q0, &r->q0);
+			cp_async16(&s_rec[buf][threadIdx.x].q1, &r->q1);
+			cp_async16(&s_rec[buf][threadIdx.x].q2, &r->q2);
 		}
 		cp_async_commit();
 	};
@@ -112,45 +124,51 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 		cp_async_wait<1>();
 		__syncthreads();
 		const int cnt = min(256, n - b * 256);
-		bool warp_done = __all_sync(0xffffffffu, done);
-		for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
+		int last_local = -1;
+		for (int c0 = 0; c0 < cnt; c0 += 32) {
+			if (__all_sync(0xffffffffu, done)) break;
 			// cull phase: one list entry per lane
 			const int e = c0 + lane;
 			bool keep = false;
-			if (e < cnt) keep = may_touch(s_q0[buf][e], s_q1[buf][e], bx0, by0, bx1, by1);
+			if (e < cnt) keep = may_touch(s_rec[buf][e].q0, s_rec[buf][e].q1, bx0, by0, bx1, by1);
 			unsigned live = __ballot_sync(0xffffffffu, keep);
+			int my_touched = 0;   // lane L accumulates the n_touched increment of entry c0 + L
 			while (live) {
-				const int j = c0 + __ffs(live) - 1;
+				const int jl = __ffs(live) - 1;
 				live &= live - 1;
-				const float4 q0 = s_q0[buf][j];
-				const float4 q1 = s_q1[buf][j];
+				const GaussRec* r = &s_rec[buf][c0 + jl];
+				const float4 q0 = r->q0;
+				const float4 q1 = r->q1;
+				const float4 q2 = r->q2;
 				const float dx = q0.x - pxf, dy = q0.y - pyf;
 				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-				const float alpha = fminf(0.99f, q1.y * expf(power));
+				const float alpha = fminf(0.99f, q1.y * gsr_exp(power));
 				bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 				const float test_T = T * (1 - alpha);
 				if (valid && test_T < 0.0001f) {
 					done = true;
 					valid = false;
 				}
-				if (__any_sync(0xffffffffu, valid)) {
-					const float4 q2 = s_q2[buf][j];
-					if (valid) {
-						C0 += q1.w * alpha * T;
-						C1 += q2.x * alpha * T;
-						C2 += q2.y * alpha * T;
-						D += q1.z * alpha * T;
-						T = test_T;
-						last_contributor = b * 256 + j + 1;
-					}
+				if (warp_hi_T) {
 					const unsigned touched = __ballot_sync(0xffffffffu, valid && test_T > 0.5f);
-					if (touched && lane == 0) atomicAdd(&n_touched[s_id[buf][j]], __popc(touched));
-				} else if (__all_sync(0xffffffffu, done)) {
-					warp_done = true;
-					break;
+					if (lane == jl) my_touched = __popc(touched);
+				}
+				if (valid) {
+					const float w = alpha * T;
+					C0 += q1.w * w;
+					C1 += q2.x * w;
+					C2 += q2.y * w;
+					D += q1.z * w;
+					T = test_T;
+					last_local = c0 + jl;
 				}
 			}
+			if (warp_hi_T) {
+				if (my_touched) atomicAdd(&n_touched[s_id[buf][e]], my_touched);
+				warp_hi_T = __any_sync(0xffffffffu, !done && T > 0.5f);
+			}
 		}
+		if (last_local >= 0) last_contributor = b * 256 + last_local + 1;
 	}
 	cp_async_wait<0>();
 	if (inside) {
@@ -169,34 +187,20 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 // backward
 // ---------------------------------------------------------------------------------------------
 
-// Sum ten per-lane values over the warp with a transposing butterfly: after the call lane L (even)
-// holds the full sum of value index red_slot(L) (or nothing when red_slot(L) < 0).
-// 12 shuffles instead of 50 for ten independent butterflies.
-__device__ __forceinline__ int red_slot(int lane)
-{
-	// bit4: {0..4} | {5..9};  bit3: first three | last two (+pad);  bit2: first two | last one;  bit1: first | second
-	const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
-	int i3;                       // index among {0,1,2} after step B, -1 = padding
-	if (!b2) i3 = b1;             // first two -> 0 or 1
-	else i3 = b1 ? -1 : 2;        // last one -> 2 (second slot is padding)
-	if (i3 < 0) return -1;
-	int i5;                       // index among {0..4} after step A
-	if (!b3) i5 = i3;             // first three: 0,1,2
-	else { if (i3 == 2) return -1; i5 = 3 + i3; }   // last two: 3,4 (third slot is padding)
-	return b4 * 5 + i5;
-}
-
-__device__ __forceinline__ float reduce10(const float v[10], int lane)
+// Sum ten per-lane values over the warp with a transposing butterfly (12 shuffles instead of 50 for ten
+// independent butterflies), then gather them so that lane 8*g (g = 0..3) holds the g-th 16-byte word of
+// the Gaussian's accumulator: g0 = {v0,v1,v2,0}  g1 = {v3,v4,0,0}  g2 = {v5,v6,v7,0}  g3 = {v8,v9,0,0}.
+__device__ __forceinline__ float4 reduce10(const float v[10], int lane)
 {
 	const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
 	float w[5], x[3], y[2];
 #pragma unroll
-	for (int k = 0; k < 5; k++) {
+	for (int k = 0; k < 5; k++) {           // halves: lanes 0-15 keep v0..4, lanes 16-31 keep v5..9
 		const float send = b4 ? v[k] : v[k + 5];
 		const float keep = b4 ? v[k + 5] : v[k];
 		w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
 	}
-	{
+	{                                       // quarters: first three | last two (+ padding)
 		const float s0 = b3 ? w[0] : w[3], k0 = b3 ? w[3] : w[0];
 		const float s1 = b3 ? w[1] : w[4], k1 = b3 ? w[4] : w[1];
 		const float s2 = b3 ? w[2] : 0.f, k2 = b3 ? 0.f : w[2];
@@ -204,7 +208,7 @@ __device__ __forceinline__ float reduce10(const float v[10], int lane)
 		x[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
 		x[2] = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
 	}
-	{
+	{                                       // eighths: first two | last one (+ padding)
 		const float s0 = b2 ? x[0] : x[2], k0 = b2 ? x[2] : x[0];
 		const float s1 = b2 ? x[1] : 0.f, k1 = b2 ? 0.f : x[1];
 		y[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
@@ -213,7 +217,10 @@ __device__ __forceinline__ float reduce10(const float v[10], int lane)
 	const float s = b1 ? y[0] : y[1], k = b1 ? y[1] : y[0];
 	float z = k + __shfl_xor_sync(0xffffffffu, s, 2);
 	z += __shfl_xor_sync(0xffffffffu, z, 1);
-	return z;
+	// within each group of 8 lanes: offsets 0,1 hold X0; 2,3 hold X1; 4,5 hold X2 (or padding 0); 6,7 padding
+	const float x1 = __shfl_down_sync(0xffffffffu, z, 2);
+	const float x2 = __shfl_down_sync(0xffffffffu, z, 4);
+	return make_float4(z, x1, x2, 0.f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -223,9 +230,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
                        GaussAcc* __restrict__ acc)
 {
-	__shared__ float4 s_q0[256], s_q1[256], s_q2[256];
-	__shared__ uint32_t s_id[256];
-	__shared__ float s_acc[256][12];
+	__shared__ GaussRec s_rec[2][256];
+	__shared__ uint32_t s_id[2][256];
 	__shared__ uint32_t s_max[8];
 
 	const int tile = blockIdx.x;
@@ -250,8 +256,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	}
 	const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
 	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-	const int my_slot = (lane & 1) ? -1 : red_slot(lane);
-	// value order of v[]: 0 mean2D.x, 1 mean2D.y, 2 conic.xx, 3 conic.xy, 4 conic.yy, 5 opacity, 6 depth, 7..9 rgb
+	// value order of v[]: 0 mean2D.x, 1 mean2D.y, 2 conic.xx | 3 conic.xy, 4 conic.yy | 5 opacity, 6 depth, 7 red | 8 green, 9 blue
 
 	// entries behind the tile's deepest contributor can never contribute (backward.cu:763)
 	uint32_t m = last_contributor;
@@ -264,96 +269,104 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	for (int w = 0; w < 8; w++) top = max(top, s_max[w]);
 	const uint32_t warp_top = m;   // this warp's deepest contributor
 
-	float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, accumd = 0.f;
-	float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_depth = 0.f;
+	// The reference keeps, per channel, accum_rec = last_alpha*last_color + (1-last_alpha)*accum_rec and sums
+	// (c - accum_rec)*dL/dC over colour and depth (backward.cu:799-813).  The sum is linear, so ONE scalar
+	// recurrence on beta = <accum_rec, dL/dpixel> with s = <(rgb,depth), dL/dpixel> is the same quantity.
+	float beta = 0.f, last_alpha = 0.f, last_s = 0.f;
 
-	for (int hi = (int)top; hi > 0; hi -= 256) {
-		const int cnt = min(256, hi);
-		__syncthreads();   // previous batch fully flushed
-		{
-			const int t = threadIdx.x;
-			if (t < cnt) {
-				const uint32_t id = __ldg(point_list + range.x + (hi - 1 - t));
-				s_id[t] = id;
-				const GaussRec* r = rec + id;
-				s_q0[t] = r->q0; s_q1[t] = r->q1; s_q2[t] = r->q2;
-			}
-#pragma unroll
-			for (int q = 0; q < 12; q++) s_acc[t][q] = 0.f;
+	const int rounds = ((int)top + 255) / 256;
+	// batch b covers list positions [hi_b - cnt_b, hi_b), hi_b = top - 256 b; smem slot t <-> position hi_b-1-t
+	auto stage = [&](int b, int buf) {
+		const int hi = (int)top - b * 256;
+		const int t = threadIdx.x;
+		if (t < hi) {
+			const uint32_t id = __ldg(point_list + range.x + (hi - 1 - t));
+			s_id[buf][t] = id;
+			const GaussRec* r = rec + id;
+			cp_async16(&s_rec[buf][t].q0, &r->q0);
+			cp_async16(&s_rec[buf][t].q1, &r->q1);
+			cp_async16(&s_rec[buf][t].q2, &r->q2);
 		}
+		cp_async_commit();
+	};
+	if (rounds > 0) stage(0, 0);
+
+	for (int b = 0; b < rounds; b++) {
+		const int buf = b & 1;
+		const int hi = (int)top - b * 256;
+		const int cnt = min(256, hi);
+		__syncthreads();   // everyone is past batch b-1: buffer buf^1 is free
+		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
+		else cp_async_commit();
+		cp_async_wait<1>();
 		__syncthreads();
-		// smem slot t holds list position hi-1-t: positions >= warp_top are skipped by this warp
+		// positions >= warp_top are skipped by this warp
 		const int first = max(0, hi - (int)warp_top);
 		for (int c0 = first & ~31; c0 < cnt; c0 += 32) {
 			const int t = c0 + lane;
 			bool keep = false;
-			if (t >= first && t < cnt) keep = may_touch(s_q0[t], s_q1[t], bx0, by0, bx1, by1);
+			if (t >= first && t < cnt) keep = may_touch(s_rec[buf][t].q0, s_rec[buf][t].q1, bx0, by0, bx1, by1);
 			unsigned live = __ballot_sync(0xffffffffu, keep);
 			while (live) {
 				const int j = c0 + __ffs(live) - 1;
 				live &= live - 1;
 				const uint32_t e = (uint32_t)(hi - 1 - j);   // 0-based position in the tile list
-				const float4 q0 = s_q0[j];
-				const float4 q1 = s_q1[j];
+				const GaussRec* r = &s_rec[buf][j];
+				const float4 q0 = r->q0;
+				const float4 q1 = r->q1;
 				const float dx = q0.x - pxf, dy = q0.y - pyf;
 				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-				const float G = expf(power);
+				const float G = gsr_exp(power);
 				const float alpha = fminf(0.99f, q1.y * G);
 				const bool valid = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-				if (!__any_sync(0xffffffffu, valid)) continue;
-				const float4 q2 = s_q2[j];
+				const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+				if (vmask == 0) continue;
+				const float4 q2 = r->q2;
 				float v[10];
 #pragma unroll
 				for (int q = 0; q < 10; q++) v[q] = 0.f;
 				if (valid) {
-					const float rcp = 1.f / (1.f - alpha);
+					const float rcp = __fdividef(1.f, 1.f - alpha);
 					T = T * rcp;
-					const float dchannel_dcolor = alpha * T;
-					float dL_dalpha = 0.0f;
-					accum0 = last_alpha * lc0 + (1.f - last_alpha) * accum0; lc0 = q1.w;
-					dL_dalpha += (q1.w - accum0) * dp0;
-					accum1 = last_alpha * lc1 + (1.f - last_alpha) * accum1; lc1 = q2.x;
-					dL_dalpha += (q2.x - accum1) * dp1;
-					accum2 = last_alpha * lc2 + (1.f - last_alpha) * accum2; lc2 = q2.y;
-					dL_dalpha += (q2.y - accum2) * dp2;
-					accumd = last_alpha * last_depth + (1.f - last_alpha) * accumd; last_depth = q1.z;
-					dL_dalpha += (q1.z - accumd) * dpd;
-					dL_dalpha *= T;
+					const float w = alpha * T;     // d(channel)/d(colour)
+					const float sdot = q1.w * dp0 + q2.x * dp1 + q2.y * dp2 + q1.z * dpd;
+					beta = last_alpha * last_s + (1.f - last_alpha) * beta;
+					last_s = sdot;
 					last_alpha = alpha;
-					dL_dalpha += (-T_final * rcp) * bg_dot;
+					const float dL_dalpha = (sdot - beta) * T + (-T_final * rcp) * bg_dot;
 					const float dL_dG = q1.y * dL_dalpha;
 					const float gdx = G * dx, gdy = G * dy;
 					const float dG_ddelx = -gdx * q0.z - gdy * q0.w;
 					const float dG_ddely = -gdy * q1.x - gdx * q0.w;
+					const float hg = -0.5f * dL_dG;
 					v[0] = dL_dG * dG_ddelx * ddelx_dx;
 					v[1] = dL_dG * dG_ddely * ddely_dy;
-					v[2] = -0.5f * gdx * dx * dL_dG;
-					v[3] = -0.5f * gdx * dy * dL_dG;
-					v[4] = -0.5f * gdy * dy * dL_dG;
+					v[2] = hg * gdx * dx;
+					v[3] = hg * gdx * dy;
+					v[4] = hg * gdy * dy;
 					v[5] = G * dL_dalpha;
-					v[6] = dchannel_dcolor * dpd;
-					v[7] = dchannel_dcolor * dp0;
-					v[8] = dchannel_dcolor * dp1;
-					v[9] = dchannel_dcolor * dp2;
+					v[6] = w * dpd;
+					v[7] = w * dp0;
+					v[8] = w * dp1;
+					v[9] = w * dp2;
 				}
-				const float z = reduce10(v, lane);
-				if (my_slot >= 0) atomicAdd(&s_acc[j][my_slot], z);
-			}
-		}
-		__syncthreads();
-		{
-			const int t = threadIdx.x;
-			if (t < cnt) {
-				const float4 a0 = make_float4(s_acc[t][0], s_acc[t][1], s_acc[t][2], s_acc[t][3]);
-				const float4 a1 = make_float4(s_acc[t][4], s_acc[t][5], s_acc[t][6], s_acc[t][7]);
-				const float4 a2 = make_float4(s_acc[t][8], s_acc[t][9], 0.f, 0.f);
-				GaussAcc* dst = acc + s_id[t];
-				if (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f) red_add_v4(&dst->a0, a0);
-				if (a1.x != 0.f || a1.y != 0.f || a1.z != 0.f || a1.w != 0.f) red_add_v4(&dst->a1, a1);
-				if (a2.x != 0.f || a2.y != 0.f) red_add_v4(&dst->a2, a2);
+				GaussAcc* dst = acc + s_id[buf][j];
+				if (__popc(vmask) <= 2) {
+					// sparse pair: the one or two contributing lanes add their terms directly
+					if (valid) {
+						red_add_v4(&dst->a0, make_float4(v[0], v[1], v[2], 0.f));
+						red_add_v4(&dst->a1, make_float4(v[3], v[4], 0.f, 0.f));
+						red_add_v4(&dst->a2, make_float4(v[5], v[6], v[7], 0.f));
+						red_add_v4(&dst->a3, make_float4(v[8], v[9], 0.f, 0.f));
+					}
+				} else {
+					const float4 z = reduce10(v, lane);
+					if ((lane & 7) == 0) red_add_v4(&dst->a0 + (lane >> 3), z);
+				}
 			}
 		}
 	}
+	cp_async_wait<0>();
 }
 
 }  // namespace
