@@ -78,6 +78,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.grid_x = (a->W + GSR_TILE - 1) / GSR_TILE;
 	s.grid_y = (a->H + GSR_TILE - 1) / GSR_TILE;
 	s.prefiltered = a->prefiltered;
+	s.accumulate_grads = a->accumulate_grads;
 	return GSR_OK;
 }
 

@@ -21,6 +21,7 @@ struct Scene {
 	float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
 	int grid_x, grid_y;
 	int prefiltered;
+	int accumulate_grads;
 };
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)

@@ -25,7 +25,7 @@ __device__ const float bSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.
 // SH backward for one Gaussian (backward.cu:21-145).  dRGB already masked by the clamp flags.
 // Writes dL_dsh[0..M) (zeros above the active degree), returns dL/dmean through the view direction.
 __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __restrict__ sh, float3 pos, float3 campos,
-                                              const float dRGB[3], float* __restrict__ dL_dsh)
+                                              const float dRGB[3], float* __restrict__ dL_dsh, bool accumulate)
 {
 	const float3 dir_o = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
 	const float len = sqrtf(dir_o.x * dir_o.x + dir_o.y * dir_o.y + dir_o.z * dir_o.z);
@@ -54,9 +54,15 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __res
 	}
 	for (int i = 0; i < M; i++) {
 		const float wi = i < ncoef ? w[i] : 0.f;
-		dL_dsh[3 * i + 0] = wi * dRGB[0];
-		dL_dsh[3 * i + 1] = wi * dRGB[1];
-		dL_dsh[3 * i + 2] = wi * dRGB[2];
+		if (accumulate) {
+			dL_dsh[3 * i + 0] += wi * dRGB[0];
+			dL_dsh[3 * i + 1] += wi * dRGB[1];
+			dL_dsh[3 * i + 2] += wi * dRGB[2];
+		} else {
+			dL_dsh[3 * i + 0] = wi * dRGB[0];
+			dL_dsh[3 * i + 1] = wi * dRGB[1];
+			dL_dsh[3 * i + 2] = wi * dRGB[2];
+		}
 	}
 	if (deg > 0) {
 #pragma unroll
@@ -273,7 +279,7 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				const float dRGB[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
 				const float3 campos = {s.campos[0], s.campos[1], s.campos[2]};
 				const float3 dm = sh_backward(s.D, s.M, s.shs + (size_t)idx * s.M * 3, make_float3(mx, my, mz), campos, dRGB,
-				                              dL_dsh + (size_t)idx * s.M * 3);
+				                              dL_dsh + (size_t)idx * s.M * 3, s.accumulate_grads != 0);
 				dmean[0] += dm.x; dmean[1] += dm.y; dmean[2] += dm.z;
 				tau[0] += -dm.x; tau[1] += -dm.y; tau[2] += -dm.z;
 			}
@@ -303,20 +309,37 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				drot[2] = 2 * x * (Gm[1][0] + Gm[0][1]) + 2 * r * (Gm[2][0] - Gm[0][2]) + 2 * zq * (Gm[1][2] + Gm[2][1]) - 4 * y * (Gm[2][2] + Gm[0][0]);
 				drot[3] = 2 * r * (Gm[0][1] - Gm[1][0]) + 2 * x * (Gm[2][0] + Gm[0][2]) + 2 * y * (Gm[1][2] + Gm[2][1]) - 4 * zq * (Gm[1][1] + Gm[0][0]);
 			}
-		} else if (s.shs) {
+		} else if (s.shs && !s.accumulate_grads) {
 			for (int i = 0; i < s.M * 3; i++) dL_dsh[(size_t)idx * s.M * 3 + i] = 0.f;
 		}
-		dL_dmeans3D[3 * idx] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
 		dL_dmeans2D[3 * idx] = dm2x; dL_dmeans2D[3 * idx + 1] = dm2y; dL_dmeans2D[3 * idx + 2] = 0.f;
-		dL_dopacity[idx] = dopac;
-		if (dL_dcolors) { dL_dcolors[3 * idx] = dcol[0]; dL_dcolors[3 * idx + 1] = dcol[1]; dL_dcolors[3 * idx + 2] = dcol[2]; }
-		if (s.scales) {
-			dL_dscales[3 * idx] = dscale[0]; dL_dscales[3 * idx + 1] = dscale[1]; dL_dscales[3 * idx + 2] = dscale[2];
-			reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
-		}
-		if (dL_dcov3D_out) {
+		if (!s.accumulate_grads) {
+			dL_dmeans3D[3 * idx] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
+			dL_dopacity[idx] = dopac;
+			if (dL_dcolors) { dL_dcolors[3 * idx] = dcol[0]; dL_dcolors[3 * idx + 1] = dcol[1]; dL_dcolors[3 * idx + 2] = dcol[2]; }
+			if (s.scales) {
+				dL_dscales[3 * idx] = dscale[0]; dL_dscales[3 * idx + 1] = dscale[1]; dL_dscales[3 * idx + 2] = dscale[2];
+				reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+			}
+			if (dL_dcov3D_out) {
 #pragma unroll
-			for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] = dcov[i];
+				for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] = dcov[i];
+			}
+		} else if (visible) {
+			// window accumulation: this thread owns row idx, plain read-modify-write (views run in stream order)
+			dL_dmeans3D[3 * idx] += dmean[0]; dL_dmeans3D[3 * idx + 1] += dmean[1]; dL_dmeans3D[3 * idx + 2] += dmean[2];
+			dL_dopacity[idx] += dopac;
+			if (dL_dcolors) { dL_dcolors[3 * idx] += dcol[0]; dL_dcolors[3 * idx + 1] += dcol[1]; dL_dcolors[3 * idx + 2] += dcol[2]; }
+			if (s.scales) {
+				dL_dscales[3 * idx] += dscale[0]; dL_dscales[3 * idx + 1] += dscale[1]; dL_dscales[3 * idx + 2] += dscale[2];
+				float4 rr = reinterpret_cast<float4*>(dL_drot)[idx];
+				rr.x += drot[0]; rr.y += drot[1]; rr.z += drot[2]; rr.w += drot[3];
+				reinterpret_cast<float4*>(dL_drot)[idx] = rr;
+			}
+			if (dL_dcov3D_out) {
+#pragma unroll
+				for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] += dcov[i];
+			}
 		}
 	}
 

@@ -29,7 +29,7 @@ class GsrScene(C.Structure):
         ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("projmatrix_raw", C.c_void_p), ("campos", C.c_void_p),
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
-        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
     ]
 
 

@@ -9,7 +9,9 @@ loop (utils/slam_frontend.py:163, 100 iterations on one frozen map) or a mapping
     (exact run) with head-room, the kernels read num_rendered on the device, and an overflow flag is
     read back with the results (overflow -> the step is re-run exactly, never silently wrong),
   * captures forward(+backward) into CUDA graphs: one launch per step instead of ~14,
-  * takes the camera as four small device tensors whose contents are replaced in place per step.
+  * takes the camera as one 208-byte device block whose contents are replaced in place per step,
+  * keeps all per-Gaussian parameter gradients in ONE flat buffer (`grad_flat`) so that a keyframe window
+    can accumulate views in place (accumulate=True) and all-reduce a single tensor across GPUs.
 All compute goes through the C-ABI (include/gsr_b200.h); torch only owns memory and streams.
 """
 import ctypes as C
@@ -30,7 +32,7 @@ class RasterEngine:
     def __init__(self, gaussians, image_width, image_height, tanfovx, tanfovy, bg, sh_degree=0, scale_modifier=1.0,
                  device="cuda", headroom=1.25):
         """gaussians: dict with means3D[P,3], opacities[P,1], shs[P,M,3] or colors_precomp[P,3],
-        scales[P,3]+rotations[P,4] or cov3D_precomp[P,6] (fp32 tensors on `device`)."""
+        scales[P,3]+rotations[P,4] or cov3D_precomp[P,6] (fp32 tensors; moved to `device`)."""
         self.dev = torch.device(device)
         f = lambda k: (gaussians[k].to(self.dev, torch.float32).contiguous() if gaussians.get(k) is not None else None)
         self.g = {k: f(k) for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp")}
@@ -48,26 +50,36 @@ class RasterEngine:
         self.bg = torch.as_tensor(bg, dtype=torch.float32).to(self.dev).contiguous()
         # camera block: view(16) | proj(16) | proj_raw(16) | campos(4)  -- one 208-byte H2D per pose
         self.cam = torch.zeros(52, **f32)
-        # outputs
         P, W, H, M = self.P, self.W, self.H, self.M
         self.color = torch.empty((3, H, W), **f32)
         self.depth = torch.empty((1, H, W), **f32)
         self.opacity = torch.empty((1, H, W), **f32)
         self.radii = torch.empty((P,), **i32)
         self.n_touched = torch.empty((P,), **i32)
-        # upstream gradients + gradients
         self.dL_dcolor = torch.zeros((3, H, W), **f32)
         self.dL_ddepth = torch.zeros((1, H, W), **f32)
-        self.g_means3D = torch.empty((P, 3), **f32)
-        self.g_means2D = torch.empty((P, 3), **f32)
-        self.g_opacity = torch.empty((P, 1), **f32)
-        self.g_sh = torch.empty((P, M, 3), **f32) if self.g["shs"] is not None else None
-        self.g_colors = torch.empty((P, 3), **f32) if self.g["colors_precomp"] is not None else None
-        self.g_scales = torch.empty((P, 3), **f32) if self.g["scales"] is not None else None
-        self.g_rot = torch.empty((P, 4), **f32) if self.g["scales"] is not None else None
-        self.g_cov = torch.empty((P, 6), **f32) if self.g["cov3D_precomp"] is not None else None
-        self.g_tau = torch.zeros((6,), **f32)
-        # workspaces
+        # flat per-Gaussian gradient buffer: [means3D 3P | colour part | opacity P | covariance part]
+        ncol = 3 * M if self.g["shs"] is not None else 3
+        ncov = 7 if self.g["scales"] is not None else 6
+        self.grad_flat = torch.zeros(P * (3 + ncol + 1 + ncov) + 32, **f32)   # +32: keeps every segment 16-B aligned
+        o = 0
+
+        def take(n, shape):
+            nonlocal o
+            o = (o + 3) // 4 * 4
+            v = self.grad_flat[o:o + n].view(shape)
+            o += n
+            return v
+
+        self.g_means3D = take(3 * P, (P, 3))
+        self.g_sh = take(3 * M * P, (P, M, 3)) if self.g["shs"] is not None else None
+        self.g_colors = take(3 * P, (P, 3)) if self.g["colors_precomp"] is not None else None
+        self.g_opacity = take(P, (P, 1))
+        self.g_rot = take(4 * P, (P, 4)) if self.g["scales"] is not None else None
+        self.g_scales = take(3 * P, (P, 3)) if self.g["scales"] is not None else None
+        self.g_cov = take(6 * P, (P, 6)) if self.g["cov3D_precomp"] is not None else None
+        self.g_means2D = torch.empty((P, 3), **f32)     # per view (densification statistic), not part of grad_flat
+        self.g_tau = torch.zeros((6,), **f32)           # per view: [rho, theta]
         self.geom_bytes = _L.gsr_geometry_bytes(P)
         self.img_bytes = _L.gsr_image_bytes(W, H)
         self.geom = torch.empty((self.geom_bytes,), **u8)
@@ -83,7 +95,7 @@ class RasterEngine:
         base = self.cam.data_ptr()
         s.viewmatrix, s.projmatrix, s.projmatrix_raw, s.campos = base, base + 64, base + 128, base + 192
         s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
-        s.prefiltered, s.debug = 0, 0
+        s.prefiltered, s.debug, s.accumulate_grads = 0, 0, 0
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.last_num_rendered = None
@@ -117,7 +129,7 @@ class RasterEngine:
         return self.capacity
 
     def calibrate(self):
-        """One exact (synchronising) forward at the current camera to size the binning workspace."""
+        """One exact (synchronising) forward plan at the current camera to size the binning workspace."""
         with torch.cuda.device(self.dev):
             _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
                                             _p(self.n_touched), self._stream()), "forward_plan")
@@ -136,11 +148,19 @@ class RasterEngine:
                                           self.capacity, -1, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
                                           _p(self.opacity), _p(self.n_touched), st), "forward_render")
 
-    def launch_backward(self):
-        _cabi.check(_L.gsr_rasterize_gaussians_backward(
-            C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
-            _p(self.dL_dcolor), _p(self.dL_ddepth), _p(self.g_means3D), _p(self.g_means2D), _p(self.g_sh), _p(self.g_colors),
-            _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov), _p(self.g_tau), self._stream()), "backward")
+    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False):
+        """dL_dcolor / dL_ddepth default to the engine's own buffers; accumulate=True adds this view's
+        per-Gaussian gradients into grad_flat (mapping window) instead of overwriting."""
+        gc = self.dL_dcolor if dL_dcolor is None else dL_dcolor
+        gd = self.dL_ddepth if dL_ddepth is None else dL_ddepth
+        self.scene.accumulate_grads = 1 if accumulate else 0
+        try:
+            _cabi.check(_L.gsr_rasterize_gaussians_backward(
+                C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
+                _p(gc), _p(gd), _p(self.g_means3D), _p(self.g_means2D), _p(self.g_sh), _p(self.g_colors),
+                _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov), _p(self.g_tau), self._stream()), "backward")
+        finally:
+            self.scene.accumulate_grads = 0
 
     def capture(self):
         """Capture forward, backward and forward+backward CUDA graphs over the persistent buffers."""

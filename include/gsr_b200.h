@@ -62,6 +62,11 @@ typedef struct gsr_scene {
 	float tan_fovx, tan_fovy;
 	int prefiltered;
 	int debug;                   /* synchronise + check after every stage (reference CHECK_CUDA) */
+	int accumulate_grads;        /* backward only: ADD into dL_dmeans3D/dL_dsh/dL_dcolors/dL_dopacity/dL_dscales/
+	                                dL_drotations/dL_dcov3D instead of overwriting them (what autograd's AccumulateGrad
+	                                does across the views of a mapping window, utils/slam_backend.py:168-232);
+	                                rows of culled Gaussians are then left untouched.  dL_dmeans2D and dL_dtau are
+	                                per-view quantities and are always overwritten. */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
