@@ -46,22 +46,21 @@ int debug_sync(const gsr_scene* s, cudaStream_t st, const char* where)
 	return check_cuda(where);
 }
 
+size_t tiles_of(int W, int H) { return (size_t)((W + GSR_TILE - 1) / GSR_TILE) * (size_t)((H + GSR_TILE - 1) / GSR_TILE); }
+
 int make_scene(const gsr_scene* a, gsr::Scene& s)
 {
 	if (!a) return fail(GSR_ERR_ARG, "null scene");
 	if (a->P < 0 || a->W <= 0 || a->H <= 0) return fail(GSR_ERR_ARG, "bad P/W/H");
-	if (a->W > 16 * 65535 || a->H > 16 * 65535 || ((a->W + 15) / 16) * (long long)((a->H + 15) / 16) > 65535)
-		return fail(GSR_ERR_ARG, "image too large: tile ids are 16-bit (max 65535 tiles)");
+	if (a->W > 16 * 65535 || a->H > 16 * 65535) return fail(GSR_ERR_ARG, "image too large: tile coordinates are 16-bit");
 	if (a->P > 0) {
 		if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->background)
 			return fail(GSR_ERR_ARG, "means3D, opacities, viewmatrix, projmatrix and background are required");
 		if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
 			return fail(GSR_ERR_ARG, "Please provide excatly one of either SHs or precomputed colors!");
-		const bool sr = a->scales != nullptr && a->rotations != nullptr;
 		if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
 		    ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
 			return fail(GSR_ERR_ARG, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-		(void)sr;
 		if (a->shs && (a->M <= 0 || a->M > 16 || (a->D + 1) * (a->D + 1) > a->M || a->D < 0 || a->D > 3))
 			return fail(GSR_ERR_ARG, "SH degree / coefficient count mismatch");
 		if (a->shs && !a->campos) return fail(GSR_ERR_ARG, "campos is required with SHs");
@@ -82,18 +81,28 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	return GSR_OK;
 }
 
+// shared-memory capacity (list entries) of the per-tile sort for a given longest-tile hint
+int pick_cap_smem(long long max_tile_hint)
+{
+	long long want = max_tile_hint > 0 ? max_tile_hint : 2048;
+	int cap = 1024;
+	while (cap < want && cap < 12288) cap += 1024;
+	return cap;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* gsr_error_string(void) { return g_err; }
-int gsr_version(void) { return 100; }
+int gsr_version(void) { return 101; }
 
-size_t gsr_geometry_bytes(int P) { return gsr::geom_bytes((size_t)(P > 0 ? P : 0)); }
+size_t gsr_geometry_bytes(int P, int W, int H) { return gsr::geom_bytes((size_t)(P > 0 ? P : 0), tiles_of(W, H)); }
 size_t gsr_image_bytes(int W, int H) { return gsr::image_bytes((size_t)W, (size_t)H); }
 size_t gsr_binning_bytes(int P, long long cap)
 {
-	return gsr::binning_bytes((size_t)(P > 0 ? P : 0), (size_t)(cap > 0 ? cap : 0));
+	(void)P;
+	return gsr::binning_bytes((size_t)(cap > 0 ? cap : 0));
 }
 
 int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* radii, int* n_touched, void* stream)
@@ -101,10 +110,11 @@ int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* rad
 	gsr::Scene s;
 	int rc = make_scene(a, s);
 	if (rc) return rc;
-	if (!geom || geom_bytes < gsr::geom_bytes(s.P)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
+	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	if (!geom || geom_bytes < gsr::geom_bytes(s.P, tiles)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
 	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
 	cudaStream_t st = (cudaStream_t)stream;
-	gsr::GeomView g = gsr::geom_view(geom, s.P);
+	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	stage_mark(0, st);
 	gsr::launch_preprocess_forward(s, g, radii, n_touched, st);
 	stage_mark(1, st);
@@ -112,36 +122,38 @@ int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* rad
 	return debug_sync(a, st, "preprocess");
 }
 
-int gsr_forward_num_rendered(void* geom, void* stream, long long* out)
+int gsr_forward_num_rendered(void* geom, void* stream, long long* out, long long* max_tile_out)
 {
 	if (!geom || !out) return fail(GSR_ERR_ARG, "null argument");
-	gsr::GeomView g = gsr::geom_view(geom, 0);
-	unsigned int r = 0;
-	cudaError_t e = cudaMemcpyAsync(&r, &g.hdr->num_rendered, sizeof(r), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	gsr::GeomView g = gsr::geom_view(geom, 0, 0);
+	gsr::GeomHeader h;
+	cudaError_t e = cudaMemcpyAsync(&h, g.hdr, 32, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
 	if (e != cudaSuccess) return fail(GSR_ERR_CUDA, "reading num_rendered: %s", cudaGetErrorString(e));
-	*out = (long long)r;
+	*out = (long long)h.num_rendered;
+	if (max_tile_out) *max_tile_out = (long long)h.max_tile_count;
 	return GSR_OK;
 }
 
 int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t binning_bytes, long long capacity,
-                       long long R_host, void* image, size_t image_bytes, float* out_color, float* out_depth,
-                       float* out_opacity, int* n_touched, void* stream)
+                       long long R_host, long long max_tile_hint, void* image, size_t image_bytes, float* out_color,
+                       float* out_depth, float* out_opacity, int* n_touched, void* stream)
 {
 	gsr::Scene s;
 	int rc = make_scene(a, s);
 	if (rc) return rc;
 	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
 	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
-	if (capacity >= (1ll << 30)) return fail(GSR_ERR_ARG, "more than 2^30 tile instances are not supported");
+	if (capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "more than 2^31 tile instances are not supported");
 	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
-	if (!binning || binning_bytes < gsr::binning_bytes(s.P, (size_t)capacity)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
 	if (!out_color || !out_depth || !out_opacity || (s.P > 0 && !n_touched)) return fail(GSR_ERR_ARG, "null output");
 	cudaStream_t st = (cudaStream_t)stream;
-	gsr::GeomView g = gsr::geom_view(geom, s.P);
-	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
+	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
+	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
-	g_launches += gsr::launch_binning(s, g, b, im, (size_t)capacity, (size_t)(R_host >= 0 ? R_host : capacity), st);
+	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), st);
 	stage_mark(2, st);
 	rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
@@ -154,7 +166,7 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 int gsr_forward_overflowed(void* geom, void* stream, int* overflowed, long long* needed)
 {
 	if (!geom || !overflowed) return fail(GSR_ERR_ARG, "null argument");
-	gsr::GeomView g = gsr::geom_view(geom, 0);
+	gsr::GeomView g = gsr::geom_view(geom, 0, 0);
 	unsigned int h[2] = {0, 0};
 	cudaError_t e = cudaMemcpyAsync(h, g.hdr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
@@ -171,15 +183,16 @@ int gsr_rasterize_gaussians(const gsr_scene* a, void* geom, size_t geom_bytes, v
 	if (!alloc || !binning_out || !R_out) return fail(GSR_ERR_ARG, "null argument");
 	int rc = gsr_forward_plan(a, geom, geom_bytes, radii, n_touched, stream);
 	if (rc) return rc;
-	long long R = 0;
-	rc = gsr_forward_num_rendered(geom, stream, &R);
+	long long R = 0, max_tile = 0;
+	rc = gsr_forward_num_rendered(geom, stream, &R, &max_tile);
 	if (rc) return rc;
 	const size_t bytes = gsr_binning_bytes(a->P, R);
 	void* bin = alloc(user, bytes);
 	if (!bin) return fail(GSR_ERR_WORKSPACE, "binning allocator returned null");
 	*binning_out = bin;
 	*R_out = R;
-	return gsr_forward_render(a, geom, bin, bytes, R, R, image, image_bytes, out_color, out_depth, out_opacity, n_touched, stream);
+	return gsr_forward_render(a, geom, bin, bytes, R, R, max_tile, image, image_bytes, out_color, out_depth, out_opacity,
+	                          n_touched, stream);
 }
 
 int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void* geom, void* binning, long long capacity,
@@ -204,8 +217,9 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 	if (s.shs && !dL_dsh) return fail(GSR_ERR_ARG, "dL_dsh is required with SHs");
 	if (s.scales && (!dL_dscales || !dL_drotations)) return fail(GSR_ERR_ARG, "dL_dscales / dL_drotations required");
 	if (dL_drotations && ((size_t)dL_drotations & 15)) return fail(GSR_ERR_ARG, "dL_drotations must be 16-byte aligned");
-	gsr::GeomView g = gsr::geom_view(geom, s.P);
-	gsr::BinView b = gsr::bin_view(binning, s.P, (size_t)capacity);
+	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
+	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	stage_mark(4, st);
 	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, st);
@@ -257,18 +271,18 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
                        unsigned long long* out)
 {
 	if (!geom || !out) return fail(GSR_ERR_ARG, "null argument");
-	gsr::GeomView g = gsr::geom_view(geom, P);
+	gsr::GeomView g = gsr::geom_view(geom, P, tiles_of(W, H));
 	out[0] = (unsigned long long)g.rec;
 	out[1] = (unsigned long long)g.tiles_touched;
 	out[2] = (unsigned long long)g.clamped;
-	out[3] = out[4] = out[5] = out[6] = 0;
+	out[3] = out[5] = out[6] = 0;
+	out[4] = (unsigned long long)g.ranges;
 	if (binning) {
-		gsr::BinView b = gsr::bin_view(binning, P, (size_t)capacity);
+		gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
 		out[3] = (unsigned long long)b.point_list;
 	}
 	if (image) {
 		gsr::ImageView im = gsr::image_view(image, W, H);
-		out[4] = (unsigned long long)im.ranges;
 		out[5] = (unsigned long long)im.final_T;
 		out[6] = (unsigned long long)im.n_contrib;
 	}

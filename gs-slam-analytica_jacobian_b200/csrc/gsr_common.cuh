@@ -37,9 +37,10 @@ struct GeomHeader {
 	unsigned int num_rendered;   // R = sum of tiles touched
 	unsigned int overflow;       // set when R exceeded the binning capacity handed to stage B
 	unsigned int num_visible;    // Gaussians with radii > 0
-	unsigned int ticket[8];      // dynamic tile tickets of the sort / emit passes
+	unsigned int fwd_blocks_done;
 	unsigned int bwd_blocks_done;
-	unsigned int pad[64 - 12];
+	unsigned int max_tile_count; // longest per-tile list
+	unsigned int pad[64 - 6];
 };
 static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");
 
@@ -48,107 +49,73 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a = GSR_ALIGN) { ret
 // Geometry workspace (one per forward call, kept for the backward):
 struct GeomView {
 	GeomHeader* hdr;
+	uint32_t* tile_count;    // [tiles]  instances per tile (integer REDs in the preprocess); zeroed with the header
+	uint32_t* tile_cursor;   // [tiles]  write cursor of the scatter pass (starts at ranges[tile].x)
+	uint2* ranges;           // [tiles]  (start, end) of every tile's list inside point_list
 	GaussRec* rec;           // [P]
 	GaussAcc* acc;           // [P]   zeroed by the forward preprocess, consumed+cleared by backward
 	uint32_t* tiles_touched; // [P]
-	uint32_t* depth_key;     // [P]   float bits of view depth, 0x7F800000 when culled
 	uint8_t* clamped;        // [P]   bit ch set when SH colour channel ch was clamped at 0
 	float* tau_partial;      // [ceil(P/256) * 8] per-block pose-gradient partials
 };
 
-__host__ __device__ inline size_t geom_bytes(size_t P)
+__host__ __device__ inline size_t geom_bytes(size_t P, size_t tiles)
 {
 	size_t s = sizeof(GeomHeader);
+	s += align_up(tiles * 4) * 2 + align_up(tiles * 8);
 	s += align_up(P * sizeof(GaussRec));
 	s += align_up(P * sizeof(GaussAcc));
-	s += align_up(P * 4);
 	s += align_up(P * 4);
 	s += align_up(P);
 	s += align_up(((P + 255) / 256) * 8 * sizeof(float));
 	return s + GSR_ALIGN;
 }
 
-__host__ __device__ inline GeomView geom_view(void* base, size_t P)
+__host__ __device__ inline GeomView geom_view(void* base, size_t P, size_t tiles)
 {
 	char* p = (char*)align_up((size_t)base);
 	GeomView g;
 	g.hdr = (GeomHeader*)p; p += sizeof(GeomHeader);
+	g.tile_count = (uint32_t*)p; p += align_up(tiles * 4);      // directly behind the header: one memset clears both
+	g.tile_cursor = (uint32_t*)p; p += align_up(tiles * 4);
+	g.ranges = (uint2*)p; p += align_up(tiles * 8);
 	g.rec = (GaussRec*)p; p += align_up(P * sizeof(GaussRec));
 	g.acc = (GaussAcc*)p; p += align_up(P * sizeof(GaussAcc));
 	g.tiles_touched = (uint32_t*)p; p += align_up(P * 4);
-	g.depth_key = (uint32_t*)p; p += align_up(P * 4);
 	g.clamped = (uint8_t*)p; p += align_up(P);
 	g.tau_partial = (float*)p;
 	return g;
 }
 
-// Image workspace: final transmittance, last contributor, per-tile ranges.
+// Image workspace: final transmittance and last contributor of every pixel.
 struct ImageView {
 	float* final_T;      // [H*W]
 	uint32_t* n_contrib; // [H*W]
-	uint2* ranges;       // [tiles]
 };
-__host__ __device__ inline size_t image_bytes(size_t W, size_t H)
-{
-	size_t tiles = ((W + 15) / 16) * ((H + 15) / 16);
-	return align_up(W * H * 4) * 2 + align_up(tiles * 8) + GSR_ALIGN;
-}
+__host__ __device__ inline size_t image_bytes(size_t W, size_t H) { return align_up(W * H * 4) * 2 + GSR_ALIGN; }
 __host__ __device__ inline ImageView image_view(void* base, size_t W, size_t H)
 {
 	char* p = (char*)align_up((size_t)base);
 	ImageView v;
 	v.final_T = (float*)p; p += align_up(W * H * 4);
-	v.n_contrib = (uint32_t*)p; p += align_up(W * H * 4);
-	v.ranges = (uint2*)p;
+	v.n_contrib = (uint32_t*)p;
 	return v;
 }
 
 // Binning workspace.  point_list[R] is the product (kept for the backward); the rest is scratch.
-#define GSR_SORT_THREADS 256
-#define GSR_SORT_ITEMS 8
-#define GSR_SORT_TILE (GSR_SORT_THREADS * GSR_SORT_ITEMS)
-
 struct BinView {
-	uint32_t* point_list;     // [R]  Gaussian ids sorted by (tile, depth)        <- kept
-	uint32_t* inst_val_alt;   // [R]  ping-pong partner of point_list
-	uint16_t* inst_tile;      // [R]  tile id of every instance (ping)
-	uint16_t* inst_tile_alt;  // [R]  (pong)
-	uint32_t* gkey_alt;       // [P]  depth-key pong
-	uint32_t* order;          // [P]  Gaussian ids in depth order (ping)
-	uint32_t* order_alt;      // [P]
-	uint32_t* hist;           // [6][256] global digit histograms: 4 depth passes, 2 tile passes
-	uint32_t* lookback;       // decoupled look-back status words, zeroed every forward
-	size_t lookback_words;
-	uint32_t* emit_status;    // [ceil(P/256)] look-back words of the scan+emit kernel (part of lookback block)
+	uint32_t* point_list;   // [R]  Gaussian ids sorted by (tile, depth, id)        <- kept
+	uint2* pairs;           // [R]  (depth key, Gaussian id) scattered into tile segments, unordered inside a segment
+	uint2* pairs_alt;       // [R]  ping-pong partner for tiles too long to sort in shared memory
 };
-__host__ __device__ inline size_t sort_tiles(size_t n) { return (n + GSR_SORT_TILE - 1) / GSR_SORT_TILE; }
-__host__ __device__ inline size_t lookback_words(size_t P, size_t R)
-{
-	// 4 depth passes + 2 tile passes, 256 words per sort tile, + emit status + histograms
-	return 4 * sort_tiles(P) * 256 + 2 * sort_tiles(R) * 256 + align_up((P + 255) / 256, 64) + 6 * 256;
-}
-__host__ __device__ inline size_t binning_bytes(size_t P, size_t R)
-{
-	size_t s = 0;
-	s += 2 * align_up(R * 4) + 2 * align_up(R * 2) + 3 * align_up(P * 4);
-	s += align_up(lookback_words(P, R) * 4);
-	return s + GSR_ALIGN;
-}
-__host__ __device__ inline BinView bin_view(void* base, size_t P, size_t R)
+__host__ __device__ inline size_t binning_bytes(size_t R) { return align_up(R * 4) + 2 * align_up(R * 8) + GSR_ALIGN; }
+__host__ __device__ inline BinView bin_view(void* base, size_t R)
 {
 	char* p = (char*)align_up((size_t)base);
 	BinView b;
 	b.point_list = (uint32_t*)p; p += align_up(R * 4);
-	b.inst_val_alt = (uint32_t*)p; p += align_up(R * 4);
-	b.inst_tile = (uint16_t*)p; p += align_up(R * 2);
-	b.inst_tile_alt = (uint16_t*)p; p += align_up(R * 2);
-	b.gkey_alt = (uint32_t*)p; p += align_up(P * 4);
-	b.order = (uint32_t*)p; p += align_up(P * 4);
-	b.order_alt = (uint32_t*)p; p += align_up(P * 4);
-	b.lookback_words = lookback_words(P, R);
-	b.hist = (uint32_t*)p;                 // first 6*256 words of the zeroed block
-	b.emit_status = b.hist + 6 * 256;
-	b.lookback = b.emit_status + align_up((P + 255) / 256, 64);
+	b.pairs = (uint2*)p; p += align_up(R * 8);
+	b.pairs_alt = (uint2*)p;
 	return b;
 }
 
@@ -164,32 +131,24 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
+// Row index i / w inside a tile rectangle without a per-instance integer division: the owning lane computes
+// magic = ceil(2^32 / w) once per Gaussian; umulhi(i, magic) == i / w whenever i * w < 2^32 (guarded by n * w).
+__device__ __forceinline__ uint32_t rect_magic(uint32_t w, uint32_t n)
+{
+	if (w < 2 || (unsigned long long)n * w >= (1ull << 32)) return 0;
+	return (uint32_t)(((1ull << 32) + w - 1) / w);
+}
+__device__ __forceinline__ uint32_t rect_row(uint32_t i, uint32_t w, uint32_t magic)
+{
+	if (w == 1) return i;
+	return magic ? __umulhi(i, magic) : i / w;
+}
+
 // vector reduction to global memory: one 16-byte RED instead of four scalar atomics (sm_90+)
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
 	             : "memory");
-}
-
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
-{
-	uint32_t v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
-{
-	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
-{
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
-{
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // cp.async 16-byte global->shared (LDGSTS), used to stage gathered Gaussian records

@@ -26,8 +26,9 @@ struct Scene {
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
-int launch_binning(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, size_t R_capacity,
-                   size_t R_bound, cudaStream_t stream);   // returns the number of kernels launched
+// returns the number of kernels launched; cap_smem = longest tile list sorted in shared memory
+int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, cudaStream_t stream);
+size_t tile_sort_smem_bytes(int cap_smem);
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, cudaStream_t stream);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,

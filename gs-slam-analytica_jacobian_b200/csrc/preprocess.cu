@@ -100,16 +100,21 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 }
 
 __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomView g, int* __restrict__ radii,
-                                                                 int* __restrict__ n_touched, int vec_mask)
+                                                                 int* __restrict__ n_touched, int vec_mask, int hist_smem)
 {
 	__shared__ __align__(16) float s_mean[768];
 	__shared__ __align__(16) float s_scale[768];
 	__shared__ __align__(16) float s_col[768];
 	__shared__ float s_view[16], s_proj[16];
 	__shared__ unsigned s_red[16];
+	__shared__ bool s_last;
+	extern __shared__ uint32_t s_hist[];   // [tiles] CTA-private tile histogram (hist_smem != 0)
 
 	const int row0 = blockIdx.x * 256;
 	const int idx = row0 + threadIdx.x;
+	const int n_tiles = s.grid_x * s.grid_y;
+	if (hist_smem)
+		for (int t = threadIdx.x; t < n_tiles; t += 256) s_hist[t] = 0;
 	if (threadIdx.x < 16) {
 		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
 		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
@@ -120,10 +125,9 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	if (dc_only) load_rows3(s.colors_precomp ? s.colors_precomp : s.shs, row0, s.P, s_col, vec_mask & 4);
 	__syncthreads();
 
-	unsigned my_tiles = 0, my_vis = 0;
+	unsigned my_tiles = 0, my_vis = 0, rect_lo = 0, rect_hi = 0;
 	if (idx < s.P) {
 		int out_radius = 0;
-		uint32_t key = 0x7F800000u;
 		GaussRec rec;
 		rec.q0 = make_float4(0.f, 0.f, 0.f, 0.f); rec.q1 = rec.q0; rec.q2 = rec.q0;
 		unsigned clamped = 0;
@@ -225,11 +229,11 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 					out_radius = mr;
 					my_tiles = area;
 					my_vis = 1;
-					key = __float_as_uint(depth);
+					rect_lo = rminx | (rminy << 16);
+					rect_hi = rmaxx | (rmaxy << 16);
 					rec.q0 = make_float4(pix_x, pix_y, conic.x, conic.y);
 					rec.q1 = make_float4(conic.z, __ldg(s.opacities + idx), depth, rgb.x);
-					rec.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(rminx | (rminy << 16)),
-					                     __uint_as_float(rmaxx | (rmaxy << 16)));
+					rec.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(rect_lo), __uint_as_float(rect_hi));
 				}
 			}
 		} else if (s.prefiltered) {
@@ -242,8 +246,35 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
 		g.acc[idx] = z;
 		g.tiles_touched[idx] = my_tiles;
-		g.depth_key[idx] = key;
 		g.clamped[idx] = (uint8_t)clamped;
+	}
+	// per-tile instance counts: the warp walks its visible Gaussians, 32 tiles per step (integer REDs)
+	{
+		unsigned live = __ballot_sync(0xffffffffu, my_tiles != 0);
+		const unsigned lane = lane_id();
+		const unsigned my_magic = rect_magic((rect_hi & 0xffff) - (rect_lo & 0xffff), my_tiles);
+		while (live) {
+			const int src = __ffs(live) - 1;
+			live &= live - 1;
+			const unsigned lo = __shfl_sync(0xffffffffu, rect_lo, src), hi = __shfl_sync(0xffffffffu, rect_hi, src);
+			const unsigned n = __shfl_sync(0xffffffffu, my_tiles, src);
+			const unsigned magic = __shfl_sync(0xffffffffu, my_magic, src);
+			const unsigned x0 = lo & 0xffff, y0 = lo >> 16, w = (hi & 0xffff) - x0;
+			for (unsigned i = lane; i < n; i += 32) {
+				const unsigned ty = rect_row(i, w, magic), tx = i - ty * w;
+				const unsigned tile = (y0 + ty) * s.grid_x + (x0 + tx);
+				if (hist_smem) atomicAdd(&s_hist[tile], 1u);
+				else atomicAdd(&g.tile_count[tile], 1u);
+			}
+		}
+	}
+	if (hist_smem) {
+		// one coalesced RED per touched tile and CTA instead of one scattered RED per instance
+		__syncthreads();
+		for (int t = threadIdx.x; t < n_tiles; t += 256) {
+			const unsigned c = s_hist[t];
+			if (c) atomicAdd(&g.tile_count[t], c);
+		}
 	}
 	// block totals -> header (integer atomics: deterministic)
 	unsigned wt = my_tiles, wv = my_vis;
@@ -253,6 +284,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		wv += __shfl_xor_sync(0xffffffffu, wv, o);
 	}
 	if (lane_id() == 0) { s_red[threadIdx.x >> 5] = wt; s_red[8 + (threadIdx.x >> 5)] = wv; }
+	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned a = 0, b = 0;
@@ -260,6 +292,41 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		for (int w = 0; w < 8; w++) { a += s_red[w]; b += s_red[8 + w]; }
 		if (a) atomicAdd(&g.hdr->num_rendered, a);
 		if (b) atomicAdd(&g.hdr->num_visible, b);
+		__threadfence();
+		s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!s_last) return;
+	// The last CTA to finish turns the tile counts into list ranges + scatter cursors (exclusive scan over
+	// the tiles).  Untouched tiles keep the range (0,0) like the reference's memset (rasterizer_impl.cu:360).
+	__threadfence();
+	{
+		const int tiles = s.grid_x * s.grid_y;
+		const int per = (tiles + 255) / 256;
+		const int t0 = min(tiles, (int)threadIdx.x * per), t1 = min(tiles, t0 + per);
+		unsigned sum = 0;
+		for (int t = t0; t < t1; t++) sum += __ldcg(&g.tile_count[t]);
+		unsigned inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane_id() >= o) inc += v;
+		}
+		__syncthreads();
+		if (lane_id() == 31) s_red[threadIdx.x >> 5] = inc;
+		__syncthreads();
+		unsigned run = inc - sum;
+		for (int w = 0; w < (int)(threadIdx.x >> 5); w++) run += s_red[w];
+		unsigned mx = 0;
+		for (int t = t0; t < t1; t++) {
+			const unsigned c = __ldcg(&g.tile_count[t]);
+			g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+			g.tile_cursor[t] = run;
+			run += c;
+			mx = max(mx, c);
+		}
+		if (mx) atomicMax(&g.hdr->max_tile_count, mx);
+		if (threadIdx.x == 0) g.hdr->fwd_blocks_done = 0;
 	}
 }
 
@@ -279,11 +346,19 @@ static inline bool aligned16(const void* p) { return ((size_t)p & 15) == 0; }
 
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream)
 {
-	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), stream);
-	if (s.P == 0) return;
+	// header and the per-tile counters behind it are cleared together
+	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader) + (size_t)s.grid_x * s.grid_y * sizeof(uint32_t), stream);
+	if (s.P == 0) {
+		cudaMemsetAsync(g.ranges, 0, (size_t)s.grid_x * s.grid_y * sizeof(uint2), stream);
+		return;
+	}
 	int vec_mask = (aligned16(s.means3D) ? 1 : 0) | (aligned16(s.scales) ? 2 : 0) |
 	               (aligned16(s.colors_precomp ? s.colors_precomp : s.shs) ? 4 : 0);
-	preprocess_forward_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, g, radii, n_touched, vec_mask);
+	// CTA-private tile histogram in shared memory while it fits next to the static arrays (<= 8192 tiles, e.g. 1920x1080)
+	const int tiles = s.grid_x * s.grid_y;
+	const int hist_smem = tiles <= 8192 ? 1 : 0;
+	preprocess_forward_kernel<<<(s.P + 255) / 256, 256, hist_smem ? tiles * sizeof(uint32_t) : 0, stream>>>(
+		s, g, radii, n_touched, vec_mask, hist_smem);
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present, cudaStream_t stream)

@@ -135,7 +135,7 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 {
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
-	render_forward_kernel<<<tiles, 256, 0, stream>>>(im.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
+	render_forward_kernel<<<tiles, 256, 0, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
 	                                                  im.final_T, im.n_contrib, out_color, out_depth, out_opacity, n_touched);
 }
 

@@ -239,7 +239,7 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 		cudaFuncSetAttribute(render_backward_kernel<NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured = true;
 	}
-	render_backward_kernel<NSLOT><<<tiles, 256, smem, stream>>>(im.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
+	render_backward_kernel<NSLOT><<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
 	                                                            im.final_T, im.n_contrib, dL_dpix, dL_dpix_depth, g.acc);
 }
 

@@ -86,7 +86,7 @@ def _forward_impl(call, capacity=None):
         color.zero_(); depth.zero_(); opacity.zero_()
         e = torch.empty((0,), **u8)
         return 0, 0, color, radii, e, e, e, depth, opacity, n_touched
-    geom_bytes = _L.gsr_geometry_bytes(P)
+    geom_bytes = _L.gsr_geometry_bytes(P, W, H)
     img_bytes = _L.gsr_image_bytes(W, H)
     geom = torch.empty((geom_bytes,), **u8)
     img = torch.empty((img_bytes,), **u8)
@@ -94,14 +94,15 @@ def _forward_impl(call, capacity=None):
     with torch.cuda.device(dev):
         _cabi.check(_L.gsr_forward_plan(C.byref(call.scene), _ptr(geom), geom_bytes, _ptr(radii), _ptr(n_touched), st), "forward_plan")
         if capacity is None:
-            R = C.c_longlong(0)
-            _cabi.check(_L.gsr_forward_num_rendered(_ptr(geom), st, C.byref(R)), "forward_num_rendered")
+            R, mt = C.c_longlong(0), C.c_longlong(0)
+            _cabi.check(_L.gsr_forward_num_rendered(_ptr(geom), st, C.byref(R), C.byref(mt)), "forward_num_rendered")
             num_rendered = cap = int(R.value)
+            max_tile = int(mt.value)
         else:
-            num_rendered, cap = -1, int(capacity)
+            num_rendered, cap, max_tile = -1, int(capacity), 0
         bin_bytes = _L.gsr_binning_bytes(P, cap)
         binning = torch.empty((bin_bytes,), **u8)
-        _cabi.check(_L.gsr_forward_render(C.byref(call.scene), _ptr(geom), _ptr(binning), bin_bytes, cap, num_rendered,
+        _cabi.check(_L.gsr_forward_render(C.byref(call.scene), _ptr(geom), _ptr(binning), bin_bytes, cap, num_rendered, max_tile,
                                           _ptr(img), img_bytes, _ptr(color), _ptr(depth), _ptr(opacity), _ptr(n_touched), st),
                     "forward_render")
     return num_rendered, cap, color, radii, geom, binning, img, depth, opacity, n_touched

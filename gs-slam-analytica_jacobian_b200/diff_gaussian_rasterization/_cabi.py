@@ -63,14 +63,14 @@ def load():
     vp, sz, ll, ip = C.c_void_p, C.c_size_t, C.c_longlong, C.c_int
     sp = C.POINTER(GsrScene)
     lib.gsr_geometry_bytes.restype = sz
-    lib.gsr_geometry_bytes.argtypes = [ip]
+    lib.gsr_geometry_bytes.argtypes = [ip, ip, ip]
     lib.gsr_image_bytes.restype = sz
     lib.gsr_image_bytes.argtypes = [ip, ip]
     lib.gsr_binning_bytes.restype = sz
     lib.gsr_binning_bytes.argtypes = [ip, ll]
     lib.gsr_forward_plan.argtypes = [sp, vp, sz, vp, vp, vp]
-    lib.gsr_forward_num_rendered.argtypes = [vp, vp, C.POINTER(ll)]
-    lib.gsr_forward_render.argtypes = [sp, vp, vp, sz, ll, ll, vp, sz, vp, vp, vp, vp, vp]
+    lib.gsr_forward_num_rendered.argtypes = [vp, vp, C.POINTER(ll), C.POINTER(ll)]
+    lib.gsr_forward_render.argtypes = [sp, vp, vp, sz, ll, ll, ll, vp, sz, vp, vp, vp, vp, vp]
     lib.gsr_forward_overflowed.argtypes = [vp, vp, C.POINTER(ip), C.POINTER(ll)]
     lib.gsr_rasterize_gaussians.argtypes = [sp, vp, sz, vp, sz, ALLOC_FN, vp, C.POINTER(vp), C.POINTER(ll),
                                             vp, vp, vp, vp, vp, vp]

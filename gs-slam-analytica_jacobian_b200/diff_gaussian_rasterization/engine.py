@@ -80,11 +80,12 @@ class RasterEngine:
         self.g_cov = take(6 * P, (P, 6)) if self.g["cov3D_precomp"] is not None else None
         self.g_means2D = torch.empty((P, 3), **f32)     # per view (densification statistic), not part of grad_flat
         self.g_tau = torch.zeros((6,), **f32)           # per view: [rho, theta]
-        self.geom_bytes = _L.gsr_geometry_bytes(P)
+        self.geom_bytes = _L.gsr_geometry_bytes(P, W, H)
         self.img_bytes = _L.gsr_image_bytes(W, H)
         self.geom = torch.empty((self.geom_bytes,), **u8)
         self.img = torch.empty((self.img_bytes,), **u8)
         self.capacity = 0
+        self.max_tile_hint = 0
         self.bin_bytes = 0
         self.binning = None
         s = GsrScene()
@@ -133,9 +134,13 @@ class RasterEngine:
         with torch.cuda.device(self.dev):
             _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
                                             _p(self.n_touched), self._stream()), "forward_plan")
-            R = C.c_longlong(0)
-            _cabi.check(_L.gsr_forward_num_rendered(_p(self.geom), self._stream(), C.byref(R)), "num_rendered")
+            R, mt = C.c_longlong(0), C.c_longlong(0)
+            _cabi.check(_L.gsr_forward_num_rendered(_p(self.geom), self._stream(), C.byref(R), C.byref(mt)), "num_rendered")
         self.last_num_rendered = int(R.value)
+        hint = int(mt.value * self.headroom) + 64      # longest per-tile list -> smem capacity of the tile sort
+        if hint > self.max_tile_hint:
+            self.max_tile_hint = hint
+            self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.ensure_capacity(R.value)
         return int(R.value)
 
@@ -145,7 +150,7 @@ class RasterEngine:
         _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
                                         _p(self.n_touched), st), "forward_plan")
         _cabi.check(_L.gsr_forward_render(C.byref(self.scene), _p(self.geom), _p(self.binning), self.bin_bytes,
-                                          self.capacity, -1, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
+                                          self.capacity, -1, self.max_tile_hint, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
                                           _p(self.opacity), _p(self.n_touched), st), "forward_render")
 
     def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False):

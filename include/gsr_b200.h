@@ -73,21 +73,25 @@ typedef struct gsr_scene {
 typedef void* (*gsr_alloc_fn)(void* user, size_t bytes);
 
 /* ---- workspace sizes (reference: required<GeometryState/ImageState/BinningState>) ---- */
-size_t gsr_geometry_bytes(int P);
+size_t gsr_geometry_bytes(int P, int W, int H);
 size_t gsr_image_bytes(int W, int H);
 size_t gsr_binning_bytes(int P, long long num_rendered_capacity);
 
 /* ---- forward ---- */
-/* Stage A: per-Gaussian preprocess (+ tile counts, depth keys).  Writes radii[P] and zero-fills
- * n_touched[P]; leaves num_rendered in the geometry workspace on the device. */
+/* Stage A: per-Gaussian preprocess, per-tile instance counts and tile ranges.  Writes radii[P] and
+ * zero-fills n_touched[P]; leaves num_rendered in the geometry workspace on the device. */
 int gsr_forward_plan(const gsr_scene* s, void* geom, size_t geom_bytes, int* radii, int* n_touched, void* stream);
-/* Blocks until stage A is done and returns num_rendered (the reference's only host sync). */
-int gsr_forward_num_rendered(void* geom, void* stream, long long* num_rendered_host);
+/* Blocks until stage A is done and returns num_rendered (the reference's only host sync) and, if
+ * max_tile_host is not null, the length of the longest per-tile list. */
+int gsr_forward_num_rendered(void* geom, void* stream, long long* num_rendered_host, long long* max_tile_host);
 /* Stage B: binning + compositing.  `num_rendered_host` >= 0: the exact count read with
  * gsr_forward_num_rendered;  < 0: unknown -- the kernels read it from the device and the call needs no
- * host synchronisation at all; gsr_forward_overflowed() must then be checked before results are used. */
+ * host synchronisation at all; gsr_forward_overflowed() must then be checked before results are used.
+ * `max_tile_hint`: expected longest per-tile list (sizes the shared memory of the per-tile sort; longer
+ * tiles still sort correctly through global memory); <= 0 = default. */
 int gsr_forward_render(const gsr_scene* s, void* geom, void* binning, size_t binning_bytes,
-                       long long binning_capacity, long long num_rendered_host, void* image, size_t image_bytes,
+                       long long binning_capacity, long long num_rendered_host, long long max_tile_hint,
+                       void* image, size_t image_bytes,
                        float* out_color /*[3,H,W]*/, float* out_depth /*[1,H,W]*/, float* out_opacity /*[1,H,W]*/,
                        int* n_touched /*[P]*/, void* stream);
 /* Synchronises and reports whether the last no-sync forward ran out of binning capacity

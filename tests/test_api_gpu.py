@@ -147,7 +147,7 @@ def test_cabi_one_call_with_allocator_callback():
     color, depth, opacity = torch.empty((3, H, W), **f32), torch.empty((1, H, W), **f32), torch.empty((1, H, W), **f32)
     radii = torch.empty(P, dtype=torch.int32, device="cuda")
     n_touched = torch.empty(P, dtype=torch.int32, device="cuda")
-    gb, ib = L.gsr_geometry_bytes(P), L.gsr_image_bytes(W, H)
+    gb, ib = L.gsr_geometry_bytes(P, W, H), L.gsr_image_bytes(W, H)
     geom = torch.empty(gb, dtype=torch.uint8, device="cuda")
     img = torch.empty(ib, dtype=torch.uint8, device="cuda")
     keep = []
