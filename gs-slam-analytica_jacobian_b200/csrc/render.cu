@@ -8,15 +8,68 @@
 // Work skipping that does not change results: a (pixel, Gaussian) pair only matters when
 // alpha = min(0.99, o*exp(-q)) >= 1/255, i.e. q <= ln(255 o).  For every chunk of 32 list entries the
 // 32 lanes test one entry each against the warp's pixel block (exact minimum of the convex quadratic q
-// over the 8x4 rectangle, with a conservative margin) and ballot; the warp then evaluates only the
-// survivors (typically < 1/3 of the entries) with the reference's per-pair decisions.
-// Every per-pair decision is predicated, so the warp stays converged and can vote its own early
-// termination (warp ballot) and aggregate the n_touched integer atomics to one RED per chunk and warp.
+// over the 8x4 rectangle, with a conservative margin), ballot, and COMPACT the survivors (typically < 1/3
+// of the entries) in list order into a warp-private shared-memory queue.  The pixel threads then run a
+// branch-free, two-way unrolled loop over the queue with the reference's per-pair decisions:
+//   * every record is three broadcast LDS.128 at immediate offsets (no per-entry bit scan / address math),
+//   * the exponent keeps the reference's expression tree (bit-identical power), exp is one ex2.approx.ftz,
+//   * "done" is carried in the sign of T (T < 0 <=> this pixel stopped; |T| is its final transmittance), so the
+//     three per-pair tests of the reference collapse into compares whose results are used as predicates,
+//   * n_touched (pixels whose transmittance after the blend is still > 0.5, forward.cu:511-514) costs one vote +
+//     one predicated store per entry while any pixel of the warp is above 0.5, nothing afterwards, and ONE
+//     integer RED per (warp, Gaussian).
 #include "render_common.cuh"
 
 namespace gsr {
 
 namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct FwdSmem {
+	GaussRec rec[2][256];
+	uint32_t id[2][256];
+	QueueRec queue[8][34];      // per warp: <= 32 survivors of a chunk + one padding record for the 2-way unroll
+	uint32_t tmask[8][32];      // per warp and queue slot: ballot of "still above 0.5 after this blend"
+};
+
+template <bool COUNT_TOUCHED>
+__device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int n, float pxf, float pyf, float& T, float& C0,
+                                            float& C1, float& C2, float& D, int& last, uint32_t* __restrict__ tmask, int lane)
+{
+	for (int k = 0; k < n; k += 2) {
+#pragma unroll
+		for (int u = 0; u < 2; u++) {
+			const QueueRec* r = q + k + u;
+			const float4 w0 = r->w0;
+			const float4 w1 = r->w1;
+			const float4 w2 = r->w2;
+			const float dx = w0.x - pxf, dy = w0.y - pyf;
+			const float power = falloff_power(w0.z, w0.w, w1.x, dx, dy);
+			const float alpha = fminf(0.99f, w1.y * gsr_exp(power));
+			const float test_T = T * (1.0f - alpha);
+			// reference order (forward.cu:481-507): skip if power > 0, skip if alpha < 1/255, stop if test_T < 1e-4.
+			// A stopped pixel has T < 0, hence test_T < 0: it can only re-enter the "stop" arm, which is idempotent.
+			const bool live = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+			const bool stop = live && (test_T < 0.0001f);
+			const bool valid = live && !(test_T < 0.0001f);
+			if (COUNT_TOUCHED) {
+				const unsigned touched = __ballot_sync(kFull, valid && test_T > 0.5f);
+				if (lane == 0) tmask[k + u] = touched;
+			}
+			const float w = alpha * T;
+			if (valid) {
+				C0 += w1.z * w;
+				C1 += w1.w * w;
+				C2 += w2.x * w;
+				D += w2.y * w;
+				T = test_T;
+				last = __float_as_int(w2.z);
+			}
+			if (stop) T = -fabsf(T);
+		}
+	}
+}
 
 __global__ void __launch_bounds__(256)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -24,12 +77,12 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched)
 {
-	__shared__ GaussRec s_rec[2][256];
-	__shared__ uint32_t s_id[2][256];
+	__shared__ FwdSmem sm;
 
 	const int tile = blockIdx.x;
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
 	int px, py;
 	pixel_of_thread(tile_x, tile_y, px, py);
 	const bool inside = px < W && py < H;
@@ -39,23 +92,24 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 	const uint2 range = ranges[tile];
 	const int n = (int)(range.y - range.x);
 	const int rounds = (n + 255) / 256;
+	QueueRec* wq = sm.queue[warp];
+	uint32_t* wmask = sm.tmask[warp];
 
-	bool done = !inside;
-	float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-	uint32_t last_contributor = 0;
-	// n_touched counts pixels whose transmittance after the blend is still > 0.5 (forward.cu:511-514).
-	// T only decreases, so once no live lane of the warp is above 0.5 the bookkeeping is skipped for good.
-	bool warp_hi_T = __any_sync(0xffffffffu, inside);
+	float T = inside ? 1.0f : -1.0f;   // sign bit = "done"
+	float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+	int last = -1;                     // list position of the last blended entry
+	// T only decreases, so once no live pixel of the warp is above 0.5 the n_touched bookkeeping is skipped for good.
+	bool warp_hi_T = __any_sync(kFull, inside);
 
 	auto stage = [&](int b, int buf) {
 		const int i = b * 256 + threadIdx.x;
 		if (i < n) {
 			const uint32_t id = __ldg(point_list + range.x + i);
-			s_id[buf][threadIdx.x] = id;
+			sm.id[buf][threadIdx.x] = id;
 			const GaussRec* r = rec + id;
-			cp_async16(&s_rec[buf][threadIdx.x].q0, &r->q0);
-			cp_async16(&s_rec[buf][threadIdx.x].q1, &r->q1);
-			cp_async16(&s_rec[buf][threadIdx.x].q2, &r->q2);
+			cp_async16(&sm.rec[buf][threadIdx.x].q0, &r->q0);
+			cp_async16(&sm.rec[buf][threadIdx.x].q1, &r->q1);
+			cp_async16(&sm.rec[buf][threadIdx.x].q2, &r->q2);
 		}
 		cp_async_commit();
 	};
@@ -63,63 +117,59 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
 	for (int b = 0; b < rounds; b++) {
 		const int buf = b & 1;
-		if (__syncthreads_and(done)) break;   // also: everyone is past batch b-1, buffer buf^1 is free
+		if (__syncthreads_and(T < 0.f)) break;   // also: everyone is past batch b-1, buffer buf^1 is free
 		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
 		else cp_async_commit();
 		cp_async_wait<1>();
 		__syncthreads();
 		const int cnt = min(256, n - b * 256);
-		int last_local = -1;
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
-			if (__all_sync(0xffffffffu, done)) break;
+			if (__all_sync(kFull, T < 0.f)) break;
 			// cull phase: one list entry per lane
 			const int e = c0 + lane;
 			bool keep = false;
-			if (e < cnt) keep = may_touch(s_rec[buf][e].q0, s_rec[buf][e].q1, bx0, by0, bx1, by1);
-			unsigned live = __ballot_sync(0xffffffffu, keep);
-			int my_touched = 0;   // lane L accumulates the n_touched increment of entry c0 + L
-			while (live) {
-				const int jl = __ffs(live) - 1;
-				live &= live - 1;
-				const GaussRec* r = &s_rec[buf][c0 + jl];
-				const float4 q0 = r->q0;
-				const float4 q1 = r->q1;
-				const float4 q2 = r->q2;
-				const float dx = q0.x - pxf, dy = q0.y - pyf;
-				const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-				const float alpha = fminf(0.99f, q1.y * gsr_exp(power));
-				bool valid = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-				const float test_T = T * (1 - alpha);
-				if (valid && test_T < 0.0001f) {
-					done = true;
-					valid = false;
-				}
-				if (warp_hi_T) {
-					const unsigned touched = __ballot_sync(0xffffffffu, valid && test_T > 0.5f);
-					if (lane == jl) my_touched = __popc(touched);
-				}
-				if (valid) {
-					const float w = alpha * T;
-					C0 += q1.w * w;
-					C1 += q2.x * w;
-					C2 += q2.y * w;
-					D += q1.z * w;
-					T = test_T;
-					last_local = c0 + jl;
-				}
+			float4 q0, q1;
+			if (e < cnt) {
+				q0 = sm.rec[buf][e].q0;
+				q1 = sm.rec[buf][e].q1;
+				keep = may_touch(q0, q1, bx0, by0, bx1, by1);
 			}
+			const unsigned mask = __ballot_sync(kFull, keep);
+			if (mask == 0) continue;
+			const int nq = __popc(mask);
+			const int pos = __popc(mask & lt);
+			if (keep) {
+				const float4 q2 = sm.rec[buf][e].q2;
+				QueueRec* dst = wq + pos;
+				dst->w0 = q0;
+				dst->w1 = make_float4(q1.x, q1.y, q1.w, q2.x);
+				dst->w2 = make_float4(q2.y, q1.z, __int_as_float(b * 256 + e), __uint_as_float(sm.id[buf][e]));
+			}
+			if (lane == 0) {   // padding record for an odd survivor count: opacity 0 -> alpha 0 -> skipped
+				wq[nq].w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+				wq[nq].w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			__syncwarp();
 			if (warp_hi_T) {
-				if (my_touched) atomicAdd(&n_touched[s_id[buf][e]], my_touched);
-				warp_hi_T = __any_sync(0xffffffffu, !done && T > 0.5f);
+				blend_queue<true>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+				__syncwarp();
+				if (keep) {
+					const unsigned m = wmask[pos];
+					if (m) atomicAdd(&n_touched[__float_as_uint(wq[pos].w2.w)], __popc(m));
+				}
+				warp_hi_T = __any_sync(kFull, T > 0.5f);
+			} else {
+				blend_queue<false>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
 			}
+			__syncwarp();   // queue fully consumed before the next chunk overwrites it
 		}
-		if (last_local >= 0) last_contributor = b * 256 + last_local + 1;
 	}
 	cp_async_wait<0>();
 	if (inside) {
 		const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
+		T = fabsf(T);
 		final_T[pix] = T;
-		n_contrib[pix] = last_contributor;
+		n_contrib[pix] = (uint32_t)(last + 1);
 		out_color[pix] = C0 + T * bg[0];
 		out_color[HW + pix] = C1 + T * bg[1];
 		out_color[2 * HW + pix] = C2 + T * bg[2];

@@ -4,13 +4,13 @@
 
 namespace gsr {
 
-#ifndef GSR_ACCURATE_EXP
-// ex2.approx(x * log2 e): relative error ~2^-21 + |x| * 2^-23 (|x| < 6 where it matters); accurate expf costs 8
-// more instructions per (pixel, Gaussian) pair in issue-bound kernels.
-__device__ __forceinline__ float gsr_exp(float x) { return __expf(x); }
-#else
-__device__ __forceinline__ float gsr_exp(float x) { return expf(x); }
-#endif
+// 2^x, one MUFU.EX2 (relative error ~2^-22)
+__device__ __forceinline__ float gsr_exp2(float x)
+{
+	float r;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 
 // thread -> pixel: each warp owns an 8x4 pixel block of the 16x16 tile (lane&7 -> x, lane>>3 -> y)
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
@@ -53,5 +53,23 @@ __device__ __forceinline__ bool may_touch(const float4 q0, const float4 q1, floa
 	const bool convex = (A > 0.f) && (Cc > 0.f) && (A * Cc > B * B);
 	return !(qmin > thr) || !convex;                                  // NaNs fall through to "keep"
 }
+
+// The Gaussian falloff exponent, written with the reference's expression tree (forward.cu:478-484) so that it
+// contracts to the same FMUL/FFMA sequence: power is then BIT-IDENTICAL to the reference's, and the three
+// threshold decisions per pair (power > 0, alpha < 1/255, T < 1e-4) can only flip through the last bits of exp.
+__device__ __forceinline__ float falloff_power(float A, float B, float Cc, float dx, float dy)
+{
+	return -0.5f * (A * dx * dx + Cc * dy * dy) - B * dx * dy;
+}
+// exp(x) as ex2.approx(x * log2 e), like __expf; .ftz: results below 2^-126 become 0, which the alpha >= 1/255
+// test rejects anyway, and saves the three denormal-fix-up instructions of the non-ftz form.
+__device__ __forceinline__ float gsr_exp(float x) { return gsr_exp2(x * 1.4426950408889634f); }
+
+// Per-warp queue of the entries that survived the cull, in list order.  16-byte words, broadcast-read by the
+// pixel threads:   w0 = { mean.x, mean.y, conic.xx, conic.xy }   w1 = { conic.yy, opacity, red, green }
+//                  w2 = { blue, depth, list position (int bits), Gaussian id (int bits) }
+struct alignas(16) QueueRec {
+	float4 w0, w1, w2;
+};
 
 }  // namespace gsr

@@ -65,7 +65,10 @@ def _check_images(o, r, tol=TOL):
     # integer side outputs: exact up to alpha-threshold flips (fp rounding of exp) on a vanishing fraction
     assert np.mean(o["n_contrib"] != r["n_contrib"]) <= 1e-3
     assert np.mean(o["n_touched"] != r["n_touched"]) <= 1e-3
-    assert rel_err(o["final_T"], r["final_T"]) <= tol
+    # a flipped stop decision (test_T within rounding of 1e-4) changes that pixel's final T by a factor (1 - alpha):
+    # compare the transmittance where the stop position agrees
+    same = o["n_contrib"] == r["n_contrib"]
+    assert rel_err(o["final_T"][same], r["final_T"][same]) <= tol
 
 
 GRAD_KEYS = ("dL_dmeans3D", "dL_dmean2D", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dsh", "dL_dtau")
