@@ -39,8 +39,7 @@ struct BwdSmem {
 	GaussRec rec[2][kBatch];
 	uint32_t id[2][kBatch];
 	float4 dpix[8][32];                       // per warp: (dL/dr, dL/dg, dL/db, dL/ddepth) of its 32 pixels
-	float panel_ga[8][kSlots * kPanelStride];
-	float panel_w[8][kSlots * kPanelStride];
+	float2 panel[8][kSlots * kPanelStride];   // per warp: [slot][pixel] (ga, w)
 	QueueRec queue[8][kQueueCap];
 	uint32_t wmax[8];
 };
@@ -53,8 +52,7 @@ struct PixelState {
 };
 
 // One thread per pixel: entries grp[0 .. cnt) (cnt even, a padding record with opacity 0 at the end if needed)
-__device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int cnt, float* __restrict__ pga,
-                                           float* __restrict__ pw, PixelState& s)
+__device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int cnt, float2* __restrict__ panel, PixelState& s)
 {
 	for (int k = 0; k < cnt; k += 2) {
 #pragma unroll
@@ -71,7 +69,7 @@ __device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int
 			const bool valid = (__float_as_int(w2.z) < s.last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 			float ga = 0.f, w = 0.f;
 			if (valid) {
-				const float rcp = __fdividef(1.f, 1.f - alpha);
+				const float rcp = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
 				s.T = s.T * rcp;
 				w = alpha * s.T;     // d(channel)/d(colour)
 				const float sdot = w1.z * s.dp0 + w1.w * s.dp1 + w2.x * s.dp2 + w2.y * s.dpd;
@@ -81,36 +79,38 @@ __device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int
 				const float dL_dalpha = (sdot - s.beta) * s.T + (-s.T_final * rcp) * s.bg_dot;
 				ga = G * dL_dalpha;
 			}
-			pga[(k + u) * kPanelStride] = ga;
-			pw[(k + u) * kPanelStride] = w;
+			panel[(k + u) * kPanelStride] = make_float2(ga, w);
 		}
 	}
 }
 
-// Role switch: lane (g, part) sums its Gaussian's panel row over 16 pixels, the halves are combined,
-// lane g < nslots converts moments to gradients and issues the REDs.
-__device__ __forceinline__ void flush_panel(const float* __restrict__ pga, const float* __restrict__ pw,
-                                            const float4* __restrict__ dpix, int nslots, int lane,
-                                            const QueueRec* __restrict__ grp, float bx0, float by0, float ddelx_dx,
+// Role switch: lane (g, part) sums its Gaussian's panel row over 16 pixels (two rows of the 8x4 block), the halves
+// are combined, lane g < nslots converts moments to gradients and issues the REDs.  The moments are accumulated
+// separably: per row  R0 = sum h, R1 = sum h x, R2 = sum h x^2  (x = 0..7 immediates), then folded with the row's y.
+__device__ __forceinline__ void flush_panel(const float2* __restrict__ panel, const float4* __restrict__ dpix, int nslots,
+                                            int lane, const QueueRec* __restrict__ grp, float bx0, float by0, float ddelx_dx,
                                             float ddely_dy, GaussAcc* __restrict__ acc)
 {
-	constexpr int PARTS = 32 / kSlots, PPL = 32 / PARTS;
-	const int g = lane % kSlots, part = lane / kSlots;
+	static_assert(kSlots == 16, "two lanes per Gaussian");
+	const int g = lane & 15, part = lane >> 4;
 	float H0 = 0.f, Hx = 0.f, Hy = 0.f, Hxx = 0.f, Hxy = 0.f, Hyy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, cd = 0.f;
-	const float* rga = pga + g * kPanelStride + part * PPL;
-	const float* rw = pw + g * kPanelStride + part * PPL;
-	const float4* rdp = dpix + part * PPL;
-	const float ry0 = (float)(part * (PPL / 8));
+	const float2* row = panel + g * kPanelStride + part * 16;
+	const float4* rdp = dpix + part * 16;
 #pragma unroll
-	for (int k = 0; k < PPL; k++) {
-		const float h = rga[k], w = rw[k];
-		const float4 dp = rdp[k];
-		const float rx = (float)(k & 7);             // pixel offset inside the warp's 8x4 block
-		const float ry = ry0 + (float)(k >> 3);
-		const float hx = h * rx, hy = h * ry;
-		H0 += h; Hx += hx; Hy += hy;
-		Hxx += hx * rx; Hxy += hx * ry; Hyy += hy * ry;
-		c0 += w * dp.x; c1 += w * dp.y; c2 += w * dp.z; cd += w * dp.w;
+	for (int r = 0; r < 2; r++) {
+		float R0 = 0.f, R1 = 0.f, R2 = 0.f;
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			const float2 hw = row[r * 8 + x];
+			const float4 dp = rdp[r * 8 + x];
+			R0 += hw.x;
+			R1 = fmaf(hw.x, (float)x, R1);
+			R2 = fmaf(hw.x, (float)(x * x), R2);
+			c0 = fmaf(hw.y, dp.x, c0); c1 = fmaf(hw.y, dp.y, c1); c2 = fmaf(hw.y, dp.z, c2); cd = fmaf(hw.y, dp.w, cd);
+		}
+		const float ry = (float)(part * 2 + r);   // row inside the warp's 8x4 block
+		H0 += R0; Hx += R1; Hxx += R2;
+		Hy = fmaf(R0, ry, Hy); Hxy = fmaf(R1, ry, Hxy); Hyy = fmaf(R0, ry * ry, Hyy);
 	}
 	H0 += __shfl_xor_sync(kFull, H0, 16); Hx += __shfl_xor_sync(kFull, Hx, 16);
 	Hy += __shfl_xor_sync(kFull, Hy, 16); Hxx += __shfl_xor_sync(kFull, Hxx, 16);
@@ -176,8 +176,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	s.bg_dot = bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2;
 	s.beta = 0.f; s.last_alpha = 0.f; s.last_s = 0.f;
 	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-	float* pga = sm.panel_ga[warp];
-	float* pw = sm.panel_w[warp];
+	float2* panel = sm.panel[warp];
 	QueueRec* wq = sm.queue[warp];
 
 	// entries behind the tile's deepest contributor can never contribute (backward.cu:763)
@@ -241,9 +240,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 			qn += __popc(mask);
 			__syncwarp();
 			while (qn >= kSlots) {
-				eval_group(wq + head, kSlots, pga + lane, pw + lane, s);
+				eval_group(wq + head, kSlots, panel + lane, s);
 				__syncwarp();
-				flush_panel(pga, pw, sm.dpix[warp], kSlots, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
+				flush_panel(panel, sm.dpix[warp], kSlots, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
 				__syncwarp();   // panel and queue group consumed
 				head = (head + kSlots == kQueueCap) ? 0 : head + kSlots;
 				qn -= kSlots;
@@ -257,9 +256,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 			wq[head + qn].w2 = make_float4(0.f, 0.f, 0.f, 0.f);
 		}
 		__syncwarp();
-		eval_group(wq + head, (qn + 1) & ~1, pga + lane, pw + lane, s);
+		eval_group(wq + head, (qn + 1) & ~1, panel + lane, s);
 		__syncwarp();
-		flush_panel(pga, pw, sm.dpix[warp], qn, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
+		flush_panel(panel, sm.dpix[warp], qn, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
 	}
 	cp_async_wait<0>();
 }

@@ -12,6 +12,13 @@ __device__ __forceinline__ float gsr_exp2(float x)
 	return r;
 }
 
+__device__ __forceinline__ float rcp_approx(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
 // thread -> pixel: each warp owns an 8x4 pixel block of the 16x16 tile (lane&7 -> x, lane>>3 -> y)
 __device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int& px, int& py)
 {
