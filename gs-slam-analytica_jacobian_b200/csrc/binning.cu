@@ -193,6 +193,106 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 	}
 }
 
+// Single-chunk variant for segments of at most kSortThreads * ITEMS pairs held in shared memory: the digit
+// histogram falls out of the ranking (per-warp counters), so there is no separate counting sweep and no atomics.
+template <int ITEMS>
+__device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, int n,
+                                                 uint32_t kmin, Field f, uint32_t* s_cnt /*[8][kMaxBins]*/,
+                                                 uint32_t* s_base /*[kMaxBins]*/)
+{
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int nb = 1 << f.bits;
+	const uint32_t mask = (uint32_t)nb - 1;
+	const uint32_t lt = (1u << lane) - 1;
+	for (int i = tid; i < 8 * kMaxBins / 4; i += kSortThreads) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+	uint32_t k[ITEMS], v[ITEMS], rank[ITEMS], dg[ITEMS];
+	const int wbase = warp * (32 * ITEMS) + lane;
+#pragma unroll
+	for (int i = 0; i < ITEMS; i++) {
+		const int pos = wbase + i * 32;
+		if (pos < n) { k[i] = kin[pos]; v[i] = vin[pos]; }
+		else { k[i] = 0xffffffffu; v[i] = 0xffffffffu; }
+	}
+#pragma unroll
+	for (int i = 0; i < ITEMS; i++) {
+		const int pos = wbase + i * 32;
+		const uint32_t d = (pos < n) ? ((((f.word == 0) ? (k[i] - kmin) : v[i]) >> f.shift) & mask) : mask;   // padding ranks last in its warp
+		dg[i] = d;
+		const unsigned peers = __match_any_sync(0xffffffffu, d);
+		const uint32_t pre = s_cnt[warp * kMaxBins + d];
+		__syncwarp();
+		rank[i] = pre + __popc(peers & lt);
+		if (lane == 31 - __clz(peers)) s_cnt[warp * kMaxBins + d] = pre + __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+	// per digit: exclusive scan over the 8 warps, total -> s_base (the padding only inflates bin `mask` behind the real keys)
+	for (int d = tid; d < nb; d += kSortThreads) {
+		uint32_t total = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) {
+			const uint32_t c = s_cnt[w * kMaxBins + d];
+			s_cnt[w * kMaxBins + d] = total;
+			total += c;
+		}
+		s_base[d] = total;
+	}
+	__syncthreads();
+	if (warp == 0) {      // exclusive scan over the digits: each lane scans nb/32 consecutive bins
+		const int per = (nb + 31) / 32;
+		uint32_t sum = 0;
+		for (int j = 0; j < per; j++) { const int b = lane * per + j; if (b < nb) sum += s_base[b]; }
+		uint32_t inc = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += t;
+		}
+		uint32_t run = inc - sum;
+		for (int j = 0; j < per; j++) {
+			const int b = lane * per + j;
+			if (b < nb) { const uint32_t c = s_base[b]; s_base[b] = run; run += c; }
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < ITEMS; i++) {
+		const int pos = wbase + i * 32;
+		if (pos < n) {
+			const uint32_t dst = s_base[dg[i]] + s_cnt[warp * kMaxBins + dg[i]] + rank[i];
+			kout[dst] = k[i];
+			vout[dst] = v[i];
+		}
+	}
+	__syncthreads();
+}
+
+// Odd-even transposition sweeps on (key, id) until the segment is in (depth, id) order; cheap finisher for a
+// segment that is already sorted on its leading key bits.  Returns false if it did not converge in max_sweeps.
+__device__ __forceinline__ bool finish_by_transposition(uint32_t* K, uint32_t* V, int n, int max_sweeps)
+{
+	for (int sweep = 0; sweep < max_sweeps; sweep++) {
+		int swapped = 0;
+#pragma unroll
+		for (int par = 0; par < 2; par++) {
+			for (int i = 2 * (int)threadIdx.x + par; i + 1 < n; i += 2 * kSortThreads) {
+				const uint32_t k0 = K[i], k1 = K[i + 1];
+				if (k0 >= k1) {
+					const uint32_t v0 = V[i], v1 = V[i + 1];
+					if (k0 > k1 || v0 > v1) {
+						K[i] = k1; K[i + 1] = k0; V[i] = v1; V[i + 1] = v0;
+						swapped = 1;
+					}
+				}
+			}
+			__syncthreads();
+		}
+		if (!__syncthreads_or(swapped)) return true;
+	}
+	return false;
+}
+
 __device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out)
 {
 	if (sigbits <= 0) return 0;
@@ -262,11 +362,36 @@ tile_sort_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* _
 	const int nd = plan_passes(sig, 0, depth_passes);
 	const int ni = plan_passes(id_bits, 1, id_passes);
 
+	if (in_smem && n <= kSortThreads * 8) {
+		// fast path: at most two single-chunk passes over the LEADING 18 key bits, then transposition sweeps settle the
+		// low bits and the id order of equal depths (adjacent by then); falls through to the full sort if they do not
+		const int top = min(sig, 2 * kMaxDigitBits);
+		Field fp[2];
+		int np = plan_passes(top, 0, fp);
+		for (int p = 0; p < np; p++) fp[p].shift += sig - top;
+		int cur = 0;
+		for (int p = 0; p < np; p++) {
+			if (n <= kSortThreads * 4)
+				radix_pass_small<4>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, s_keys + (cur ^ 1) * cap_smem,
+				                    s_vals + (cur ^ 1) * cap_smem, n, kmin, fp[p], s_cnt, s_base);
+			else
+				radix_pass_small<8>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, s_keys + (cur ^ 1) * cap_smem,
+				                    s_vals + (cur ^ 1) * cap_smem, n, kmin, fp[p], s_cnt, s_base);
+			cur ^= 1;
+		}
+		uint32_t* K = s_keys + cur * cap_smem;
+		uint32_t* V = s_vals + cur * cap_smem;
+		if (finish_by_transposition(K, V, n, 24)) {
+			for (int i = tid; i < n; i += kSortThreads) point_list[start + i] = V[i];
+			return;
+		}
+		__syncthreads();
+	}
 	if (in_smem) {
 		int cur = 0;
-		for (int attempt = 0; attempt < 2; attempt++) {
+		for (int attempt = (n <= kSortThreads * 8) ? 1 : 0; attempt < 2; attempt++) {
 			// attempt 0: depth digits only (stable w.r.t. the arbitrary scatter order);
-			// attempt 1 (only if a depth tie came out in the wrong id order): id digits first, then depth
+			// attempt 1 (a depth tie came out in the wrong id order, or the fast path gave up): id digits first, then depth
 			if (attempt == 1) {
 				for (int i = tid; i < n; i += kSortThreads) { const uint2 kv = seg[i]; s_keys[i] = kv.x; s_vals[i] = kv.y; }
 				cur = 0;
