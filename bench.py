@@ -326,6 +326,164 @@ def run_ours(args, rank, world, device):
     return line
 
 
+def run_window(args, rank, world, device):
+    """Mapping-window / candidate-pose workloads (C2, C3, C4): V views over one replicated map, sharded by view
+    across the ranks.  One step = forward+backward of ALL V views; per-Gaussian gradients are
+    accumulated in the backward kernel and summed over ranks by ONE all-reduce (NCCL over NVLink) per step for the
+    mapping shapes; the candidate-pose batch (C3) needs no collective.  Strong scaling: total work is fixed."""
+    from diff_gaussian_rasterization import _cabi
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    L = _cabi.load()
+    K, Wm = args.steps, args.warmup
+    name = args.workload
+    cfg = S.CONFIGS[name]
+    V = args.views or cfg["V"]
+    reduce = not name.startswith("C3")
+    sc = S.make_scene(name, seed=0)
+    W, H = cfg["W"], cfg["H"]
+    poses = S.noisy_poses(V, seed=2) if name.startswith("C3") else S.arc_poses(V, radius=0.5, seed=2)
+    cams = np.stack([np.concatenate([c["viewmatrix"].reshape(-1), c["projmatrix"].reshape(-1), c["projmatrix_raw"].reshape(-1),
+                                     c["campos"], [0.0]]).astype(np.float32)
+                     for c in (S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c) for w2c in poses)])
+    dc, dd = S.make_pixel_grads(W, H, seed=1)
+    t = S.to_torch(sc, device)
+    eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                       W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
+    cams_dev = torch.from_numpy(cams).to(device)
+    cams_pin = torch.from_numpy(cams).pin_memory()
+    dc_pin, dd_pin = torch.from_numpy(dc).pin_memory(), torch.from_numpy(dd).pin_memory()
+    eng.dL_dcolor.copy_(dc_pin)
+    eng.dL_ddepth.copy_(dd_pin)
+    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world)
+    win.calibrate()
+    Rs = []
+    for v in win.views:
+        eng.set_camera(cams_dev[v])
+        Rs.append(eng.calibrate())
+    up = lambda v: (eng.dL_dcolor, eng.dL_ddepth)
+    flush = l2_flusher(device)
+    stream = torch.cuda.current_stream(device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    l0 = L.gsr_kernel_launch_count()
+    win.iteration(up, reduce=reduce)
+    torch.cuda.synchronize(device)
+    launches_per_step = int(L.gsr_kernel_launch_count() - l0)
+    for _ in range(Wm):
+        flush()
+        win.iteration(up, reduce=reduce)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device())
+    barrier()
+    sampler.start()
+    for i in range(K):
+        flush()
+        ev[i][0].record(stream)
+        win.iteration(up, reduce=reduce)
+        ev[i][1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    _, overflow = eng.header()
+    assert not overflow
+    gnorm_check = float(eng.grad_flat.double().norm())
+
+    # e2e: camera blocks + dL/dpixel from pinned host memory every view, dL/dtau of the local views + the gradient
+    # norm (what an optimiser step would read first) back to the host, host blocks every step
+    tau_pin = torch.empty((max(len(win.views), 1), 6), dtype=torch.float32).pin_memory()
+    norm_pin = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def up_host(v):
+        eng.dL_dcolor.copy_(dc_pin, non_blocking=True)
+        eng.dL_ddepth.copy_(dd_pin, non_blocking=True)
+        return eng.dL_dcolor, eng.dL_ddepth
+
+    def e2e_step():
+        cams_dev.copy_(cams_pin, non_blocking=True)
+        win.iteration(up_host, reduce=reduce)
+        tau_pin[:len(win.views)].copy_(win.tau, non_blocking=True)
+        norm_pin.copy_(eng.grad_flat.norm().reshape(1), non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(Wm):
+        flush()
+        torch.cuda.synchronize(device)
+        e2e_step()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(K):
+        flush()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    h2d = cams.nbytes + len(win.views) * (dc.nbytes + dd.nbytes)
+    d2h = len(win.views) * 24 + 4
+
+    # per-stage timing on this rank's first view
+    names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
+    stage = np.zeros(5)
+    if win.views:
+        L.gsr_stage_timing(1)
+        out5 = (C.c_float * 5)()
+        eng.set_camera(cams_dev[win.views[0]])
+        for i in range(3):
+            flush()
+            eng.step(use_graph=False)
+            _cabi.check(L.gsr_stage_times_ms(out5), "stage_times")
+            stage += np.array(list(out5))
+        stage /= 3
+        L.gsr_stage_timing(0)
+    tmax, emax = dev_ms, e2e_s
+    R_sum = float(sum(Rs))
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        tmax, emax = float(tt[0]), float(tt[1])
+        rr = torch.tensor([R_sum], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(rr)
+        R_sum = float(rr[0])
+    if rank != 0:
+        return None
+    HW = W * H
+    R_view = R_sum / V
+    rb = roofline_bytes(cfg["P"], R_view, HW)
+    peak, peak_src = peaks()
+    dom = int(np.argmax([stage[2], stage[3]])) + 2
+    achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+    grad_bytes = int(eng.grad_flat.numel() * 4)
+    line = {
+        "metric": "fwd+bwd raster window iters/s incl. pose dL/dtau", "value": K / (tmax * 1e-3), "unit": "window iters/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": tmax / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %dx%d, P=%d Gaussians, SH deg %d, V=%d views/step sharded by view over %d GPU(s)"
+                   % (name, W, H, cfg["P"], cfg["sh_degree"], V, world),
+                   "views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view,
+                   "collective": ("all_reduce(sum) of %d B of packed per-Gaussian gradients per step" % grad_bytes) if reduce else "none",
+                   "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
+                   "parallelism": "keyframe-parallel x%d" % world},
+        "e2e": {"value": K / emax, "unit": "window iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": emax / K * 1e3},
+        "gpu_launches": launches_per_step * K,
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
+                     "whole_step": {"alg_bytes": int(sum(rb.values()) * V),
+                                    "frac": round(sum(rb.values()) * V / (tmax / K * 1e-3) / 1e9 / (peak * world), 4)},
+                     "stages_one_view": {n: round(float(ms), 4) for n, ms in zip(names, stage)}},
+        "clocks": clocks, "check": {"grad_norm": gnorm_check},
+    }
+    return line
+
+
 class _RawView:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
@@ -337,12 +495,25 @@ def run_reference(args, rank, world, device):
     from diff_gaussian_rasterization import scenes as S
 
     K, Wm = args.steps, args.warmup
-    cfg, sc, cams, dc, dd = build_workload(args.workload, K + Wm, 0, device)
+    window = not args.workload.startswith(("C0", "C1"))
+    if window:      # V views per step over one map, per-view gradients summed like autograd does (slam_backend.py:168-232)
+        cfg = S.CONFIGS[args.workload]
+        V = args.views or cfg["V"]
+        sc = S.make_scene(args.workload, seed=0)
+        poses = S.noisy_poses(V, seed=2) if args.workload.startswith("C3") else S.arc_poses(V, radius=0.5, seed=2)
+        cams = np.stack([np.concatenate([c["viewmatrix"].reshape(-1), c["projmatrix"].reshape(-1), c["projmatrix_raw"].reshape(-1),
+                                         c["campos"], [0.0]]).astype(np.float32)
+                         for c in (S.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c) for w2c in poses)])
+        dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=1)
+    else:
+        V = 1
+        cfg, sc, cams, dc, dd = build_workload(args.workload, K + Wm, 0, device)
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libgsref.so")
-    base = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload + ": %dx%d, P=%d Gaussians, SH deg %d, 1 view/step, pose perturbed every step"
-                       % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"])}}
+    base = {"metric": METRIC if not window else "fwd+bwd raster window iters/s incl. pose dL/dtau",
+            "unit": UNIT if not window else "window iters/s", "n_gpus": world, "steps": K, "warmup": Wm, "higher_is_better": True,
+            "scaling": "weak" if not window else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload + (": %dx%d, P=%d Gaussians, SH deg %d, " % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"]))
+                       + ("1 view/step, pose perturbed every step" if not window else "V=%d views/step on one GPU" % V)}}
     if not (os.path.exists(ref_so) and torch.cuda.is_available()):
         v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd)
         base.update(value=v, ms_per_step=1e3 / v,
@@ -367,7 +538,21 @@ def run_reference(args, rank, world, device):
     cp = cam.data_ptr()
     view, proj, praw, campos = C.c_void_p(cp), C.c_void_p(cp + 64), C.c_void_p(cp + 128), C.c_void_p(cp + 192)
 
+    acc = {k: torch.zeros_like(g[k]) for k in ("m3d", "m2d", "sh", "opac", "sc", "rot")} if window else None
+
     def step(i):
+        if not window:
+            return view_step(i)
+        for a in acc.values():
+            a.zero_()
+        tau = None
+        for v in range(V):
+            tau = view_step(v)
+            for k, a in acc.items():      # autograd's accumulation of the per-view parameter gradients
+                a.add_(g[k])
+        return tau
+
+    def view_step(i):
         cam.copy_(cams_dev[i])
         for v in out.values():          # torch::full(0) of the binding, rasterize_points.cu:84-88
             v.zero_()
@@ -420,6 +605,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1_tum_tracking")
+    ap.add_argument("--views", type=int, default=0, help="override the window size of C2/C3/C4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -441,7 +627,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    line = run_ours(args, rank, world, device)
+    line = run_ours(args, rank, world, device) if args.workload.startswith(("C0", "C1")) else run_window(args, rank, world, device)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
