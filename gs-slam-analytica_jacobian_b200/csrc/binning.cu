@@ -6,8 +6,8 @@
 //
 //   (preprocess)  every visible Gaussian adds 1 to the counters of the tiles in its rectangle (integer
 //                 REDs); the last preprocess CTA scans the counters into ranges[tile] and scatter cursors.
-//   1. scatter    warp-cooperative: the lanes of a warp walk one Gaussian's rectangle 32 tiles per step,
-//                 claim a slot in the tile's segment with an integer atomic and store (depth bits, id).
+//   1. scatter    every lane walks its own Gaussian's rectangle (large rectangles: the whole warp, 32 tiles per
+//                 step), claims a slot in the tile's segment with an integer atomic and stores (depth bits, id).
 //                 Segments come out contiguous per tile but unordered inside.
 //   2. tile sort  one CTA per tile sorts its segment in shared memory: stable LSD radix sort on the
 //                 depth bits that actually differ inside the tile (min/max -> typically 3 passes of <= 9
@@ -32,7 +32,6 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
                int n_tiles, int use_smem)
 {
 	const int idx = blockIdx.x * 256 + threadIdx.x;
-	const unsigned lane = threadIdx.x & 31;
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
 		n = tiles_touched[idx];
@@ -46,25 +45,12 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 	extern __shared__ uint32_t s_tile[];          // [2][tiles]: CTA-local counts, then claimed bases (use_smem != 0)
 	uint32_t* s_cnt = s_tile;
 	uint32_t* s_base = s_tile + n_tiles;
-	const unsigned all_live = __ballot_sync(0xffffffffu, n != 0);
-	const uint32_t magic = rect_magic((hi & 0xffff) - (lo & 0xffff), n);
 	if (use_smem) {
 		// pass 1: CTA-local tile histogram; then ONE global atomic per (CTA, touched tile) claims a contiguous
 		// slice of the tile's segment (coalesced over consecutive tiles) instead of one atomic per instance
 		for (int t = threadIdx.x; t < n_tiles; t += 256) s_cnt[t] = 0;
 		__syncthreads();
-		unsigned live = all_live;
-		while (live) {
-			const int src = __ffs(live) - 1;
-			live &= live - 1;
-			const uint32_t g_lo = __shfl_sync(0xffffffffu, lo, src), g_hi = __shfl_sync(0xffffffffu, hi, src);
-			const uint32_t g_n = __shfl_sync(0xffffffffu, n, src), g_magic = __shfl_sync(0xffffffffu, magic, src);
-			const uint32_t x0 = g_lo & 0xffff, y0 = g_lo >> 16, w = (g_hi & 0xffff) - x0;
-			for (uint32_t i = lane; i < g_n; i += 32) {
-				const uint32_t ty = rect_row(i, w, g_magic), tx = i - ty * w;
-				atomicAdd(&s_cnt[(y0 + ty) * grid_x + (x0 + tx)], 1u);
-			}
-		}
+		for_each_tile(n, lo, hi, grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
 		__syncthreads();
 		for (int t = threadIdx.x; t < n_tiles; t += 256) {
 			const uint32_t c = s_cnt[t];
@@ -73,24 +59,12 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 		}
 		__syncthreads();
 	}
-	unsigned live = all_live;
 	bool overflow = false;
-	while (live) {
-		const int src = __ffs(live) - 1;
-		live &= live - 1;
-		const uint32_t g_lo = __shfl_sync(0xffffffffu, lo, src), g_hi = __shfl_sync(0xffffffffu, hi, src);
-		const uint32_t g_n = __shfl_sync(0xffffffffu, n, src), g_key = __shfl_sync(0xffffffffu, key, src);
-		const uint32_t g_id = (uint32_t)(blockIdx.x * 256 + (threadIdx.x & ~31) + src);
-		const uint32_t g_magic = __shfl_sync(0xffffffffu, magic, src);
-		const uint32_t x0 = g_lo & 0xffff, y0 = g_lo >> 16, w = (g_hi & 0xffff) - x0;
-		for (uint32_t i = lane; i < g_n; i += 32) {
-			const uint32_t ty = rect_row(i, w, g_magic), tx = i - ty * w;
-			const uint32_t tile = (y0 + ty) * grid_x + (x0 + tx);
-			const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
-			if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
-			else overflow = true;
-		}
-	}
+	for_each_tile(n, lo, hi, grid_x, key, (uint32_t)idx, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
+		const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
+		if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
+		else overflow = true;
+	});
 	if (overflow) hdr->overflow = 1;
 }
 

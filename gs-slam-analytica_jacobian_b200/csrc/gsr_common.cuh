@@ -144,6 +144,38 @@ __device__ __forceinline__ uint32_t rect_row(uint32_t i, uint32_t w, uint32_t ma
 	return magic ? __umulhi(i, magic) : i / w;
 }
 
+// Visit every tile of the rectangles held by the lanes of a warp (n = tile count of this lane's Gaussian, 0 = none;
+// lo/hi = packed rectangle).  Rectangles of up to kSoloTiles tiles are walked by their own lane (all lanes in
+// parallel, a handful of iterations); the rare large ones are walked by the whole warp, 32 tiles per step.
+// f(tile, key, id) is called once per (Gaussian, tile) with the owner's key / id.  Must be called by all 32 lanes.
+constexpr uint32_t kSoloTiles = 32;
+template <typename F>
+__device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t hi, int grid_x, uint32_t key, uint32_t id, F&& f)
+{
+	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
+	if (n != 0 && n <= kSoloTiles) {
+		for (uint32_t y = y0; y < y1; y++) {
+			uint32_t tile = y * grid_x + x0;
+			for (uint32_t x = x0; x < x1; x++, tile++) f(tile, key, id);
+		}
+	}
+	unsigned big = __ballot_sync(0xffffffffu, n > kSoloTiles);
+	const unsigned lane = threadIdx.x & 31;
+	while (big) {
+		const int src = __ffs(big) - 1;
+		big &= big - 1;
+		const uint32_t g_lo = __shfl_sync(0xffffffffu, lo, src), g_hi = __shfl_sync(0xffffffffu, hi, src);
+		const uint32_t g_n = __shfl_sync(0xffffffffu, n, src);
+		const uint32_t g_key = __shfl_sync(0xffffffffu, key, src), g_id = __shfl_sync(0xffffffffu, id, src);
+		const uint32_t gx0 = g_lo & 0xffff, gy0 = g_lo >> 16, w = (g_hi & 0xffff) - gx0;
+		const uint32_t magic = rect_magic(w, g_n);
+		for (uint32_t i = lane; i < g_n; i += 32) {
+			const uint32_t ty = rect_row(i, w, magic), tx = i - ty * w;
+			f((gy0 + ty) * grid_x + (gx0 + tx), g_key, g_id);
+		}
+	}
+}
+
 // vector reduction to global memory: one 16-byte RED instead of four scalar atomics (sm_90+)
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 {

@@ -248,26 +248,11 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		g.tiles_touched[idx] = my_tiles;
 		g.clamped[idx] = (uint8_t)clamped;
 	}
-	// per-tile instance counts: the warp walks its visible Gaussians, 32 tiles per step (integer REDs)
-	{
-		unsigned live = __ballot_sync(0xffffffffu, my_tiles != 0);
-		const unsigned lane = lane_id();
-		const unsigned my_magic = rect_magic((rect_hi & 0xffff) - (rect_lo & 0xffff), my_tiles);
-		while (live) {
-			const int src = __ffs(live) - 1;
-			live &= live - 1;
-			const unsigned lo = __shfl_sync(0xffffffffu, rect_lo, src), hi = __shfl_sync(0xffffffffu, rect_hi, src);
-			const unsigned n = __shfl_sync(0xffffffffu, my_tiles, src);
-			const unsigned magic = __shfl_sync(0xffffffffu, my_magic, src);
-			const unsigned x0 = lo & 0xffff, y0 = lo >> 16, w = (hi & 0xffff) - x0;
-			for (unsigned i = lane; i < n; i += 32) {
-				const unsigned ty = rect_row(i, w, magic), tx = i - ty * w;
-				const unsigned tile = (y0 + ty) * s.grid_x + (x0 + tx);
-				if (hist_smem) atomicAdd(&s_hist[tile], 1u);
-				else atomicAdd(&g.tile_count[tile], 1u);
-			}
-		}
-	}
+	// per-tile instance counts (integer REDs): small rectangles lane-parallel, large ones warp-cooperative
+	for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) {
+		if (hist_smem) atomicAdd(&s_hist[tile], 1u);
+		else atomicAdd(&g.tile_count[tile], 1u);
+	});
 	if (hist_smem) {
 		// one coalesced RED per touched tile and CTA instead of one scattered RED per instance
 		__syncthreads();
