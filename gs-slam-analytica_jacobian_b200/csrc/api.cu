@@ -81,13 +81,11 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	return GSR_OK;
 }
 
-// shared-memory capacity (list entries) of the per-tile sort for a given longest-tile hint
+// shared-memory capacity (list entries) of the 256-thread per-tile sort for a given longest-tile hint: one chunk;
+// lists of 2049..8192 entries are sorted by the long-list kernel, longer ones through global memory
 int pick_cap_smem(long long max_tile_hint)
 {
-	long long want = max_tile_hint > 0 ? max_tile_hint : 2048;
-	int cap = 1024;
-	while (cap < want && cap < 12288) cap += 1024;
-	return cap;
+	return (max_tile_hint > 0 && max_tile_hint <= 1024) ? 1024 : 2048;
 }
 
 }  // namespace
@@ -153,7 +151,7 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
-	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), st);
+	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, st);
 	stage_mark(2, st);
 	rc = debug_sync(a, st, "binning");
 	if (rc) return rc;

@@ -9,12 +9,16 @@
 //   1. scatter    every lane walks its own Gaussian's rectangle (large rectangles: the whole warp, 32 tiles per
 //                 step), claims a slot in the tile's segment with an integer atomic and stores (depth bits, id).
 //                 Segments come out contiguous per tile but unordered inside.
-//   2. tile sort  one CTA per tile sorts its segment in shared memory: stable LSD radix sort on the
-//                 depth bits that actually differ inside the tile (min/max -> typically 3 passes of <= 9
-//                 bits instead of 6 passes of 8 over 64-bit keys), then checks adjacent equal depths; only
-//                 if such a tie is out of id order the tile is re-sorted with the id digits first.  Tiles
-//                 longer than the shared-memory capacity run the same passes through global ping-pong
-//                 buffers.  The result is the unique (tile, depth, id) order, i.e. the reference's list.
+//   2. tile sort  one CTA per tile sorts its segment in shared memory.  Fast path (lists that fit one chunk of
+//                 8 keys per thread): two stable single-chunk radix passes over the LEADING 18 of the depth bits
+//                 that differ inside the tile (min/max), ranks from warp match.any + per-warp counters (no
+//                 atomics, no counting sweep), then odd-even transposition sweeps on (depth, id) settle the low
+//                 bits and the id order of equal depths.  256-thread CTAs take lists up to 2048 entries; longer
+//                 lists are queued by the preprocess scan and sorted by a second launch of 512-thread CTAs (same
+//                 code; one chunk up to 4096 entries, chunked passes through global ping-pong buffers beyond).
+//                 If the finisher does not converge (masses of equal depths) the list takes the general path:
+//                 stable LSD passes over the id digits, then every differing depth bit.
+//                 The result is the unique (tile, depth, id) order, i.e. the reference's list.
 //
 // HBM/L2 traffic per instance: 8 B scatter + 8 B read + 4 B list write = 20 B (reference: >= 144 B), and the
 // forward needs 4 kernel launches instead of 14.  Every kernel reads num_rendered-dependent quantities from
@@ -69,53 +73,63 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 }
 
 // ---- 2. per-tile sort -------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;                       // keys per thread and chunk
-constexpr int kSortChunk = kSortThreads * kSortItems;
 constexpr int kMaxDigitBits = 9;
 constexpr int kMaxBins = 1 << kMaxDigitBits;
+constexpr int kSmallThreads = 256, kLongThreads = 512;
+constexpr int kSmallChunk = kSmallThreads * kSortItems;   // 2048
+constexpr int kLongChunk = kLongThreads * kSortItems;     // 4096
 
 struct Field {       // which 32-bit word of the pair a pass looks at
 	int word;        // 0 = depth key (minus the tile minimum), 1 = Gaussian id
 	int shift, bits;
 };
 
-// One stable counting pass over n pairs held in (kin, vin) -> (kout, vout); all arrays may live in shared or
-// global memory.  Chunks of 2048 pairs are ranked with warp match.any + per-warp digit counters (stable),
-// digit bases advance chunk by chunk.
+__device__ __forceinline__ uint32_t digit_of(uint32_t k, uint32_t v, uint32_t kmin, Field f, uint32_t mask)
+{
+	return (((f.word == 0) ? (k - kmin) : v) >> f.shift) & mask;
+}
+
+// exclusive scan of s_base[0..nb) by warp 0 (nb <= 512: each lane scans nb/32 consecutive bins)
+__device__ __forceinline__ void scan_bins(uint32_t* s_base, int nb, int lane)
+{
+	const int per = (nb + 31) / 32;
+	uint32_t sum = 0;
+	for (int j = 0; j < per; j++) { const int b = lane * per + j; if (b < nb) sum += s_base[b]; }
+	uint32_t inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += t;
+	}
+	uint32_t run = inc - sum;
+	for (int j = 0; j < per; j++) {
+		const int b = lane * per + j;
+		if (b < nb) { const uint32_t c = s_base[b]; s_base[b] = run; run += c; }
+	}
+}
+
+// General stable counting pass over n pairs held in (kin, vin) -> (kout, vout); all arrays may live in shared or
+// global memory.  A counting sweep (shared-memory atomics) gives the digit bases; chunks of NT*8 pairs are then
+// ranked with warp match.any + per-warp digit counters (stable) and scattered, bases advancing chunk by chunk.
+template <int NT>
 __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* vin, int in_stride, uint32_t* kout,
                                            uint32_t* vout, int out_stride, int n, uint32_t kmin, Field f,
-                                           uint32_t* s_cnt /*[8][kMaxBins]*/, uint32_t* s_base /*[kMaxBins]*/)
+                                           uint32_t* s_cnt /*[NT/32][kMaxBins]*/, uint32_t* s_base /*[kMaxBins]*/)
 {
+	constexpr int NW = NT / 32;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int nb = 1 << f.bits;
 	const uint32_t mask = (uint32_t)nb - 1;
-	auto digit = [&](uint32_t k, uint32_t v) -> uint32_t { return (((f.word == 0) ? (k - kmin) : v) >> f.shift) & mask; };
-	// digit histogram of the whole segment -> exclusive scan -> s_base
-	for (int i = tid; i < nb; i += kSortThreads) s_base[i] = 0;
+	for (int i = tid; i < nb; i += NT) s_base[i] = 0;
 	__syncthreads();
-	for (int i = tid; i < n; i += kSortThreads) atomicAdd(&s_base[digit(kin[(size_t)i * in_stride], vin[(size_t)i * in_stride])], 1u);
+	for (int i = tid; i < n; i += NT) atomicAdd(&s_base[digit_of(kin[(size_t)i * in_stride], vin[(size_t)i * in_stride], kmin, f, mask)], 1u);
 	__syncthreads();
-	if (warp == 0) {      // nb <= 512: each lane scans nb/32 consecutive bins
-		const int per = (nb + 31) / 32;
-		uint32_t sum = 0;
-		for (int j = 0; j < per; j++) { const int b = lane * per + j; if (b < nb) sum += s_base[b]; }
-		uint32_t inc = sum;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= o) inc += t;
-		}
-		uint32_t run = inc - sum;
-		for (int j = 0; j < per; j++) {
-			const int b = lane * per + j;
-			if (b < nb) { const uint32_t c = s_base[b]; s_base[b] = run; run += c; }
-		}
-	}
+	if (warp == 0) scan_bins(s_base, nb, lane);
 	__syncthreads();
 	const uint32_t lt = (1u << lane) - 1;
-	for (int c0 = 0; c0 < n; c0 += kSortChunk) {
-		for (int i = tid; i < 8 * kMaxBins / 4; i += kSortThreads) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	for (int c0 = 0; c0 < n; c0 += NT * kSortItems) {
+		for (int i = tid; i < NW * kMaxBins / 4; i += NT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
 		__syncthreads();
 		uint32_t k[kSortItems], v[kSortItems], rank[kSortItems];
 		const int wbase = c0 + warp * (32 * kSortItems) + lane;
@@ -128,7 +142,7 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 #pragma unroll
 		for (int i = 0; i < kSortItems; i++) {
 			const int pos = wbase + i * 32;
-			const uint32_t d = (pos < n) ? digit(k[i], v[i]) : mask;   // padding ranks after every real key of its warp
+			const uint32_t d = (pos < n) ? digit_of(k[i], v[i], kmin, f, mask) : mask;   // padding ranks after every real key of its warp
 			const unsigned peers = __match_any_sync(0xffffffffu, d);
 			const uint32_t pre = s_cnt[warp * kMaxBins + d];
 			__syncwarp();
@@ -137,12 +151,12 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 			__syncwarp();
 		}
 		__syncthreads();
-		// per digit: exclusive scan over the 8 warps; chunk total advances the base AFTER the scatter
-		uint32_t tot[2] = {0, 0};
-		for (int j = 0, d = tid; d < nb; d += kSortThreads, j++) {
+		// per digit: exclusive scan over the warps; chunk total advances the base AFTER the scatter
+		uint32_t tot[(kMaxBins + NT - 1) / NT];
+		for (int j = 0, d = tid; d < nb; d += NT, j++) {
 			uint32_t total = 0;
-#pragma unroll
-			for (int w = 0; w < 8; w++) {
+#pragma unroll 8
+			for (int w = 0; w < NW; w++) {
 				const uint32_t c = s_cnt[w * kMaxBins + d];
 				s_cnt[w * kMaxBins + d] = total;
 				total += c;
@@ -154,31 +168,32 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 		for (int i = 0; i < kSortItems; i++) {
 			const int pos = wbase + i * 32;
 			if (pos < n) {
-				const uint32_t d = digit(k[i], v[i]);
+				const uint32_t d = digit_of(k[i], v[i], kmin, f, mask);
 				const uint32_t dst = s_base[d] + s_cnt[warp * kMaxBins + d] + rank[i];
 				kout[(size_t)dst * out_stride] = k[i];
 				vout[(size_t)dst * out_stride] = v[i];
 			}
 		}
 		__syncthreads();
-		for (int j = 0, d = tid; d < nb; d += kSortThreads, j++) s_base[d] += tot[j];
+		for (int j = 0, d = tid; d < nb; d += NT, j++) s_base[d] += tot[j];
 		// (the padding of the last chunk only inflates bin `mask` after its real keys: harmless)
 		__syncthreads();
 	}
 }
 
-// Single-chunk variant for segments of at most kSortThreads * ITEMS pairs held in shared memory: the digit
-// histogram falls out of the ranking (per-warp counters), so there is no separate counting sweep and no atomics.
-template <int ITEMS>
+// Single-chunk variant for segments of at most NT * ITEMS pairs held in shared memory: the digit histogram falls
+// out of the ranking (per-warp counters), so there is no separate counting sweep and no atomics.
+template <int NT, int ITEMS>
 __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, int n,
-                                                 uint32_t kmin, Field f, uint32_t* s_cnt /*[8][kMaxBins]*/,
+                                                 uint32_t kmin, Field f, uint32_t* s_cnt /*[NT/32][kMaxBins]*/,
                                                  uint32_t* s_base /*[kMaxBins]*/)
 {
+	constexpr int NW = NT / 32;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int nb = 1 << f.bits;
 	const uint32_t mask = (uint32_t)nb - 1;
 	const uint32_t lt = (1u << lane) - 1;
-	for (int i = tid; i < 8 * kMaxBins / 4; i += kSortThreads) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	for (int i = tid; i < NW * kMaxBins / 4; i += NT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
 	__syncthreads();
 	uint32_t k[ITEMS], v[ITEMS], rank[ITEMS], dg[ITEMS];
 	const int wbase = warp * (32 * ITEMS) + lane;
@@ -191,7 +206,7 @@ __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint
 #pragma unroll
 	for (int i = 0; i < ITEMS; i++) {
 		const int pos = wbase + i * 32;
-		const uint32_t d = (pos < n) ? ((((f.word == 0) ? (k[i] - kmin) : v[i]) >> f.shift) & mask) : mask;   // padding ranks last in its warp
+		const uint32_t d = (pos < n) ? digit_of(k[i], v[i], kmin, f, mask) : mask;   // padding ranks last in its warp
 		dg[i] = d;
 		const unsigned peers = __match_any_sync(0xffffffffu, d);
 		const uint32_t pre = s_cnt[warp * kMaxBins + d];
@@ -201,11 +216,11 @@ __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint
 		__syncwarp();
 	}
 	__syncthreads();
-	// per digit: exclusive scan over the 8 warps, total -> s_base (the padding only inflates bin `mask` behind the real keys)
-	for (int d = tid; d < nb; d += kSortThreads) {
+	// per digit: exclusive scan over the warps, total -> s_base (the padding only inflates bin `mask` behind the real keys)
+	for (int d = tid; d < nb; d += NT) {
 		uint32_t total = 0;
-#pragma unroll
-		for (int w = 0; w < 8; w++) {
+#pragma unroll 8
+		for (int w = 0; w < NW; w++) {
 			const uint32_t c = s_cnt[w * kMaxBins + d];
 			s_cnt[w * kMaxBins + d] = total;
 			total += c;
@@ -213,22 +228,7 @@ __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint
 		s_base[d] = total;
 	}
 	__syncthreads();
-	if (warp == 0) {      // exclusive scan over the digits: each lane scans nb/32 consecutive bins
-		const int per = (nb + 31) / 32;
-		uint32_t sum = 0;
-		for (int j = 0; j < per; j++) { const int b = lane * per + j; if (b < nb) sum += s_base[b]; }
-		uint32_t inc = sum;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= o) inc += t;
-		}
-		uint32_t run = inc - sum;
-		for (int j = 0; j < per; j++) {
-			const int b = lane * per + j;
-			if (b < nb) { const uint32_t c = s_base[b]; s_base[b] = run; run += c; }
-		}
-	}
+	if (warp == 0) scan_bins(s_base, nb, lane);
 	__syncthreads();
 #pragma unroll
 	for (int i = 0; i < ITEMS; i++) {
@@ -243,19 +243,22 @@ __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint
 }
 
 // Odd-even transposition sweeps on (key, id) until the segment is in (depth, id) order; cheap finisher for a
-// segment that is already sorted on its leading key bits.  Returns false if it did not converge in max_sweeps.
-__device__ __forceinline__ bool finish_by_transposition(uint32_t* K, uint32_t* V, int n, int max_sweeps)
+// segment that is already sorted on its leading key bits.  K / V may be shared (stride 1) or the two words of global
+// uint2 pairs (stride 2).  Returns false if it did not converge in max_sweeps.
+template <int NT>
+__device__ __forceinline__ bool finish_by_transposition(uint32_t* K, uint32_t* V, int stride, int n, int max_sweeps)
 {
 	for (int sweep = 0; sweep < max_sweeps; sweep++) {
 		int swapped = 0;
 #pragma unroll
 		for (int par = 0; par < 2; par++) {
-			for (int i = 2 * (int)threadIdx.x + par; i + 1 < n; i += 2 * kSortThreads) {
-				const uint32_t k0 = K[i], k1 = K[i + 1];
+			for (int i = 2 * (int)threadIdx.x + par; i + 1 < n; i += 2 * NT) {
+				const size_t a = (size_t)i * stride, b = a + stride;
+				const uint32_t k0 = K[a], k1 = K[b];
 				if (k0 >= k1) {
-					const uint32_t v0 = V[i], v1 = V[i + 1];
+					const uint32_t v0 = V[a], v1 = V[b];
 					if (k0 > k1 || v0 > v1) {
-						K[i] = k1; K[i + 1] = k0; V[i] = v1; V[i + 1] = v0;
+						K[a] = k1; K[b] = k0; V[a] = v1; V[b] = v0;
 						swapped = 1;
 					}
 				}
@@ -280,26 +283,27 @@ __device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out)
 	return np;
 }
 
-// smem: keys[2][cap] | vals[2][cap] | cnt[8][512] | base[512] | red[32]
-__global__ void __launch_bounds__(kSortThreads, 4)
-tile_sort_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* __restrict__ pairs_alt,
-                 uint32_t* __restrict__ point_list, unsigned capacity, int cap_smem, int id_bits, GeomHeader* hdr)
+// Sorts the segment of one tile.  smem: keys[2][cap] | vals[2][cap] | cnt[NT/32][512] | base[512] | red[64]
+template <int NT>
+__device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, uint2* __restrict__ pairs,
+                                          uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list, unsigned capacity,
+                                          int cap_smem, int id_bits, GeomHeader* hdr, uint32_t* sm)
 {
-	extern __shared__ __align__(16) uint32_t sm[];
+	constexpr int NW = NT / 32;
 	uint32_t* s_keys = sm;
 	uint32_t* s_vals = sm + 2 * (size_t)cap_smem;
 	uint32_t* s_cnt = sm + 4 * (size_t)cap_smem;
-	uint32_t* s_base = s_cnt + 8 * kMaxBins;
+	uint32_t* s_base = s_cnt + NW * kMaxBins;
 	uint32_t* s_red = s_base + kMaxBins;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-	const uint2 range = ranges[blockIdx.x];
+	const uint2 range = ranges[tile];
 	unsigned start = range.x, end = range.y;
 	if (end > capacity) {      // un-synchronised forward ran out of workspace: stay inside it, flag, caller re-runs
 		end = capacity;
 		if (tid == 0) {
 			hdr->overflow = 1;
-			ranges[blockIdx.x] = make_uint2(min(start, capacity), capacity);   // the render kernels stay in bounds too
+			ranges[tile] = make_uint2(min(start, capacity), capacity);   // the render kernels stay in bounds too
 		}
 		if (start >= end) return;
 	}
@@ -314,7 +318,7 @@ tile_sort_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* _
 
 	// min / max depth key of the tile -> the digits that matter
 	uint32_t kmin = 0xffffffffu, kmax = 0;
-	for (int i = tid; i < n; i += kSortThreads) {
+	for (int i = tid; i < n; i += NT) {
 		const uint2 kv = seg[i];
 		if (in_smem) { s_keys[i] = kv.x; s_vals[i] = kv.y; }
 		kmin = min(kmin, kv.x);
@@ -325,92 +329,127 @@ tile_sort_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* _
 		kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
 		kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
 	}
-	if (lane == 0) { s_red[warp] = kmin; s_red[8 + warp] = kmax; }
+	if (lane == 0) { s_red[warp] = kmin; s_red[32 + warp] = kmax; }
 	__syncthreads();
-	kmin = s_red[0]; kmax = s_red[8];
-#pragma unroll
-	for (int w = 1; w < 8; w++) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[8 + w]); }
+	kmin = s_red[0]; kmax = s_red[32];
+	for (int w = 1; w < NW; w++) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[32 + w]); }
 	const int sig = (kmax == kmin) ? 0 : 32 - __clz(kmax - kmin);
 
 	Field depth_passes[4], id_passes[4];
 	const int nd = plan_passes(sig, 0, depth_passes);
 	const int ni = plan_passes(id_bits, 1, id_passes);
+	const bool one_chunk = in_smem && n <= NT * kSortItems;
 
-	if (in_smem && n <= kSortThreads * 8) {
-		// fast path: at most two single-chunk passes over the LEADING 18 key bits, then transposition sweeps settle the
-		// low bits and the id order of equal depths (adjacent by then); falls through to the full sort if they do not
+	// Fast path: at most two stable passes over the LEADING 18 key bits, then transposition sweeps settle the low bits
+	// and the id order of equal depths (adjacent by then); falls through to the general sort if they do not converge.
+	{
 		const int top = min(sig, 2 * kMaxDigitBits);
 		Field fp[2];
-		int np = plan_passes(top, 0, fp);
+		const int np = plan_passes(top, 0, fp);
 		for (int p = 0; p < np; p++) fp[p].shift += sig - top;
-		int cur = 0;
-		for (int p = 0; p < np; p++) {
-			if (n <= kSortThreads * 4)
-				radix_pass_small<4>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, s_keys + (cur ^ 1) * cap_smem,
-				                    s_vals + (cur ^ 1) * cap_smem, n, kmin, fp[p], s_cnt, s_base);
-			else
-				radix_pass_small<8>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, s_keys + (cur ^ 1) * cap_smem,
-				                    s_vals + (cur ^ 1) * cap_smem, n, kmin, fp[p], s_cnt, s_base);
-			cur ^= 1;
+		uint32_t *K, *V;
+		int stride;
+		if (in_smem) {
+			int cur = 0;
+			for (int p = 0; p < np; p++) {
+				uint32_t *ki = s_keys + cur * cap_smem, *vi = s_vals + cur * cap_smem;
+				uint32_t *ko = s_keys + (cur ^ 1) * cap_smem, *vo = s_vals + (cur ^ 1) * cap_smem;
+				if (!one_chunk) radix_pass<NT>(ki, vi, 1, ko, vo, 1, n, kmin, fp[p], s_cnt, s_base);
+				else if (n <= NT * 4) radix_pass_small<NT, 4>(ki, vi, ko, vo, n, kmin, fp[p], s_cnt, s_base);
+				else radix_pass_small<NT, kSortItems>(ki, vi, ko, vo, n, kmin, fp[p], s_cnt, s_base);
+				cur ^= 1;
+			}
+			K = s_keys + cur * cap_smem; V = s_vals + cur * cap_smem; stride = 1;
+		} else {
+			// list beyond the shared-memory capacity: the same passes through the global ping-pong buffers.  The original
+			// order is not needed again: the general sort below starts with the id digits.
+			uint2* A = pairs + start;
+			uint2* B = pairs_alt + start;
+			for (int p = 0; p < np; p++) {
+				radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, fp[p], s_cnt, s_base);
+				uint2* t = A; A = B; B = t;
+			}
+			if (A != pairs + start) {      // keep the data in `pairs` so that the general sort finds it there
+				for (int i = tid; i < n; i += NT) B[i] = A[i];
+				__syncthreads();
+				A = B;
+			}
+			K = &A->x; V = &A->y; stride = 2;
 		}
-		uint32_t* K = s_keys + cur * cap_smem;
-		uint32_t* V = s_vals + cur * cap_smem;
-		if (finish_by_transposition(K, V, n, 24)) {
-			for (int i = tid; i < n; i += kSortThreads) point_list[start + i] = V[i];
+		if (finish_by_transposition<NT>(K, V, stride, n, in_smem ? 24 : 8)) {
+			for (int i = tid; i < n; i += NT) point_list[start + i] = V[(size_t)i * stride];
 			return;
 		}
 		__syncthreads();
 	}
+	// General sort: stable LSD passes, id digits first, then every differing depth bit.
 	if (in_smem) {
+		for (int i = tid; i < n; i += NT) { const uint2 kv = seg[i]; s_keys[i] = kv.x; s_vals[i] = kv.y; }
+		__syncthreads();
 		int cur = 0;
-		for (int attempt = (n <= kSortThreads * 8) ? 1 : 0; attempt < 2; attempt++) {
-			// attempt 0: depth digits only (stable w.r.t. the arbitrary scatter order);
-			// attempt 1 (a depth tie came out in the wrong id order, or the fast path gave up): id digits first, then depth
-			if (attempt == 1) {
-				for (int i = tid; i < n; i += kSortThreads) { const uint2 kv = seg[i]; s_keys[i] = kv.x; s_vals[i] = kv.y; }
-				cur = 0;
-				__syncthreads();
-				for (int p = 0; p < ni; p++) {
-					radix_pass(s_keys + cur * cap_smem, s_vals + cur * cap_smem, 1, s_keys + (cur ^ 1) * cap_smem,
-					           s_vals + (cur ^ 1) * cap_smem, 1, n, kmin, id_passes[p], s_cnt, s_base);
-					cur ^= 1;
-				}
-			}
-			for (int p = 0; p < nd; p++) {
-				radix_pass(s_keys + cur * cap_smem, s_vals + cur * cap_smem, 1, s_keys + (cur ^ 1) * cap_smem,
-				           s_vals + (cur ^ 1) * cap_smem, 1, n, kmin, depth_passes[p], s_cnt, s_base);
-				cur ^= 1;
-			}
-			const uint32_t* K = s_keys + cur * cap_smem;
-			const uint32_t* V = s_vals + cur * cap_smem;
-			int bad = 0;
-			if (attempt == 0)
-				for (int i = tid; i + 1 < n; i += kSortThreads) bad |= (K[i] == K[i + 1]) && (V[i] > V[i + 1]);
-			if (!__syncthreads_or(bad)) {
-				for (int i = tid; i < n; i += kSortThreads) point_list[start + i] = V[i];
-				return;
-			}
+		for (int p = 0; p < ni + nd; p++) {
+			const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
+			radix_pass<NT>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, 1, s_keys + (cur ^ 1) * cap_smem,
+			               s_vals + (cur ^ 1) * cap_smem, 1, n, kmin, f, s_cnt, s_base);
+			cur ^= 1;
 		}
+		const uint32_t* V = s_vals + cur * cap_smem;
+		for (int i = tid; i < n; i += NT) point_list[start + i] = V[i];
 	} else {
-		// long tile: same passes through global ping-pong buffers; id digits always first (the input is consumed)
 		uint2* A = pairs + start;
 		uint2* B = pairs_alt + start;
 		for (int p = 0; p < ni + nd; p++) {
 			const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
-			radix_pass(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, f, s_cnt, s_base);
+			radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, f, s_cnt, s_base);
 			uint2* t = A; A = B; B = t;
-			__threadfence_block();
 		}
-		for (int i = tid; i < n; i += kSortThreads) point_list[start + i] = A[i].y;
+		for (int i = tid; i < n; i += NT) point_list[start + i] = A[i].y;
+	}
+}
+
+// one CTA per tile; lists queued for the long-list kernel (use_long) are skipped here
+__global__ void __launch_bounds__(kSmallThreads, 4)
+tile_sort_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* __restrict__ pairs_alt,
+                 uint32_t* __restrict__ point_list, unsigned capacity, int cap_smem, int id_bits, GeomHeader* hdr, int use_long)
+{
+	extern __shared__ __align__(16) uint32_t sm[];
+	if (use_long) {
+		const uint2 r = ranges[blockIdx.x];
+		const unsigned n = r.y - r.x;
+		if (n > (unsigned)kSmallChunk && r.y <= capacity) return;
+	}
+	sort_tile<kSmallThreads>(blockIdx.x, ranges, pairs, pairs_alt, point_list, capacity, cap_smem, id_bits, hdr, sm);
+}
+
+// lists of more than 2048 entries (queued by the scan at the end of the preprocess kernel): 512-thread CTAs, one
+// chunk in shared memory up to 4096 entries, global ping-pong beyond
+__global__ void __launch_bounds__(kLongThreads, 2)
+tile_sort_long_kernel(uint2* __restrict__ ranges, uint2* __restrict__ pairs, uint2* __restrict__ pairs_alt,
+                      uint32_t* __restrict__ point_list, unsigned capacity, int id_bits, GeomHeader* hdr,
+                      const uint32_t* __restrict__ long_tiles)
+{
+	extern __shared__ __align__(16) uint32_t sm[];
+	const unsigned num = hdr->num_long_tiles;
+	for (unsigned i = blockIdx.x; i < num; i += gridDim.x) {
+		const uint32_t tile = long_tiles[i];
+		if (ranges[tile].y > capacity) continue;      // overflowing step: the 256-thread kernel clamps and flags it
+		sort_tile<kLongThreads>((int)tile, ranges, pairs, pairs_alt, point_list, capacity, kLongChunk, id_bits, hdr, sm);
+		__syncthreads();
 	}
 }
 
 }  // namespace
 
-size_t tile_sort_smem_bytes(int cap_smem) { return ((size_t)4 * cap_smem + 8 * kMaxBins + kMaxBins + 32) * sizeof(uint32_t); }
+static size_t sort_smem_bytes(int cap_smem, int threads)
+{
+	return ((size_t)4 * cap_smem + (size_t)(threads / 32) * kMaxBins + kMaxBins + 64) * sizeof(uint32_t);
+}
+size_t tile_sort_smem_bytes(int cap_smem) { return sort_smem_bytes(cap_smem, kSmallThreads); }
 
-// R_capacity: instance capacity of the binning workspace.  cap_smem: longest tile list sorted in shared memory.
-int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, cudaStream_t stream)
+// R_capacity: instance capacity of the binning workspace.  cap_smem: longest tile list sorted in shared memory by the
+// 256-thread kernel; max_tile_hint: longest list expected (<= 0: unknown).
+int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
+                   cudaStream_t stream)
 {
 	if (s.P == 0 || R_capacity == 0) return 0;
 	const int tiles = s.grid_x * s.grid_y;
@@ -425,15 +464,25 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 		s.P, g.rec, g.tiles_touched, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
 	int id_bits = 1;
 	while (id_bits < 32 && (1ll << id_bits) < (long long)s.P) id_bits++;
-	const size_t smem = tile_sort_smem_bytes(cap_smem);
+	const int use_long = (max_tile_hint <= 0 || max_tile_hint > kSmallChunk) ? 1 : 0;
+	const size_t smem = sort_smem_bytes(cap_smem, kSmallThreads);
 	static size_t configured = 0;
 	if (smem > configured) {
 		cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured = smem;
 	}
-	tile_sort_kernel<<<tiles, kSortThreads, smem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list, (unsigned)R_capacity,
-	                                                         cap_smem, id_bits, g.hdr);
-	return 2;
+	tile_sort_kernel<<<tiles, kSmallThreads, smem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list, (unsigned)R_capacity,
+	                                                         cap_smem, id_bits, g.hdr, use_long);
+	if (!use_long) return 2;
+	const size_t lsmem = sort_smem_bytes(kLongChunk, kLongThreads);
+	static bool long_configured = false;
+	if (!long_configured) {
+		cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+		long_configured = true;
+	}
+	tile_sort_long_kernel<<<min(tiles, 2 * 148), kLongThreads, lsmem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list,
+	                                                                         (unsigned)R_capacity, id_bits, g.hdr, g.long_tiles);
+	return 3;
 }
 
 }  // namespace gsr

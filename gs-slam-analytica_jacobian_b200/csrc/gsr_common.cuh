@@ -40,7 +40,8 @@ struct GeomHeader {
 	unsigned int fwd_blocks_done;
 	unsigned int bwd_blocks_done;
 	unsigned int max_tile_count; // longest per-tile list
-	unsigned int pad[64 - 6];
+	unsigned int num_long_tiles; // tiles queued for the long-list sort kernel (> 2048 entries)
+	unsigned int pad[64 - 7];
 };
 static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");
 
@@ -52,6 +53,7 @@ struct GeomView {
 	uint32_t* tile_count;    // [tiles]  instances per tile (integer REDs in the preprocess); zeroed with the header
 	uint32_t* tile_cursor;   // [tiles]  write cursor of the scatter pass (starts at ranges[tile].x)
 	uint2* ranges;           // [tiles]  (start, end) of every tile's list inside point_list
+	uint32_t* long_tiles;    // [tiles]  ids of the tiles whose lists go to the long-list sort kernel
 	GaussRec* rec;           // [P]
 	GaussAcc* acc;           // [P]   zeroed by the forward preprocess, consumed+cleared by backward
 	uint32_t* tiles_touched; // [P]
@@ -62,7 +64,7 @@ struct GeomView {
 __host__ __device__ inline size_t geom_bytes(size_t P, size_t tiles)
 {
 	size_t s = sizeof(GeomHeader);
-	s += align_up(tiles * 4) * 2 + align_up(tiles * 8);
+	s += align_up(tiles * 4) * 3 + align_up(tiles * 8);
 	s += align_up(P * sizeof(GaussRec));
 	s += align_up(P * sizeof(GaussAcc));
 	s += align_up(P * 4);
@@ -79,6 +81,7 @@ __host__ __device__ inline GeomView geom_view(void* base, size_t P, size_t tiles
 	g.tile_count = (uint32_t*)p; p += align_up(tiles * 4);      // directly behind the header: one memset clears both
 	g.tile_cursor = (uint32_t*)p; p += align_up(tiles * 4);
 	g.ranges = (uint2*)p; p += align_up(tiles * 8);
+	g.long_tiles = (uint32_t*)p; p += align_up(tiles * 4);
 	g.rec = (GaussRec*)p; p += align_up(P * sizeof(GaussRec));
 	g.acc = (GaussAcc*)p; p += align_up(P * sizeof(GaussAcc));
 	g.tiles_touched = (uint32_t*)p; p += align_up(P * 4);

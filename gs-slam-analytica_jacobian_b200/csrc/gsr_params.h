@@ -26,8 +26,10 @@ struct Scene {
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
-// returns the number of kernels launched; cap_smem = longest tile list sorted in shared memory
-int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, cudaStream_t stream);
+// returns the number of kernels launched; cap_smem = longest tile list the 256-thread sort holds in shared memory,
+// max_tile_hint = longest list expected (<= 0: unknown)
+int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
+                   cudaStream_t stream);
 size_t tile_sort_smem_bytes(int cap_smem);
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, cudaStream_t stream);

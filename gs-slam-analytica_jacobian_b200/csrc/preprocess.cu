@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			const unsigned c = __ldcg(&g.tile_count[t]);
 			g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
 			g.tile_cursor[t] = run;
+			if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;   // binning.cu: kSmallChunk, kLongChunk
 			run += c;
 			mx = max(mx, c);
 		}
