@@ -99,7 +99,7 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __res
 	return dm;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
                            float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
