@@ -56,10 +56,18 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 		__syncthreads();
 		for_each_tile(n, lo, hi, grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
 		__syncthreads();
-		for (int t = threadIdx.x; t < n_tiles; t += 256) {
-			const uint32_t c = s_cnt[t];
-			if (c) s_base[t] = atomicAdd(&cursor[t], c);
-			s_cnt[t] = 0;
+		// (four claims in flight per thread: the atomics return values and would otherwise serialise on their latency)
+		for (int t0 = threadIdx.x; t0 < n_tiles; t0 += 4 * 256) {
+			uint32_t c[4], base[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) { const int t = t0 + u * 256; c[u] = t < n_tiles ? s_cnt[t] : 0u; }
+#pragma unroll
+			for (int u = 0; u < 4; u++) base[u] = c[u] ? atomicAdd(&cursor[t0 + u * 256], c[u]) : 0u;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int t = t0 + u * 256;
+				if (t < n_tiles) { s_base[t] = base[u]; s_cnt[t] = 0; }
+			}
 		}
 		__syncthreads();
 	}
