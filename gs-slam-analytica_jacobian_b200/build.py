@@ -36,6 +36,8 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("GSR_PHASE_PROBE"):      # diagnostic build (tools/phase_probe.py), never the product
+        extra += ["-DGSR_PHASE_PROBE"]
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

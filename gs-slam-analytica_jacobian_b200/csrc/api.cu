@@ -7,6 +7,12 @@
 #include "../../include/gsr_b200.h"
 #include "gsr_params.h"
 
+namespace gsr {
+int probe_read_preprocess(unsigned long long*);
+int probe_read_scatter(unsigned long long*);
+int probe_read_preprocess_backward(unsigned long long*);
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -238,6 +244,16 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSR_ERR_ARG, "bad argument");
 	gsr::launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 	return check_cuda("mark_visible");
+}
+
+int gsr_debug_probe(unsigned long long* out, size_t bytes)
+{
+	const size_t one = 4096 * 8;
+	if (!out || bytes < 3 * one * sizeof(unsigned long long)) return fail(GSR_ERR_ARG, "probe buffer too small");
+	if (cudaDeviceSynchronize() != cudaSuccess) return fail(GSR_ERR_CUDA, "sync failed");
+	if (gsr::probe_read_preprocess(out) || gsr::probe_read_scatter(out + one) || gsr::probe_read_preprocess_backward(out + 2 * one))
+		return fail(GSR_ERR_ARG, "library built without GSR_PHASE_PROBE");
+	return GSR_OK;
 }
 
 unsigned long long gsr_kernel_launch_count(void) { return g_launches.load(); }

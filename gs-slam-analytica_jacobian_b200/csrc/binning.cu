@@ -35,6 +35,7 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
                uint32_t* __restrict__ cursor, uint2* __restrict__ pairs, unsigned capacity, GeomHeader* hdr,
                int n_tiles, int use_smem)
 {
+	GSR_PROBE(1, 0);
 	const int idx = blockIdx.x * 256 + threadIdx.x;
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
@@ -54,8 +55,10 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 		// slice of the tile's segment (coalesced over consecutive tiles) instead of one atomic per instance
 		for (int t = threadIdx.x; t < n_tiles; t += 256) s_cnt[t] = 0;
 		__syncthreads();
+		GSR_PROBE(1, 1);
 		for_each_tile(n, lo, hi, grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
 		__syncthreads();
+		GSR_PROBE(1, 2);
 		// (four claims in flight per thread: the atomics return values and would otherwise serialise on their latency)
 		for (int t0 = threadIdx.x; t0 < n_tiles; t0 += 4 * 256) {
 			uint32_t c[4], base[4];
@@ -71,13 +74,17 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 		}
 		__syncthreads();
 	}
+	GSR_PROBE(1, 3);
 	bool overflow = false;
+	// pass 2: claim a slot per (Gaussian, tile) inside the CTA's slice and store the pair.  (Bound by the shared-memory
+	// atomic rate, ~2 cycles per lane and SM; batching the atomics of a lane does not help.)
 	for_each_tile(n, lo, hi, grid_x, key, (uint32_t)idx, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
 		const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
 		if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
 		else overflow = true;
 	});
 	if (overflow) hdr->overflow = 1;
+	GSR_PROBE(1, 4);
 }
 
 // ---- 2. per-tile sort -------------------------------------------------------------------------------
@@ -492,5 +499,7 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	                                                                         (unsigned)R_capacity, id_bits, g.hdr, g.long_tiles);
 	return 3;
 }
+
+GSR_PROBE_READER(probe_read_scatter)
 
 }  // namespace gsr

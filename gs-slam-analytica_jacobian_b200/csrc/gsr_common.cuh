@@ -179,6 +179,27 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t 
 	}
 }
 
+// Optional phase probe (compile with -DGSR_PHASE_PROBE): thread 0 of every CTA records %globaltimer at phase
+// boundaries; tools/phase_probe.py reads the table through gsr_debug_probe().  Not compiled into the product build.
+#ifdef GSR_PHASE_PROBE
+static __device__ unsigned long long g_probe[4096][8];      // one table per translation unit (= per probed kernel)
+__device__ __forceinline__ void probe(int slot)
+{
+	if (threadIdx.x == 0 && blockIdx.x < 4096) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+		g_probe[blockIdx.x][slot] = t;
+	}
+}
+#define GSR_PROBE(k, s) probe(s)
+#define GSR_PROBE_READER(name) \
+	int name(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_probe, sizeof(g_probe)); }
+#else
+#define GSR_PROBE(k, s)
+#define GSR_PROBE_READER(name) \
+	int name(unsigned long long*) { return -1; }
+#endif
+
 // vector reduction to global memory: one 16-byte RED instead of four scalar atomics (sm_90+)
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 {

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	__shared__ bool s_last;
 	extern __shared__ uint32_t s_hist[];   // [tiles] CTA-private tile histogram (hist_smem != 0)
 
+	GSR_PROBE(0, 0);
 	const int row0 = blockIdx.x * 256;
 	const int idx = row0 + threadIdx.x;
 	const int n_tiles = s.grid_x * s.grid_y;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	const bool dc_only = (s.colors_precomp != nullptr) || (s.M == 1);
 	if (dc_only) load_rows3(s.colors_precomp ? s.colors_precomp : s.shs, row0, s.P, s_col, vec_mask & 4);
 	__syncthreads();
+	GSR_PROBE(0, 1);
 
 	unsigned my_tiles = 0, my_vis = 0, rect_lo = 0, rect_hi = 0;
 	if (idx < s.P) {
@@ -248,20 +250,15 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		g.tiles_touched[idx] = my_tiles;
 		g.clamped[idx] = (uint8_t)clamped;
 	}
+	GSR_PROBE(0, 2);
 	// per-tile instance counts (integer REDs): small rectangles lane-parallel, large ones warp-cooperative
 	for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) {
 		if (hist_smem) atomicAdd(&s_hist[tile], 1u);
 		else atomicAdd(&g.tile_count[tile], 1u);
 	});
-	if (hist_smem) {
-		// one coalesced RED per touched tile and CTA instead of one scattered RED per instance
-		__syncthreads();
-		for (int t = threadIdx.x; t < n_tiles; t += 256) {
-			const unsigned c = s_hist[t];
-			if (c) atomicAdd(&g.tile_count[t], c);
-		}
-	}
-	// block totals -> header (integer atomics: deterministic)
+	GSR_PROBE(0, 3);
+	// block totals -> header (integer atomics: deterministic); issued BEFORE the histogram flush so that one fence
+	// covers every global update of this CTA
 	unsigned wt = my_tiles, wv = my_vis;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
@@ -269,28 +266,43 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		wv += __shfl_xor_sync(0xffffffffu, wv, o);
 	}
 	if (lane_id() == 0) { s_red[threadIdx.x >> 5] = wt; s_red[8 + (threadIdx.x >> 5)] = wv; }
-	__threadfence();
-	__syncthreads();
+	__syncthreads();      // also: the CTA-private histogram is complete
 	if (threadIdx.x == 0) {
 		unsigned a = 0, b = 0;
 #pragma unroll
 		for (int w = 0; w < 8; w++) { a += s_red[w]; b += s_red[8 + w]; }
 		if (a) atomicAdd(&g.hdr->num_rendered, a);
 		if (b) atomicAdd(&g.hdr->num_visible, b);
-		__threadfence();
-		s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
 	}
+	if (hist_smem) {
+		// one coalesced RED per touched tile and CTA instead of one scattered RED per instance
+		for (int t = threadIdx.x; t < n_tiles; t += 256) {
+			const unsigned c = s_hist[t];
+			if (c) atomicAdd(&g.tile_count[t], c);
+		}
+	}
+	GSR_PROBE(0, 4);
+	__threadfence();
 	__syncthreads();
+	if (threadIdx.x == 0) s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
+	__syncthreads();
+	GSR_PROBE(0, 5);
 	if (!s_last) return;
 	// The last CTA to finish turns the tile counts into list ranges + scatter cursors (exclusive scan over
 	// the tiles).  Untouched tiles keep the range (0,0) like the reference's memset (rasterizer_impl.cu:360).
 	__threadfence();
 	{
-		const int tiles = s.grid_x * s.grid_y;
+		const int tiles = n_tiles;
 		const int per = (tiles + 255) / 256;
 		const int t0 = min(tiles, (int)threadIdx.x * per), t1 = min(tiles, t0 + per);
+		constexpr int kHold = 8;      // counts of up to 8 tiles per thread stay in registers between the two sweeps
+		unsigned held[kHold];
 		unsigned sum = 0;
-		for (int t = t0; t < t1; t++) sum += __ldcg(&g.tile_count[t]);
+#pragma unroll
+		for (int u = 0; u < kHold; u++) held[u] = (t0 + u < t1) ? __ldcg(&g.tile_count[t0 + u]) : 0u;
+#pragma unroll
+		for (int u = 0; u < kHold; u++) sum += held[u];
+		for (int t = t0 + kHold; t < t1; t++) sum += __ldcg(&g.tile_count[t]);
 		unsigned inc = sum;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -304,16 +316,17 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		for (int w = 0; w < (int)(threadIdx.x >> 5); w++) run += s_red[w];
 		unsigned mx = 0;
 		for (int t = t0; t < t1; t++) {
-			const unsigned c = __ldcg(&g.tile_count[t]);
+			const unsigned c = (t - t0 < kHold) ? held[t - t0] : __ldcg(&g.tile_count[t]);
 			g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
 			g.tile_cursor[t] = run;
-			if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;   // binning.cu: kSmallChunk, kLongChunk
+			if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;   // binning.cu: kSmallChunk
 			run += c;
 			mx = max(mx, c);
 		}
 		if (mx) atomicMax(&g.hdr->max_tile_count, mx);
 		if (threadIdx.x == 0) g.hdr->fwd_blocks_done = 0;
 	}
+	GSR_PROBE(0, 6);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ vm,
@@ -352,5 +365,7 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 	if (P == 0) return;
 	mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
 }
+
+GSR_PROBE_READER(probe_read_preprocess)
 
 }  // namespace gsr

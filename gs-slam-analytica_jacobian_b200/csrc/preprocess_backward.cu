@@ -108,6 +108,7 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 	__shared__ float s_view[16], s_proj[16], s_raw[16];
 	__shared__ float s_tau[8][6];
 	__shared__ bool s_last;
+	GSR_PROBE(2, 0);
 	if (threadIdx.x < 16) {
 		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
 		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
@@ -343,6 +344,7 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 		}
 	}
 
+	GSR_PROBE(2, 1);
 	// ---- block-level 6-vector reduction of the pose gradient ----
 #pragma unroll
 	for (int i = 0; i < 6; i++) tau[i] = warp_sum(tau[i]);
@@ -361,18 +363,29 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 	__syncthreads();
 	if (threadIdx.x == 0) s_last = (atomicAdd(&g.hdr->bwd_blocks_done, 1u) == gridDim.x - 1);
 	__syncthreads();
+	GSR_PROBE(2, 2);
 	if (s_last) {
 		__threadfence();
 		// deterministic final sum: 6 warps, one component each, fixed strided order + shuffle tree
 		const int comp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 		if (comp < 6) {
 			float v = 0.f;
-			for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&g.tau_partial[(size_t)b * 8 + comp]);
+			for (unsigned b0 = lane; b0 < gridDim.x; b0 += 32 * 8) {     // eight independent loads in flight, fixed order
+				float p[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					const unsigned b = b0 + 32 * u;
+					p[u] = b < gridDim.x ? __ldcg(&g.tau_partial[(size_t)b * 8 + comp]) : 0.f;
+				}
+#pragma unroll
+				for (int u = 0; u < 8; u++) v += p[u];
+			}
 			v = warp_sum(v);
 			if (lane == 0) dL_dtau[comp] = v;
 		}
 		if (threadIdx.x == 0) g.hdr->bwd_blocks_done = 0;
 	}
+	GSR_PROBE(2, 3);
 }
 
 }  // namespace
@@ -389,5 +402,7 @@ void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* ra
 	preprocess_backward_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
 	                                                                  dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dtau);
 }
+
+GSR_PROBE_READER(probe_read_preprocess_backward)
 
 }  // namespace gsr

@@ -18,7 +18,7 @@ EXPORTS = (
     "gsr_geometry_bytes", "gsr_image_bytes", "gsr_binning_bytes", "gsr_forward_plan", "gsr_forward_num_rendered",
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
-    "gsr_stage_timing", "gsr_stage_times_ms",
+    "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe",
 )
 
 

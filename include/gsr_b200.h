@@ -138,6 +138,9 @@ unsigned long long gsr_kernel_launch_count(void);
  * forward+backward: {preprocess, binning, render_forward, render_backward, preprocess_backward} */
 int gsr_stage_timing(int enable);
 int gsr_stage_times_ms(float* out5);
+/* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3][4096][8] %globaltimer table
+ * (kernel, CTA, phase) to the host; returns an error in the product build, which carries no probes */
+int gsr_debug_probe(unsigned long long* out, size_t bytes);
 
 const char* gsr_error_string(void);
 int gsr_version(void);
