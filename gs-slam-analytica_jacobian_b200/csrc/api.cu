@@ -103,10 +103,10 @@ int gsr_version(void) { return 101; }
 
 size_t gsr_geometry_bytes(int P, int W, int H) { return gsr::geom_bytes((size_t)(P > 0 ? P : 0), tiles_of(W, H)); }
 size_t gsr_image_bytes(int W, int H) { return gsr::image_bytes((size_t)W, (size_t)H); }
-size_t gsr_binning_bytes(int P, long long cap)
+size_t gsr_binning_bytes(int P, int W, int H, long long cap)
 {
 	(void)P;
-	return gsr::binning_bytes((size_t)(cap > 0 ? cap : 0));
+	return gsr::binning_bytes((size_t)(cap > 0 ? cap : 0), tiles_of(W, H));
 }
 
 int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* radii, int* n_touched, void* stream)
@@ -150,12 +150,12 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
 	if (capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "more than 2^31 tile instances are not supported");
 	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
-	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles_of(s.W, s.H))) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
 	if (!out_color || !out_depth || !out_opacity || (s.P > 0 && !n_touched)) return fail(GSR_ERR_ARG, "null output");
 	cudaStream_t st = (cudaStream_t)stream;
 	const size_t tiles = (size_t)s.grid_x * s.grid_y;
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
-	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
+	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, st);
 	stage_mark(2, st);
@@ -190,7 +190,7 @@ int gsr_rasterize_gaussians(const gsr_scene* a, void* geom, size_t geom_bytes, v
 	long long R = 0, max_tile = 0;
 	rc = gsr_forward_num_rendered(geom, stream, &R, &max_tile);
 	if (rc) return rc;
-	const size_t bytes = gsr_binning_bytes(a->P, R);
+	const size_t bytes = gsr_binning_bytes(a->P, a->W, a->H, R);
 	void* bin = alloc(user, bytes);
 	if (!bin) return fail(GSR_ERR_WORKSPACE, "binning allocator returned null");
 	*binning_out = bin;
@@ -223,7 +223,7 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 	if (dL_drotations && ((size_t)dL_drotations & 15)) return fail(GSR_ERR_ARG, "dL_drotations must be 16-byte aligned");
 	const size_t tiles = (size_t)s.grid_x * s.grid_y;
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
-	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
+	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	stage_mark(4, st);
 	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, st);
@@ -292,7 +292,7 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
 	out[3] = out[5] = out[6] = 0;
 	out[4] = (unsigned long long)g.ranges;
 	if (binning) {
-		gsr::BinView b = gsr::bin_view(binning, (size_t)capacity);
+		gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles_of(W, H));
 		out[3] = (unsigned long long)b.point_list;
 	}
 	if (image) {

@@ -105,18 +105,28 @@ __host__ __device__ inline ImageView image_view(void* base, size_t W, size_t H)
 	return v;
 }
 
-// Binning workspace.  point_list[R] is the product (kept for the backward); the rest is scratch.
+// Binning workspace.  point_list[R] and cull_masks are the products (kept for the backward); the rest is scratch.
 struct BinView {
 	uint32_t* point_list;   // [R]  Gaussian ids sorted by (tile, depth, id)        <- kept
+	uint32_t* cull_masks;   // [(R/32 + tiles) * 8]  per tile, group of 32 list positions and warp: the forward's cull
+	                        //      ballot (bit i = entry 32 g + i may touch the warp's 8x4 pixel block)   <- kept
 	uint2* pairs;           // [R]  (depth key, Gaussian id) scattered into tile segments, unordered inside a segment
 	uint2* pairs_alt;       // [R]  ping-pong partner for tiles too long to sort in shared memory
 };
-__host__ __device__ inline size_t binning_bytes(size_t R) { return align_up(R * 4) + 2 * align_up(R * 8) + GSR_ALIGN; }
-__host__ __device__ inline BinView bin_view(void* base, size_t R)
+__host__ __device__ inline size_t cull_mask_words(size_t R, size_t tiles) { return (R / 32 + tiles + 1) * 8; }
+// first mask word of a tile: groups of different tiles never overlap because a tile with n entries owns
+// ceil(n / 32) <= n / 32 + 1 groups starting at (range.x / 32 + tile)
+__host__ __device__ inline size_t cull_mask_base(uint32_t range_start, uint32_t tile) { return ((size_t)(range_start >> 5) + tile) * 8; }
+__host__ __device__ inline size_t binning_bytes(size_t R, size_t tiles)
+{
+	return align_up(R * 4) + align_up(cull_mask_words(R, tiles) * 4) + 2 * align_up(R * 8) + GSR_ALIGN;
+}
+__host__ __device__ inline BinView bin_view(void* base, size_t R, size_t tiles)
 {
 	char* p = (char*)align_up((size_t)base);
 	BinView b;
 	b.point_list = (uint32_t*)p; p += align_up(R * 4);
+	b.cull_masks = (uint32_t*)p; p += align_up(cull_mask_words(R, tiles) * 4);
 	b.pairs = (uint2*)p; p += align_up(R * 8);
 	b.pairs_alt = (uint2*)p;
 	return b;

@@ -18,6 +18,8 @@
 //   * n_touched (pixels whose transmittance after the blend is still > 0.5, forward.cu:511-514) costs one vote +
 //     one predicated store per entry while any pixel of the warp is above 0.5, nothing afterwards, and ONE
 //     integer RED per (warp, Gaussian).
+// The cull ballots are also written out (one word per warp and 32 list positions): the backward kernel replays them
+// instead of repeating the test.
 #include "render_common.cuh"
 
 namespace gsr {
@@ -75,7 +77,8 @@ __global__ void __launch_bounds__(256)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-                      float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched)
+                      float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched,
+                      uint32_t* __restrict__ cull_masks)
 {
 	__shared__ FwdSmem sm;
 
@@ -94,6 +97,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 	const int rounds = (n + 255) / 256;
 	QueueRec* wq = sm.queue[warp];
 	uint32_t* wmask = sm.tmask[warp];
+	uint32_t* my_masks = cull_masks + cull_mask_base(range.x, (uint32_t)tile) + warp;   // [group of 32 positions][warp]
 
 	float T = inside ? 1.0f : -1.0f;   // sign bit = "done"
 	float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -135,6 +139,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 				keep = may_touch(q0, q1, bx0, by0, bx1, by1);
 			}
 			const unsigned mask = __ballot_sync(kFull, keep);
+			if (lane == 0) my_masks[(b * 8 + (c0 >> 5)) * 8] = mask;   // the backward re-uses the cull instead of repeating it
 			if (mask == 0) continue;
 			const int nq = __popc(mask);
 			const int pos = __popc(mask & lt);
@@ -186,7 +191,8 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
 	render_forward_kernel<<<tiles, 256, 0, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-	                                                  im.final_T, im.n_contrib, out_color, out_depth, out_opacity, n_touched);
+	                                                  im.final_T, im.n_contrib, out_color, out_depth, out_opacity, n_touched,
+	                                                  b.cull_masks);
 }
 
 }  // namespace gsr

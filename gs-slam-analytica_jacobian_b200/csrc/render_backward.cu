@@ -6,8 +6,9 @@
 // The reference reduces ten values per (tile, Gaussian) through a 256-thread shared-memory tree with ~12
 // __syncthreads (backward.cu:626-644, 844-850) followed by ten scalar global atomics (:859-868).
 // Here each warp:
-//   0. culls 32 list entries per step (one per lane, exact test against its 8x4 pixel block) and appends
-//      the survivors, in back-to-front order, to a warp-private ring queue in shared memory;
+//   0. replays the forward's cull ballots (one word per warp and 32 list positions: the exact test of an entry
+//      against the warp's 8x4 pixel block is not repeated) and appends the survivors, in back-to-front order, to a
+//      warp-private ring queue in shared memory;
 //   1. whenever 16 entries are queued, evaluates them with one thread per pixel in a branch-free two-way
 //      unrolled loop (three broadcast LDS.128 per entry at immediate offsets) and boils
 //      every pair down to TWO numbers per pixel,
@@ -145,7 +146,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
-                       GaussAcc* __restrict__ acc)
+                       GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -158,7 +159,6 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	pixel_of_thread(tile_x, tile_y, px, py);
 	const bool inside = px < W && py < H;
 	const float bx0 = (float)(tile_x * GSR_TILE + (warp & 1) * 8), by0 = (float)(tile_y * GSR_TILE + (warp >> 1) * 4);
-	const float bx1 = bx0 + 7.f, by1 = by0 + 3.f;
 	const uint2 range = ranges[tile];
 	const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
 
@@ -190,14 +190,19 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	for (int w = 0; w < 8; w++) top = max(top, sm.wmax[w]);
 	const uint32_t warp_top = m;   // this warp's deepest contributor
 
-	const int rounds = ((int)top + kBatch - 1) / kBatch;
-	// batch b covers list positions [hi_b - cnt_b, hi_b), hi_b = top - kBatch b; smem slot t <-> position hi_b-1-t
+	// The list is walked back to front in groups of 32 positions aligned like the forward's cull chunks, so that the
+	// forward's ballots (cull_masks) can be replayed: batch b covers positions [hi_b - kBatch, hi_b) with
+	// hi_b = top32 - kBatch b (a multiple of 32); smem slot t <-> position hi_b - 1 - t.
+	const int top32 = ((int)top + 31) & ~31;
+	const int rounds = (top32 + kBatch - 1) / kBatch;
+	const uint32_t* my_masks = cull_masks + cull_mask_base(range.x, (uint32_t)tile) + warp;
 	auto stage = [&](int b, int buf) {
-		const int hi = (int)top - b * kBatch;
+		const int hi = top32 - b * kBatch;
 		for (int i = threadIdx.x; i < 3 * kBatch; i += 256) {
 			const int t = i / 3, part = i - 3 * t;
-			if (t < hi) {
-				const uint32_t id = __ldg(point_list + range.x + (hi - 1 - t));
+			const int pos = hi - 1 - t;
+			if (pos >= 0 && pos < (int)top) {
+				const uint32_t id = __ldg(point_list + range.x + pos);
 				if (part == 0) sm.id[buf][t] = id;
 				cp_async16(&sm.rec[buf][t].q0 + part, &rec[id].q0 + part);
 			}
@@ -209,33 +214,37 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	int head = 0, qn = 0;   // ring queue: qn entries starting at slot head (head is a multiple of kSlots)
 	for (int b = 0; b < rounds; b++) {
 		const int buf = b & 1;
-		const int hi = (int)top - b * kBatch;
+		const int hi = top32 - b * kBatch;
 		const int cnt = min(kBatch, hi);
 		__syncthreads();   // everyone is past batch b-1: buffer buf^1 is free
 		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
 		else cp_async_commit();
+		// this warp's cull ballots of the (up to) four groups of the batch: lane j fetches group hi/32 - 1 - j
+		uint32_t fetched = 0;
+		{
+			const int g = (hi >> 5) - 1 - lane;
+			if (lane < kBatch / 32 && g >= 0 && g * 32 < (int)warp_top) fetched = __ldg(my_masks + (size_t)g * 8);
+		}
 		cp_async_wait<1>();
 		__syncthreads();
-		const int first = max(0, hi - (int)warp_top);   // positions >= warp_top are skipped by this warp
-		for (int c0 = first & ~31; c0 < cnt; c0 += 32) {
-			const int t = c0 + lane;
-			bool keep = false;
-			float4 q0, q1;
-			if (t >= first && t < cnt) {
-				q0 = sm.rec[buf][t].q0;
-				q1 = sm.rec[buf][t].q1;
-				keep = may_touch(q0, q1, bx0, by0, bx1, by1);
-			}
+		for (int c0 = 0; c0 < cnt; c0 += 32) {
+			// lane L <-> slot c0 + L <-> position p = hi - 1 - c0 - L = 32 g + (31 - L)
+			const uint32_t fm = __shfl_sync(kFull, fetched, c0 >> 5);
+			const int p = hi - 1 - c0 - lane;
+			const bool keep = ((fm >> (31 - lane)) & 1u) && p < (int)warp_top;   // positions >= warp_top cannot contribute
 			const unsigned mask = __ballot_sync(kFull, keep);
 			if (mask == 0) continue;
 			if (keep) {
+				const int t = c0 + lane;
+				const float4 q0 = sm.rec[buf][t].q0;
+				const float4 q1 = sm.rec[buf][t].q1;
 				const float4 q2 = sm.rec[buf][t].q2;
 				int slot = head + qn + __popc(mask & lt);
 				if (slot >= kQueueCap) slot -= kQueueCap;
 				QueueRec* dst = wq + slot;
 				dst->w0 = q0;
 				dst->w1 = make_float4(q1.x, q1.y, q1.w, q2.x);
-				dst->w2 = make_float4(q2.y, q1.z, __int_as_float(hi - 1 - t), __uint_as_float(sm.id[buf][t]));
+				dst->w2 = make_float4(q2.y, q1.z, __int_as_float(p), __uint_as_float(sm.id[buf][t]));
 			}
 			qn += __popc(mask);
 			__syncwarp();
@@ -277,7 +286,7 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 		configured = true;
 	}
 	render_backward_kernel<<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-	                                                     im.final_T, im.n_contrib, dL_dpix, dL_dpix_depth, g.acc);
+	                                                     im.final_T, im.n_contrib, dL_dpix, dL_dpix_depth, g.acc, b.cull_masks);
 }
 
 }  // namespace gsr

@@ -100,7 +100,7 @@ def _forward_impl(call, capacity=None):
             max_tile = int(mt.value)
         else:
             num_rendered, cap, max_tile = -1, int(capacity), 0
-        bin_bytes = _L.gsr_binning_bytes(P, cap)
+        bin_bytes = _L.gsr_binning_bytes(P, W, H, cap)
         binning = torch.empty((bin_bytes,), **u8)
         _cabi.check(_L.gsr_forward_render(C.byref(call.scene), _ptr(geom), _ptr(binning), bin_bytes, cap, num_rendered, max_tile,
                                           _ptr(img), img_bytes, _ptr(color), _ptr(depth), _ptr(opacity), _ptr(n_touched), st),

@@ -67,7 +67,7 @@ def load():
     lib.gsr_image_bytes.restype = sz
     lib.gsr_image_bytes.argtypes = [ip, ip]
     lib.gsr_binning_bytes.restype = sz
-    lib.gsr_binning_bytes.argtypes = [ip, ll]
+    lib.gsr_binning_bytes.argtypes = [ip, ip, ip, ll]
     lib.gsr_forward_plan.argtypes = [sp, vp, sz, vp, vp, vp]
     lib.gsr_forward_num_rendered.argtypes = [vp, vp, C.POINTER(ll), C.POINTER(ll)]
     lib.gsr_forward_render.argtypes = [sp, vp, vp, sz, ll, ll, ll, vp, sz, vp, vp, vp, vp, vp]

@@ -124,7 +124,7 @@ class RasterEngine:
         need = int(num_rendered * self.headroom) + 4096
         if need > self.capacity:
             self.capacity = need
-            self.bin_bytes = _L.gsr_binning_bytes(self.P, self.capacity)
+            self.bin_bytes = _L.gsr_binning_bytes(self.P, self.W, self.H, self.capacity)
             self.binning = torch.empty((self.bin_bytes,), dtype=torch.uint8, device=self.dev)
             self.graph_fwd = self.graph_bwd = self.graph_all = None   # pointers changed
         return self.capacity

@@ -75,7 +75,7 @@ typedef void* (*gsr_alloc_fn)(void* user, size_t bytes);
 /* ---- workspace sizes (reference: required<GeometryState/ImageState/BinningState>) ---- */
 size_t gsr_geometry_bytes(int P, int W, int H);
 size_t gsr_image_bytes(int W, int H);
-size_t gsr_binning_bytes(int P, long long num_rendered_capacity);
+size_t gsr_binning_bytes(int P, int W, int H, long long num_rendered_capacity);
 
 /* ---- forward ---- */
 /* Stage A: per-Gaussian preprocess, per-tile instance counts and tile ranges.  Writes radii[P] and

@@ -34,7 +34,7 @@ def test_workspace_sizes_monotone():
     g1, g2 = lib.gsr_geometry_bytes(1000, 640, 480), lib.gsr_geometry_bytes(100000, 640, 480)
     assert 0 < g1 < g2 and g2 >= 100000 * (48 + 64 + 4 + 1) + 1200 * 16
     assert lib.gsr_image_bytes(640, 480) >= 640 * 480 * 8
-    b1, b2 = lib.gsr_binning_bytes(1000, 10000), lib.gsr_binning_bytes(1000, 1000000)
+    b1, b2 = lib.gsr_binning_bytes(1000, 640, 480, 10000), lib.gsr_binning_bytes(1000, 640, 480, 1000000)
     assert b1 < b2 and b2 >= 1000000 * 12
     assert lib.gsr_geometry_bytes(0, 16, 16) > 0
 
