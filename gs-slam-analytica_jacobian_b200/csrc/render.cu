@@ -127,6 +127,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 		cp_async_wait<1>();
 		__syncthreads();
 		const int cnt = min(256, n - b * 256);
+		uint32_t held_mask = 0;
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
 			if (__all_sync(kFull, T < 0.f)) break;
 			// cull phase: one list entry per lane
@@ -139,7 +140,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 				keep = may_touch(q0, q1, bx0, by0, bx1, by1);
 			}
 			const unsigned mask = __ballot_sync(kFull, keep);
-			if (lane == 0) my_masks[(b * 8 + (c0 >> 5)) * 8] = mask;   // the backward re-uses the cull instead of repeating it
+			if (lane == (c0 >> 5)) held_mask = mask;   // lane j keeps the ballot of chunk j; stored once per batch
 			if (mask == 0) continue;
 			const int nq = __popc(mask);
 			const int pos = __popc(mask & lt);
@@ -168,6 +169,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 			}
 			__syncwarp();   // queue fully consumed before the next chunk overwrites it
 		}
+		// the backward replays these ballots instead of repeating the cull (chunks this warp skipped stay 0: they lie
+		// behind its last contributor and are never read)
+		if (lane < 8 && (b * 8 + lane) * 32 < n) my_masks[(b * 8 + lane) * 8] = held_mask;   // only this tile's own groups
 	}
 	cp_async_wait<0>();
 	if (inside) {
