@@ -2,6 +2,7 @@
 // carve-up, stream plumbing; no torch types, no global state beyond a thread-local error string.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include "../../include/gsr_b200.h"
@@ -19,6 +20,7 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py: gpu_launches)
 // optional stage timing (bench.py roofline): CUDA events recorded on the launching stream between stages
 bool g_timing = false;
+const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
 cudaEvent_t g_ev[7];
 void stage_mark(int i, cudaStream_t st)
 {
@@ -157,11 +159,13 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
-	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, st);
+	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
+	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= 2048 && !g_no_fused_sort;
+	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st);
 	stage_mark(2, st);
 	rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
-	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, st);
+	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, (size_t)capacity, st);
 	stage_mark(3, st);
 	g_launches += 1;
 	return debug_sync(a, st, "render");

@@ -28,11 +28,14 @@ struct Scene {
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
 // returns the number of kernels launched; cap_smem = longest tile list the 256-thread sort holds in shared memory,
 // max_tile_hint = longest list expected (<= 0: unknown)
+// fuse_sort: launch only the scatter; the per-tile sort then runs inside the forward compositing kernel
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
-                   cudaStream_t stream);
+                   bool fuse_sort, cudaStream_t stream);
 size_t tile_sort_smem_bytes(int cap_smem);
+// fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
-                           float* out_depth, float* out_opacity, int* n_touched, cudaStream_t stream);
+                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, size_t R_capacity,
+                           cudaStream_t stream);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
                             const float* dL_dpix, const float* dL_dpix_depth, cudaStream_t stream);
 void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,

@@ -21,6 +21,7 @@
 // The cull ballots are also written out (one word per warp and 32 list positions): the backward kernel replays them
 // instead of repeating the test.
 #include "render_common.cuh"
+#include "tile_sort.cuh"
 
 namespace gsr {
 
@@ -73,14 +74,41 @@ __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int 
 	}
 }
 
-__global__ void __launch_bounds__(256)
-render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+// FUSED_SORT: the CTA first sorts its tile's scattered (depth, id) segment (tile_sort.cuh; lists of at most 2048 entries
+// in shared memory, anything else through the general path) and composites straight from the sorted ids it keeps in
+// shared memory.  One launch less, no point_list round trip before the first gather, and the latency-bound sort phases
+// of one CTA overlap the issue-bound blending of the other CTAs on the SM.
+struct FusedSortArgs {
+	uint2* ranges;
+	uint2* pairs;
+	uint2* pairs_alt;
+	uint32_t* point_list;
+	unsigned capacity;
+	int id_bits;
+	GeomHeader* hdr;
+};
+constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
+constexpr int kFusedIdsCap = 2048;
+
+template <bool FUSED_SORT>
+__global__ void __launch_bounds__(256, 4)
+render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched,
-                      uint32_t* __restrict__ cull_masks)
+                      uint32_t* __restrict__ cull_masks, FusedSortArgs fs)
 {
-	__shared__ FwdSmem sm;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	static_assert(sizeof(FwdSmem) <= kFusedIdsOffset, "sorted ids must sit behind the compositing overlay");
+	FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+	const uint32_t* s_ids = reinterpret_cast<const uint32_t*>(smem_raw + kFusedIdsOffset);
+	if (FUSED_SORT) {
+		sort_tile<256>((int)blockIdx.x, fs.ranges, fs.pairs, fs.pairs_alt, fs.point_list, fs.capacity, kSmallChunk, fs.id_bits,
+		               fs.hdr, reinterpret_cast<uint32_t*>(smem_raw), reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset),
+		               kFusedIdsCap);
+		__threadfence_block();
+		__syncthreads();      // sorted ids (shared + global) and a possibly clamped range are visible to the whole CTA
+	}
 
 	const int tile = blockIdx.x;
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
@@ -92,9 +120,10 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 	const float pxf = (float)px, pyf = (float)py;
 	const float bx0 = (float)(tile_x * GSR_TILE + (warp & 1) * 8), by0 = (float)(tile_y * GSR_TILE + (warp >> 1) * 4);
 	const float bx1 = bx0 + 7.f, by1 = by0 + 3.f;
-	const uint2 range = ranges[tile];
+	const uint2 range = FUSED_SORT ? __ldcg(&fs.ranges[tile]) : ranges[tile];
 	const int n = (int)(range.y - range.x);
 	const int rounds = (n + 255) / 256;
+	const bool ids_in_smem = FUSED_SORT && n <= kFusedIdsCap;
 	QueueRec* wq = sm.queue[warp];
 	uint32_t* wmask = sm.tmask[warp];
 	uint32_t* my_masks = cull_masks + cull_mask_base(range.x, (uint32_t)tile) + warp;   // [group of 32 positions][warp]
@@ -108,7 +137,8 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 	auto stage = [&](int b, int buf) {
 		const int i = b * 256 + threadIdx.x;
 		if (i < n) {
-			const uint32_t id = __ldg(point_list + range.x + i);
+			// fused: ids come from shared memory; a list too long for it was written by this CTA -> coherent load
+			const uint32_t id = ids_in_smem ? s_ids[i] : (FUSED_SORT ? __ldcg(point_list + range.x + i) : __ldg(point_list + range.x + i));
 			sm.id[buf][threadIdx.x] = id;
 			const GaussRec* r = rec + id;
 			cp_async16(&sm.rec[buf][threadIdx.x].q0, &r->q0);
@@ -190,13 +220,33 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 }  // namespace
 
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
-                           float* out_depth, float* out_opacity, int* n_touched, cudaStream_t stream)
+                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, size_t R_capacity,
+                           cudaStream_t stream)
 {
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
-	render_forward_kernel<<<tiles, 256, 0, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-	                                                  im.final_T, im.n_contrib, out_color, out_depth, out_opacity, n_touched,
-	                                                  b.cull_masks);
+	FusedSortArgs fs;
+	fs.ranges = g.ranges; fs.pairs = b.pairs; fs.pairs_alt = b.pairs_alt; fs.point_list = b.point_list;
+	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr;
+	fs.id_bits = 1;
+	while (fs.id_bits < 32 && (1ll << fs.id_bits) < (long long)s.P) fs.id_bits++;
+	static bool configured = false;
+	const size_t smem_plain = sizeof(FwdSmem);
+	const size_t smem_fused = sort_smem_bytes(kSmallChunk, 256) > (size_t)kFusedIdsOffset + kFusedIdsCap * 4
+	                              ? sort_smem_bytes(kSmallChunk, 256) : (size_t)kFusedIdsOffset + kFusedIdsCap * 4;
+	if (!configured) {
+		cudaFuncSetAttribute(render_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused);
+		cudaFuncSetAttribute(render_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
+		configured = true;
+	}
+	if (fused_sort && s.P > 0 && R_capacity > 0)
+		render_forward_kernel<true><<<tiles, 256, smem_fused, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
+		                                                                im.final_T, im.n_contrib, out_color, out_depth, out_opacity,
+		                                                                n_touched, b.cull_masks, fs);
+	else
+		render_forward_kernel<false><<<tiles, 256, smem_plain, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
+		                                                                 im.final_T, im.n_contrib, out_color, out_depth, out_opacity,
+		                                                                 n_touched, b.cull_masks, fs);
 }
 
 }  // namespace gsr
