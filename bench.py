@@ -127,15 +127,23 @@ def l2_flusher(device):
     return flush
 
 
-def roofline_bytes(P, R, HW):
-    """Algorithmic bytes per stage (SH degree 0)."""
+def roofline_bytes(P, R, HW, fused_sort=False):
+    """Algorithmic bytes per stage (SH degree 0).  The 44 B/instance of binning are 12 (write key +
+    value) + 24 (one ideal sort pass: 12 read + 12 write) + 8 (key read for the ranges); when the forward compositing
+    kernel sorts its own tile (lists <= 2048 entries) the "binning" stage is the scatter alone and the sort + range
+    bytes move to "render_forward"."""
+    sort = 32 * R if fused_sort else 0
     return {
         "preprocess": (56 + 8 + 44) * P,
-        "binning": 44 * R,
-        "render_forward": 44 * R + 28 * HW,
+        "binning": 44 * R - sort,
+        "render_forward": 44 * R + 28 * HW + sort,
         "render_backward": (44 + 40) * R + 24 * HW + 40 * P,
         "preprocess_backward": (60 + 40 + 68) * P,
     }
+
+
+def fused_sort_active(eng):
+    return 0 < eng.max_tile_hint <= 2048 and not os.environ.get("GSR_NO_FUSED_SORT")
 
 
 def peaks():
@@ -279,7 +287,7 @@ def run_ours(args, rank, world, device):
     names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
     R_mean = float(np.mean(Rs[Wm:]))
     HW = cfg["W"] * cfg["H"]
-    rb = roofline_bytes(cfg["P"], R_mean, HW)
+    rb = roofline_bytes(cfg["P"], R_mean, HW, fused_sort_active(eng))
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2       # dominant single kernel: one of the two composite kernels
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9
@@ -307,7 +315,8 @@ def run_ours(args, rank, world, device):
                    "num_rendered_mean": R_mean, "tiles": ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16),
                    "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
                    "parallelism": "pose-parallel x%d (one independent tracking stream per GPU, no collective)" % world,
-                   "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d" % eng.capacity},
+                   "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d; per-tile sort %s"
+                           % (eng.capacity, "fused into the forward compositing kernel" if fused_sort_active(eng) else "in its own kernels")},
         "e2e": {"value": world * K / emax, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3,
                 "what": "pinned pose block + pinned dL/dcolor,dL/ddepth H2D, dL/dtau + header D2H, host sync every step"},
@@ -455,7 +464,7 @@ def run_window(args, rank, world, device):
         return None
     HW = W * H
     R_view = R_sum / V
-    rb = roofline_bytes(cfg["P"], R_view, HW)
+    rb = roofline_bytes(cfg["P"], R_view, HW, fused_sort_active(eng))
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
