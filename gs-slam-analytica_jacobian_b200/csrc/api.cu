@@ -260,6 +260,39 @@ int gsr_debug_probe(unsigned long long* out, size_t bytes)
 	return GSR_OK;
 }
 
+size_t gsr_slam_loss_scratch_bytes(int W, int H) { return gsr::slam_loss_scratch_bytes(W, H); }
+
+int gsr_slam_loss(int W, int H, const float* color, const float* depth, const float* opacity, const float* gt_color,
+                  const float* gt_depth, const unsigned char* grad_mask, const float* exposure, float rgb_boundary_threshold,
+                  float alpha, int use_depth, int opacity_weighted, float* dL_dcolor, float* dL_ddepth, float* sums,
+                  void* scratch, void* stream)
+{
+	if (W <= 0 || H <= 0) return fail(GSR_ERR_ARG, "bad W/H");
+	if (!color || !depth || !opacity || !gt_color || !dL_dcolor || !dL_ddepth || !sums || !scratch) return fail(GSR_ERR_ARG, "null argument");
+	if (use_depth && !gt_depth) return fail(GSR_ERR_ARG, "gt_depth is required by the RGB-D loss");
+	gsr::SlamLossArgs a;
+	a.W = W; a.H = H; a.color = color; a.depth = depth; a.opacity = opacity; a.gt_color = gt_color; a.gt_depth = gt_depth;
+	a.grad_mask = grad_mask; a.exposure = exposure; a.rgb_boundary_threshold = rgb_boundary_threshold; a.alpha = alpha;
+	a.use_depth = use_depth; a.opacity_weighted = opacity_weighted; a.dL_dcolor = dL_dcolor; a.dL_ddepth = dL_ddepth; a.sums = sums;
+	gsr::launch_slam_loss(a, scratch, (cudaStream_t)stream);
+	g_launches += 1;
+	return check_cuda("slam_loss");
+}
+
+int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* exposure, float* adam_state, float* RT,
+                      const float* proj_raw, float* camera_block, int* status, float lr_rot, float lr_trans, float lr_exposure,
+                      float converged_threshold, void* stream)
+{
+	if (!dL_dtau || !adam_state || !RT || !proj_raw || !camera_block || !status) return fail(GSR_ERR_ARG, "null argument");
+	gsr::TrackingStepArgs a;
+	a.dL_dtau = dL_dtau; a.dL_dexposure = dL_dexposure; a.exposure = exposure; a.adam_state = adam_state; a.RT = RT;
+	a.proj_raw = proj_raw; a.camera_block = camera_block; a.status = status; a.lr_rot = lr_rot; a.lr_trans = lr_trans;
+	a.lr_exposure = lr_exposure; a.converged_threshold = converged_threshold;
+	gsr::launch_tracking_step(a, (cudaStream_t)stream);
+	g_launches += 1;
+	return check_cuda("tracking_step");
+}
+
 unsigned long long gsr_kernel_launch_count(void) { return g_launches.load(); }
 
 int gsr_stage_timing(int enable)

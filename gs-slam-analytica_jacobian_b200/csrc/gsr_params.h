@@ -24,6 +24,38 @@ struct Scene {
 	int accumulate_grads;
 };
 
+// slam_ops.cu -------------------------------------------------------------------------------------------------------
+struct SlamLossArgs {
+	int W, H;
+	const float* color;        // [3,H,W] rendered
+	const float* depth;        // [1,H,W] rendered
+	const float* opacity;      // [1,H,W] rendered
+	const float* gt_color;     // [3,H,W]
+	const float* gt_depth;     // [1,H,W] or null when use_depth == 0
+	const unsigned char* grad_mask;   // [H,W] bool or null
+	const float* exposure;     // [2] = (a, b) or null (initialization: image_ab = image)
+	float rgb_boundary_threshold, alpha;
+	int use_depth;             // RGB-D loss (alpha * rgb + (1 - alpha) * depth) instead of rgb only
+	int opacity_weighted;      // tracking variant: rgb term weighted by opacity, depth term masked by opacity > 0.95
+	float* dL_dcolor;          // [3,H,W] out
+	float* dL_ddepth;          // [1,H,W] out
+	float* sums;               // [4] out: loss, dL/dexposure_a, dL/dexposure_b, 0
+};
+struct TrackingStepArgs {
+	const float* dL_dtau;      // [6] = [rho, theta] gradient of the rasterizer
+	const float* dL_dexposure; // [4] the loss kernel's `sums` (or null)
+	float* exposure;           // [2] in/out (or null)
+	float* adam_state;         // [17]: exp_avg[8], exp_avg_sq[8], step
+	float* RT;                 // [12] in/out: R row-major (9), T (3)   (world-to-camera)
+	const float* proj_raw;     // [16] projection_matrix as the reference stores it (transposed P)
+	float* camera_block;       // [52] out: view | proj | proj_raw | campos (RasterEngine camera block)
+	int* status;               // [4] out: converged, iterations done, first converged iteration, 0
+	float lr_rot, lr_trans, lr_exposure, converged_threshold;
+};
+size_t slam_loss_scratch_bytes(int W, int H);
+void launch_slam_loss(const SlamLossArgs& a, void* scratch, cudaStream_t stream);
+void launch_tracking_step(const TrackingStepArgs& a, cudaStream_t stream);
+
 // launchers (defined in the .cu files, all asynchronous on `stream`)
 void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
 // returns the number of kernels launched; cap_smem = longest tile list the 256-thread sort holds in shared memory,

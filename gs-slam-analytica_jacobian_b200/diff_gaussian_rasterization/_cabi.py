@@ -18,7 +18,8 @@ EXPORTS = (
     "gsr_geometry_bytes", "gsr_image_bytes", "gsr_binning_bytes", "gsr_forward_plan", "gsr_forward_num_rendered",
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
-    "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe",
+    "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
+    "gsr_tracking_step",
 )
 
 
@@ -81,6 +82,12 @@ def load():
     lib.gsr_kernel_launch_count.restype = C.c_ulonglong
     lib.gsr_stage_timing.argtypes = [ip]
     lib.gsr_stage_times_ms.argtypes = [C.POINTER(C.c_float)]
+    lib.gsr_debug_probe.argtypes = [C.POINTER(C.c_ulonglong), sz]
+    lib.gsr_slam_loss_scratch_bytes.restype = sz
+    lib.gsr_slam_loss_scratch_bytes.argtypes = [ip, ip]
+    fl = C.c_float
+    lib.gsr_slam_loss.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, vp, fl, fl, ip, ip, vp, vp, vp, vp, vp]
+    lib.gsr_tracking_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, fl, fl, fl, fl, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

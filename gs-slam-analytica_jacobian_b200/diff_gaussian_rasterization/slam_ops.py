@@ -1,0 +1,151 @@
+"""The callers on either side of the rasterizer in the SLAM loops, on the device:
+
+  slam_loss(...)        the reference's tracking / mapping losses (utils/slam_utils.py:56-128) and their gradients
+                        w.r.t. the rendered images and the exposure parameters in ONE kernel;
+  tracking_step(...)    torch.optim.Adam on [cam_rot_delta, cam_trans_delta, exposure_a, exposure_b]
+                        (utils/slam_frontend.py:129-162) + update_pose (utils/pose_utils.py:76-93) + the camera tensors
+                        of the next render (utils/camera_utils.py:96-109) in ONE kernel;
+  TrackingLoop          render -> loss -> backward -> optimiser -> pose update captured as ONE CUDA graph per iteration
+                        on top of a RasterEngine: the reference's tracking loop (utils/slam_frontend.py:163-192) without a
+                        host round trip per iteration; convergence is polled every `check_every` iterations.
+All compute goes through the C-ABI (include/gsr_b200.h); torch owns memory and streams.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+
+_L = _cabi.load()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class LossWorkspace:
+    """Reusable outputs + scratch of slam_loss for one image size."""
+
+    def __init__(self, W, H, device="cuda"):
+        dev = torch.device(device)
+        self.W, self.H, self.dev = int(W), int(H), dev
+        self.dL_dcolor = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        self.dL_ddepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(4, dtype=torch.float32, device=dev)      # loss, dL/da, dL/db, 0
+        self.scratch = torch.zeros(_L.gsr_slam_loss_scratch_bytes(W, H), dtype=torch.uint8, device=dev)
+
+
+def slam_loss(ws, color, depth, opacity, gt_color, gt_depth=None, grad_mask=None, exposure=None, rgb_boundary_threshold=0.01,
+              alpha=0.95, tracking=True, dL_dcolor=None, dL_ddepth=None):
+    """One kernel: loss + dL/dcolor + dL/ddepth + dL/dexposure.  tracking=True: get_loss_tracking (opacity-weighted,
+    grad_mask); False: get_loss_mapping.  gt_depth=None selects the monocular variants.  exposure: device tensor (a, b) or
+    None.  Gradients land in ws.dL_dcolor / ws.dL_ddepth unless explicit outputs are given; returns ws.sums (device)."""
+    gc = ws.dL_dcolor if dL_dcolor is None else dL_dcolor
+    gd = ws.dL_ddepth if dL_ddepth is None else dL_ddepth
+    with torch.cuda.device(ws.dev):
+        _cabi.check(_L.gsr_slam_loss(ws.W, ws.H, _p(color), _p(depth), _p(opacity), _p(gt_color), _p(gt_depth), _p(grad_mask),
+                                     _p(exposure), float(rgb_boundary_threshold), float(alpha), 0 if gt_depth is None else 1,
+                                     1 if tracking else 0, _p(gc), _p(gd), _p(ws.sums), _p(ws.scratch), _stream(ws.dev)), "slam_loss")
+    return ws.sums
+
+
+class PoseState:
+    """World-to-camera pose (R row-major, T), exposure (a, b), Adam state and status of one tracked frame, on the device."""
+
+    def __init__(self, R, T, proj_raw, device="cuda", exposure=(0.0, 0.0)):
+        dev = torch.device(device)
+        self.dev = dev
+        self.RT = torch.cat([torch.as_tensor(R, dtype=torch.float32).reshape(9), torch.as_tensor(T, dtype=torch.float32).reshape(3)]).to(dev)
+        self.proj_raw = torch.as_tensor(proj_raw, dtype=torch.float32).reshape(16).to(dev).contiguous()
+        self.exposure = torch.tensor(exposure, dtype=torch.float32, device=dev)
+        self.adam = torch.zeros(17, dtype=torch.float32, device=dev)
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)     # converged, iterations, first converged iteration
+
+    def reset_optimizer(self):
+        self.adam.zero_()
+        self.status.zero_()
+
+
+def tracking_step(pose, dL_dtau, dL_dexposure, camera_block, lr_rot=0.003, lr_trans=0.001, lr_exposure=0.01,
+                  converged_threshold=1e-4):
+    """Adam + update_pose + next camera block, one kernel.  dL_dtau: the rasterizer's [rho, theta] gradient;
+    dL_dexposure: the `sums` tensor of slam_loss (or None)."""
+    with torch.cuda.device(pose.dev):
+        _cabi.check(_L.gsr_tracking_step(_p(dL_dtau), _p(dL_dexposure), _p(pose.exposure), _p(pose.adam), _p(pose.RT), _p(pose.proj_raw),
+                                         _p(camera_block), _p(pose.status), float(lr_rot), float(lr_trans), float(lr_exposure),
+                                         float(converged_threshold), _stream(pose.dev)), "tracking_step")
+
+
+def camera_block_from_pose(pose, camera_block):
+    """Fill the engine's camera block from the current R, T without moving the pose (zero gradients, fresh Adam state)."""
+    z6 = torch.zeros(6, dtype=torch.float32, device=pose.dev)
+    adam, status, expo = pose.adam.clone(), pose.status.clone(), pose.exposure.clone()
+    tracking_step(pose, z6, None, camera_block, 0.0, 0.0, 0.0, -1.0)
+    pose.adam.copy_(adam); pose.status.copy_(status); pose.exposure.copy_(expo)
+
+
+class TrackingLoop:
+    """The reference's per-frame tracking loop (utils/slam_frontend.py:129-192) as one CUDA graph per iteration."""
+
+    def __init__(self, engine, pose, gt_color, gt_depth=None, grad_mask=None, rgb_boundary_threshold=0.01, alpha=0.95,
+                 lr_rot=0.003, lr_trans=0.001, lr_exposure=0.01, converged_threshold=1e-4):
+        self.eng, self.pose = engine, pose
+        self.gt_color, self.gt_depth, self.grad_mask = gt_color, gt_depth, grad_mask
+        self.ws = LossWorkspace(engine.W, engine.H, engine.dev)
+        self.kw = dict(rgb_boundary_threshold=rgb_boundary_threshold, alpha=alpha)
+        self.lrs = (lr_rot, lr_trans, lr_exposure, converged_threshold)
+        self.graph = None
+        camera_block_from_pose(pose, engine.cam)
+
+    def _iteration(self):
+        eng = self.eng
+        eng.launch_forward()
+        slam_loss(self.ws, eng.color, eng.depth, eng.opacity, self.gt_color, self.gt_depth, self.grad_mask, self.pose.exposure,
+                  tracking=True, dL_dcolor=eng.dL_dcolor, dL_ddepth=eng.dL_ddepth, **self.kw)
+        eng.launch_backward()
+        tracking_step(self.pose, eng.g_tau, self.ws.sums, eng.cam, *self.lrs)
+
+    def capture(self):
+        eng = self.eng
+        if eng.binning is None:
+            eng.calibrate()
+        # warm-up on a side stream with the state restored afterwards (the warm-up moves the pose)
+        keep = [t.clone() for t in (self.pose.RT, self.pose.exposure, self.pose.adam, self.pose.status, eng.cam)]
+        side = torch.cuda.Stream(eng.dev)
+        side.wait_stream(torch.cuda.current_stream(eng.dev))
+        with torch.cuda.stream(side):
+            self._iteration()
+        torch.cuda.current_stream(eng.dev).wait_stream(side)
+        torch.cuda.synchronize(eng.dev)
+        for dst, src in zip((self.pose.RT, self.pose.exposure, self.pose.adam, self.pose.status, eng.cam), keep):
+            dst.copy_(src)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        for dst, src in zip((self.pose.RT, self.pose.exposure, self.pose.adam, self.pose.status, eng.cam), keep):
+            dst.copy_(src)
+
+    def run(self, max_iters=100, check_every=10, use_graph=True):
+        """Iterate until converged (polled every `check_every` iterations like the reference's GUI cadence) or max_iters.
+        Returns (iterations run, first converged iteration or 0, overflow flag of the last forward)."""
+        if use_graph and self.graph is None:
+            self.capture()
+        done = 0
+        while done < max_iters:
+            n = min(check_every, max_iters - done)
+            for _ in range(n):
+                if use_graph:
+                    self.graph.replay()
+                else:
+                    self._iteration()
+            done += n
+            st = self.pose.status.cpu()
+            if int(st[2]) != 0:
+                break
+        _, overflow = self.eng.header()
+        st = self.pose.status.cpu()
+        return int(st[1]), int(st[2]), overflow

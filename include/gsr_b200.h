@@ -124,6 +124,32 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* s, const int* radii, void*
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present /*[P] bool*/, void* stream);
 
+/* ---- the callers on either side of the path, so that a whole tracking / mapping iteration can
+ *      run without host round trips ---- */
+/* Loss of utils/slam_utils.py:56-128 and its gradients in one pass over the pixels.
+ *   tracking, RGB-D:    use_depth=1 opacity_weighted=1 grad_mask!=null   (get_loss_tracking_rgbd :76-89)
+ *   tracking, monocular use_depth=0 opacity_weighted=1 grad_mask!=null   (get_loss_tracking_rgb  :63-73)
+ *   mapping,  RGB-D:    use_depth=1 opacity_weighted=0 grad_mask=null    (get_loss_mapping_rgbd  :115-128)
+ *   mapping,  monocular use_depth=0 opacity_weighted=0 grad_mask=null    (get_loss_mapping_rgb   :100-112)
+ * exposure = (a, b) device pointer: image_ab = exp(a) image + b; null = no exposure (initialization).
+ * sums[4] <- {loss, dL/da, dL/db, 0}.  The gradient w.r.t. the opacity image is not produced: the reference
+ * rasterizer drops it (diff_gaussian_rasterization/__init__.py:114,139-140).
+ * scratch: gsr_slam_loss_scratch_bytes() bytes, zero-filled ONCE by the caller, reusable across calls. */
+size_t gsr_slam_loss_scratch_bytes(int W, int H);
+int gsr_slam_loss(int W, int H, const float* color, const float* depth, const float* opacity, const float* gt_color,
+                  const float* gt_depth, const unsigned char* grad_mask, const float* exposure, float rgb_boundary_threshold,
+                  float alpha, int use_depth, int opacity_weighted, float* dL_dcolor, float* dL_ddepth, float* sums,
+                  void* scratch, void* stream);
+/* torch.optim.Adam step on [cam_rot_delta, cam_trans_delta, exposure_a, exposure_b] (utils/slam_frontend.py:129-162,
+ * torch defaults) + update_pose (utils/pose_utils.py:76-93) + the camera tensors of the next render
+ * (utils/camera_utils.py:96-109) as the 52-float camera block view|proj|proj_raw|campos.
+ * adam_state[17] = exp_avg[8], exp_avg_sq[8], step (zero-initialised by the caller per tracked frame);
+ * RT[12] = R row-major, T (world-to-camera), updated in place; status[4] <- {converged, iterations, first converged
+ * iteration (sticky, 0 = not yet), 0}; dL_dexposure = the loss call's `sums` (or null), exposure may be null. */
+int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* exposure, float* adam_state, float* RT,
+                      const float* proj_raw, float* camera_block, int* status, float lr_rot, float lr_trans, float lr_exposure,
+                      float converged_threshold, void* stream);
+
 /* ---- introspection (tests / parity): device pointers into the workspaces of the last forward ---- */
 /* out[0]=records (48 B each: x,y,conic.xx,conic.xy | conic.yy,opacity,depth,r | g,b,rect_min,rect_max)
  * out[1]=tiles_touched u32[P]  out[2]=clamped u8[P]  out[3]=point_list u32[R]  out[4]=ranges u32[2*tiles]
