@@ -493,6 +493,140 @@ def run_window(args, rank, world, device):
     return line
 
 
+def _tracking_setup(device):
+    """C1 scene, ground-truth images rendered at the base pose, start pose = Exp(noise) * base."""
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+
+    cfg = S.CONFIGS["C1_tum_tracking"]
+    sc = S.make_scene("C1_tum_tracking", seed=0)
+    t = S.to_torch(sc, device)
+    mk = lambda: RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                              cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
+    base = S.base_pose()
+    cam = S.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], base)
+    eng = mk()
+    eng.set_camera(RasterEngine.pack_camera(*(torch.from_numpy(cam[k]) for k in ("viewmatrix", "projmatrix", "projmatrix_raw", "campos"))).to(device))
+    eng.calibrate()
+    eng.launch_forward()
+    gt_color, gt_depth = eng.color.clone(), eng.depth.clone()
+    start = S.se3_exp([0.01, -0.008, 0.012, 0.004, -0.003, 0.002]) @ base
+    gmask = torch.ones((cfg["H"], cfg["W"]), dtype=torch.uint8, device=device)
+    return cfg, sc, t, cam, mk, start, gt_color, gt_depth, gmask
+
+
+def run_tracking_loop(args, rank, world, device):
+    """Whole tracking iterations (render -> loss -> backward -> Adam -> update_pose -> camera tensors) per second:
+    ours = one CUDA graph replay per iteration (slam_ops.TrackingLoop); value is device time per replay, e2e is the wall
+    clock of the loop with the convergence status polled every 10 iterations."""
+    from diff_gaussian_rasterization import _cabi
+    from diff_gaussian_rasterization import slam_ops as SO
+
+    L = _cabi.load()
+    K, Wm = args.steps, args.warmup
+    cfg, sc, t, cam, mk, start, gt_color, gt_depth, gmask = _tracking_setup(device)
+    eng = mk()
+    pose = SO.PoseState(start[:3, :3], start[:3, 3], cam["projmatrix_raw"], device=device)
+    loop = SO.TrackingLoop(eng, pose, gt_color, gt_depth, gmask, alpha=0.9, converged_threshold=0.0)   # never "converged": fixed work
+    eng.calibrate()
+    l0 = L.gsr_kernel_launch_count()
+    loop.capture()
+    launches = int(L.gsr_kernel_launch_count() - l0) // 2
+    flush = l2_flusher(device)
+    stream = torch.cuda.current_stream(device)
+    for _ in range(Wm):
+        flush(); loop.graph.replay()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(torch.cuda.current_device())
+    torch.cuda.synchronize(device)
+    sampler.start()
+    for i in range(K):
+        flush()
+        ev[i][0].record(stream); loop.graph.replay(); ev[i][1].record(stream)
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop()
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    t0 = time.perf_counter()
+    n, first, overflow = loop.run(max_iters=K, check_every=10)
+    e2e_s = time.perf_counter() - t0
+    assert not overflow
+    return {"metric": "tracking iterations/s (render + loss + backward + Adam + pose update)", "value": K / (ms * 1e-3), "unit": "iters/s",
+            "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C1_tracking_loop: C1 scene, RGB-D tracking loss (alpha 0.9), Adam lr 0.003/0.001/0.01, one CUDA graph per iteration",
+                       "l2": "flushed between iterations (device-timed value); e2e runs back to back"},
+            "e2e": {"value": K / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 / 10,
+                    "what": "wall clock of TrackingLoop.run, status D2H + host sync every 10 iterations"},
+            "gpu_launches": launches * K, "clocks": clocks,
+            "check": {"loss": float(loop.ws.sums[0]), "trans_err_m": float(np.linalg.norm(pose.RT.cpu().numpy()[9:] - cam["w2c"][:3, 3]))}}
+
+
+def run_tracking_loop_reference(args, device):
+    """The same loop the way the reference runs it (utils/slam_frontend.py:163-192): its rasterizer kernels, torch autograd
+    for the loss, torch.optim.Adam, update_pose and the camera properties as eager torch ops, `if converged` sync each iteration."""
+    from oracle import slam_ref as SR
+
+    K, Wm = args.steps, args.warmup
+    cfg, sc, t, cam, mk, start, gt_color, gt_depth, gmask = _tracking_setup(device)
+    Lr = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgsref.so"))
+    Lr.gsref_create.restype = C.c_void_p
+    h = C.c_void_p(Lr.gsref_create())
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    f32 = dict(dtype=torch.float32, device=device)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    Rm = torch.tensor(start[:3, :3], **f32); Tm = torch.tensor(start[:3, 3], **f32)
+    proj = torch.from_numpy(cam["projmatrix_raw"]).to(device)
+    rot = torch.zeros(3, requires_grad=True, **f32); trans = torch.zeros(3, requires_grad=True, **f32)
+    ea = torch.zeros(1, requires_grad=True, **f32); eb = torch.zeros(1, requires_grad=True, **f32)
+    opt = torch.optim.Adam([{"params": [rot], "lr": 0.003}, {"params": [trans], "lr": 0.001}, {"params": [ea], "lr": 0.01}, {"params": [eb], "lr": 0.01}])
+    gshape = dict(m2d=(P, 3), conic=(P, 2, 2), opac=(P, 1), col=(P, 3), dep=(P, 1), m3d=(P, 3), cov=(P, 6), sh=(P, 1, 3), sc=(P, 3), rot=(P, 4), tau=(P, 6))
+    gm = gmask.view(1, H, W).bool()
+
+    def iteration():
+        nonlocal Rm, Tm
+        wvt, full, center = SR.camera_tensors(Rm, Tm, proj)                       # camera properties, camera_utils.py:96-109
+        wvt, full, center = wvt.contiguous(), full.contiguous(), center.contiguous()
+        out = dict(color=torch.zeros((3, H, W), **f32), depth=torch.zeros((1, H, W), **f32), opacity=torch.zeros((1, H, W), **f32),
+                   radii=torch.zeros((P,), dtype=torch.int32, device=device), n_touched=torch.zeros((P,), dtype=torch.int32, device=device))
+        Rn = Lr.gsref_forward(h, P, 0, 1, p(t["bg"]), W, H, p(t["means3D"]), p(t["shs"]), None, p(t["opacities"]), p(t["scales"]),
+                              C.c_float(1.0), p(t["rotations"]), None, p(wvt), p(full), p(center), C.c_float(sc["tanfovx"]),
+                              C.c_float(sc["tanfovy"]), 0, p(out["color"]), p(out["depth"]), p(out["opacity"]), p(out["radii"]), p(out["n_touched"]), 0)
+        image = out["color"].requires_grad_(True); depth = out["depth"].requires_grad_(True)
+        opt.zero_grad()
+        loss = SR.loss_tracking(image, depth, out["opacity"], gt_color, gt_depth, gm, ea, eb, 0.01, 0.9, False)
+        loss.backward()
+        g = {k: torch.zeros(s, **f32) for k, s in gshape.items()}
+        Lr.gsref_backward(h, P, 0, 1, Rn, p(t["bg"]), W, H, p(t["means3D"]), p(t["shs"]), None, p(t["scales"]), C.c_float(1.0),
+                          p(t["rotations"]), None, p(wvt), p(full), p(proj), p(center), C.c_float(sc["tanfovx"]), C.c_float(sc["tanfovy"]),
+                          p(out["radii"]), p(image.grad), p(depth.grad), p(g["m2d"]), p(g["conic"]), p(g["opac"]), p(g["col"]), p(g["dep"]),
+                          p(g["m3d"]), p(g["cov"]), p(g["sh"]), p(g["sc"]), p(g["rot"]), p(g["tau"]), 0)
+        tau = torch.sum(g["tau"].view(-1, 6), dim=0)
+        rot.grad, trans.grad = tau[3:].clone(), tau[:3].clone()
+        with torch.no_grad():
+            opt.step()
+            Rm, Tm, conv = SR.update_pose(Rm, Tm, trans.detach(), rot.detach(), converged_threshold=0.0)
+            rot.zero_(); trans.zero_()
+        return loss
+
+    for _ in range(Wm):
+        iteration()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss = iteration()
+    torch.cuda.synchronize(device)
+    el = time.perf_counter() - t0
+    v = K / el
+    return {"metric": "tracking iterations/s (render + loss + backward + Adam + pose update)", "value": v, "unit": "iters/s", "n_gpus": 1,
+            "steps": K, "warmup": Wm, "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "C1_tracking_loop: reference rasterizer kernels + eager torch loss / Adam / update_pose, wall clock"},
+            "cpu_baseline": {"value": v, "unit": "iters/s", "cores": 1, "kind": "reference", "device": "cuda",
+                             "sample": "all %d iterations; reference CUDA kernels + torch eager ops driven by one host thread" % K},
+            "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "check": {"loss": float(loss.detach()), "trans_err_m": float(np.linalg.norm(Tm.cpu().numpy() - cam["w2c"][:3, 3]))}}
+
+
 class _RawView:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
@@ -627,6 +761,9 @@ def main():
         device = "cuda:%d" % local if torch.cuda.is_available() else "cpu"
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
+        if args.workload == "C1_tracking_loop":
+            print(json.dumps(run_tracking_loop_reference(args, device)), flush=True)
+            return 0
         print(json.dumps(run_reference(args, rank, world, device)), flush=True)
         return 0
     if not torch.cuda.is_available():
@@ -636,7 +773,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    line = run_ours(args, rank, world, device) if args.workload.startswith(("C0", "C1")) else run_window(args, rank, world, device)
+    if args.workload == "C1_tracking_loop":
+        line = run_tracking_loop(args, rank, world, device)
+    else:
+        line = run_ours(args, rank, world, device) if args.workload.startswith(("C0", "C1")) else run_window(args, rank, world, device)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

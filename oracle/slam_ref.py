@@ -44,7 +44,7 @@ def loss_mapping(image, depth, gt_image, gt_depth, exposure_a, exposure_b, rgb_b
 # ---- utils/pose_utils.py ---------------------------------------------------------------------------------------------
 def skew_sym_mat(x):
     """utils/pose_utils.py:12-23."""
-    ssm = torch.zeros(3, 3, dtype=x.dtype)
+    ssm = torch.zeros(3, 3, device=x.device, dtype=x.dtype)
     ssm[0, 1] = -x[2]; ssm[0, 2] = x[1]; ssm[1, 0] = x[2]; ssm[1, 2] = -x[0]; ssm[2, 0] = -x[1]; ssm[2, 1] = x[0]
     return ssm
 
@@ -54,7 +54,7 @@ def SO3_exp(theta):
     W = skew_sym_mat(theta)
     W2 = W @ W
     angle = torch.norm(theta)
-    I = torch.eye(3, dtype=theta.dtype)
+    I = torch.eye(3, device=theta.device, dtype=theta.dtype)
     if angle < 1e-5:
         return I + W + 0.5 * W2
     return I + (torch.sin(angle) / angle) * W + ((1 - torch.cos(angle)) / (angle**2)) * W2
@@ -62,7 +62,7 @@ def SO3_exp(theta):
 
 def V(theta):
     """utils/pose_utils.py:44-58."""
-    I = torch.eye(3, dtype=theta.dtype)
+    I = torch.eye(3, device=theta.device, dtype=theta.dtype)
     W = skew_sym_mat(theta)
     W2 = W @ W
     angle = torch.norm(theta)
@@ -73,7 +73,7 @@ def V(theta):
 
 def SE3_exp(tau):
     """utils/pose_utils.py:61-73."""
-    T = torch.eye(4, dtype=tau.dtype)
+    T = torch.eye(4, device=tau.device, dtype=tau.dtype)
     T[:3, :3] = SO3_exp(tau[3:])
     T[:3, 3] = V(tau[3:]) @ tau[:3]
     return T
@@ -82,17 +82,17 @@ def SE3_exp(tau):
 def update_pose(R, T, cam_trans_delta, cam_rot_delta, converged_threshold=1e-4):
     """utils/pose_utils.py:76-93 -> (new_R, new_T, converged)."""
     tau = torch.cat([cam_trans_delta, cam_rot_delta], axis=0)
-    T_w2c = torch.eye(4, dtype=tau.dtype)
+    T_w2c = torch.eye(4, device=tau.device, dtype=tau.dtype)
     T_w2c[0:3, 0:3] = R
     T_w2c[0:3, 3] = T
     new_w2c = SE3_exp(tau) @ T_w2c
-    return new_w2c[0:3, 0:3], new_w2c[0:3, 3], bool(tau.norm() < converged_threshold)
+    return new_w2c[0:3, 0:3], new_w2c[0:3, 3], bool(tau.norm() < converged_threshold)      # bool(): the reference's `if converged` sync
 
 
 def camera_tensors(R, T, projection_matrix):
     """world_view_transform, full_proj_transform, camera_center: utils/camera_utils.py:96-109 with getWorld2View2
     (gaussian_splatting/utils/graphics_utils.py:33-46, translate 0, scale 1)."""
-    Rt = torch.zeros((4, 4), dtype=R.dtype)
+    Rt = torch.zeros((4, 4), device=R.device, dtype=R.dtype)
     Rt[:3, :3] = R
     Rt[:3, 3] = T
     Rt[3, 3] = 1.0
