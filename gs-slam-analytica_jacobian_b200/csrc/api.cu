@@ -86,6 +86,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.grid_y = (a->H + GSR_TILE - 1) / GSR_TILE;
 	s.prefiltered = a->prefiltered;
 	s.accumulate_grads = a->accumulate_grads;
+	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
 	return GSR_OK;
 }
 

@@ -22,6 +22,9 @@ struct Scene {
 	int grid_x, grid_y;
 	int prefiltered;
 	int accumulate_grads;
+	float* densify_grad_accum;    // [P] or null
+	float* densify_denom;         // [P] or null
+	float* max_radii2D;           // [P] or null
 };
 
 // slam_ops.cu -------------------------------------------------------------------------------------------------------

@@ -314,6 +314,11 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 			for (int i = 0; i < s.M * 3; i++) dL_dsh[(size_t)idx * s.M * 3 + i] = 0.f;
 		}
 		dL_dmeans2D[3 * idx] = dm2x; dL_dmeans2D[3 * idx + 1] = dm2y; dL_dmeans2D[3 * idx + 2] = 0.f;
+		if (visible) {      // densification statistics (gaussian_model.py:767-771, slam_backend.py:115-121)
+			if (s.densify_grad_accum) s.densify_grad_accum[idx] += sqrtf(dm2x * dm2x + dm2y * dm2y);
+			if (s.densify_denom) s.densify_denom[idx] += 1.f;
+			if (s.max_radii2D) s.max_radii2D[idx] = fmaxf(s.max_radii2D[idx], (float)radii[idx]);
+		}
 		if (!s.accumulate_grads) {
 			dL_dmeans3D[3 * idx] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
 			dL_dopacity[idx] = dopac;

@@ -31,6 +31,7 @@ class GsrScene(C.Structure):
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("projmatrix_raw", C.c_void_p), ("campos", C.c_void_p),
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
+        ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
     ]
 
 

@@ -97,6 +97,7 @@ class RasterEngine:
         s.viewmatrix, s.projmatrix, s.projmatrix_raw, s.campos = base, base + 64, base + 128, base + 192
         s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
         s.prefiltered, s.debug, s.accumulate_grads = 0, 0, 0
+        s.densify_grad_accum = s.densify_denom = s.max_radii2D = None
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.last_num_rendered = None
@@ -152,6 +153,17 @@ class RasterEngine:
         _cabi.check(_L.gsr_forward_render(C.byref(self.scene), _p(self.geom), _p(self.binning), self.bin_bytes,
                                           self.capacity, -1, self.max_tile_hint, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
                                           _p(self.opacity), _p(self.n_touched), st), "forward_render")
+
+    def attach_densification_stats(self, xyz_gradient_accum=None, denom=None, max_radii2D=None):
+        """fp32 [P] (or [P,1]) device tensors updated in the backward's epilogue for the visible Gaussians of each view:
+        xyz_gradient_accum += ||dL/dmeans2D[:2]||, denom += 1, max_radii2D = max(., radii)
+        (gaussian_model.py:767-771, utils/slam_backend.py:115-121).  None detaches."""
+        for name, t in (("densify_grad_accum", xyz_gradient_accum), ("densify_denom", denom), ("max_radii2D", max_radii2D)):
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.numel() == self.P and t.is_contiguous()
+            setattr(self.scene, name, None if t is None else t.data_ptr())
+        self._densify_refs = (xyz_gradient_accum, denom, max_radii2D)      # keep the tensors alive
+        self.graph_fwd = self.graph_bwd = self.graph_all = None
 
     def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False):
         """dL_dcolor / dL_ddepth default to the engine's own buffers; accumulate=True adds this view's

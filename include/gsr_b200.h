@@ -67,6 +67,12 @@ typedef struct gsr_scene {
 	                                does across the views of a mapping window, utils/slam_backend.py:168-232);
 	                                rows of culled Gaussians are then left untouched.  dL_dmeans2D and dL_dtau are
 	                                per-view quantities and are always overwritten. */
+	/* backward only, optional (null = off): densification statistics of the view, updated for the Gaussians with
+	 * radii > 0 in the backward's per-Gaussian epilogue instead of by masked torch ops afterwards
+	 * (gaussian_splatting/scene/gaussian_model.py:767-771, utils/slam_backend.py:115-121) */
+	float* densify_grad_accum;   /* [P]  += || dL/dmeans2D[:2] ||   (xyz_gradient_accum) */
+	float* densify_denom;        /* [P]  += 1                       (denom) */
+	float* max_radii2D;          /* [P]   = max(., radii)           (max_radii2D) */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */

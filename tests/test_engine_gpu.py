@@ -105,3 +105,43 @@ def test_window_accumulates_views():
     win.iteration((gc, gd))
     expect = sum(r["dL_dmeans3D"].astype(np.float64) for r in refs)
     assert rel_err(eng.g_means3D.cpu().numpy(), expect) <= 1e-5
+
+
+def test_densification_statistics_in_backward_epilogue():
+    """xyz_gradient_accum / denom / max_radii2D updated by the backward kernel == the reference's masked torch ops after
+    each view (gaussian_splatting/scene/gaussian_model.py:767-771, utils/slam_backend.py:115-121)."""
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    V = 3
+    cfg, sc, cams = _scene_and_cams(V=V)
+    eng = _engine(sc, cfg)
+    P = eng.P
+    accum = torch.zeros((P, 1), dtype=torch.float32, device="cuda")
+    denom = torch.zeros((P, 1), dtype=torch.float32, device="cuda")
+    maxr = torch.zeros((P,), dtype=torch.float32, device="cuda")
+    eng.attach_densification_stats(accum, denom, maxr)
+    packed = torch.stack([_pack(c) for c in cams])
+    grads = [S.make_pixel_grads(cfg["W"], cfg["H"], seed=20 + v) for v in range(V)]
+    gc = torch.stack([torch.from_numpy(g[0]) for g in grads]).cuda()
+    gd = torch.stack([torch.from_numpy(g[1]) for g in grads]).cuda()
+    win = KeyframeWindow(eng, packed)
+    win.calibrate()
+    e_acc, e_den, e_max = np.zeros((P, 1)), np.zeros((P, 1)), np.zeros(P)
+
+    def on_view(i, v):      # the reference's per-view statistics, from the per-view outputs
+        nonlocal e_max
+        vis = eng.radii.cpu().numpy() > 0                                         # visibility_filter = radii > 0
+        g2 = eng.g_means2D.cpu().numpy().astype(np.float64)
+        e_acc[vis] += np.linalg.norm(g2[vis, :2], axis=-1, keepdims=True)          # add_densification_stats
+        e_den[vis] += 1
+        e_max[vis] = np.maximum(e_max[vis], eng.radii.cpu().numpy()[vis])
+
+    win.iteration((gc, gd), on_view=on_view)
+    torch.cuda.synchronize()
+    assert rel_err(accum.cpu().numpy(), e_acc) <= 1e-6
+    np.testing.assert_array_equal(denom.cpu().numpy(), e_den)
+    np.testing.assert_array_equal(maxr.cpu().numpy(), e_max)
+    eng.attach_densification_stats()      # detach: a further backward must leave the statistics alone
+    win.iteration((gc, gd))
+    np.testing.assert_array_equal(denom.cpu().numpy(), e_den)
