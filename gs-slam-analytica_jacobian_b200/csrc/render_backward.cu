@@ -47,9 +47,9 @@ struct BwdSmem {
 
 struct PixelState {
 	float pxf, pyf;
-	float dp0, dp1, dp2, dpd, bg_dot, T_final;
+	float dp0, dp1, dp2, dpd, c_bg;
 	int last_contributor;
-	float T, beta, last_alpha, last_s;
+	float T, beta;
 };
 
 // One thread per pixel: entries grp[0 .. cnt) (cnt even, a padding record with opacity 0 at the end if needed)
@@ -74,10 +74,12 @@ __device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int
 				s.T = s.T * rcp;
 				w = alpha * s.T;     // d(channel)/d(colour)
 				const float sdot = w1.z * s.dp0 + w1.w * s.dp1 + w2.x * s.dp2 + w2.y * s.dpd;
-				s.beta = s.last_alpha * s.last_s + (1.f - s.last_alpha) * s.beta;
-				s.last_s = sdot;
-				s.last_alpha = alpha;
-				const float dL_dalpha = (sdot - s.beta) * s.T + (-s.T_final * rcp) * s.bg_dot;
+				// beta = <accum_rec, dL/dpixel> of the entries behind this one.  The reference updates accum_rec when it
+				// reaches the NEXT entry, as last_alpha * last_color + (1 - last_alpha) * accum_rec (backward.cu:799-813);
+				// the same value is beta + alpha * (sdot - beta), and (sdot - beta) is needed for dL/dalpha anyway.
+				const float d = sdot - s.beta;
+				const float dL_dalpha = d * s.T + s.c_bg * rcp;       // c_bg = -T_final * <bg, dL/dcolour>   (:823-828)
+				s.beta = fmaf(alpha, d, s.beta);
 				ga = G * dL_dalpha;
 			}
 			panel[(k + u) * kPanelStride] = make_float2(ga, w);
@@ -164,8 +166,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 
 	PixelState s;
 	s.pxf = (float)px; s.pyf = (float)py;
-	s.T_final = inside ? final_T[pix] : 0.f;
-	s.T = s.T_final;
+	const float T_final = inside ? final_T[pix] : 0.f;
+	s.T = T_final;
 	s.last_contributor = inside ? (int)n_contrib[pix] : 0;
 	s.dp0 = s.dp1 = s.dp2 = s.dpd = 0.f;
 	if (inside) {
@@ -173,8 +175,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		s.dpd = dL_dpix_depth[pix];
 	}
 	sm.dpix[warp][lane] = make_float4(s.dp0, s.dp1, s.dp2, s.dpd);
-	s.bg_dot = bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2;
-	s.beta = 0.f; s.last_alpha = 0.f; s.last_s = 0.f;
+	s.c_bg = -T_final * (bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2);
+	s.beta = 0.f;
 	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 	float2* panel = sm.panel[warp];
 	QueueRec* wq = sm.queue[warp];

@@ -153,6 +153,24 @@ def test_precomputed_cov_and_colors(ref):
     _check_grads(o, rb, keys=("dL_dmeans3D", "dL_dmean2D", "dL_dopacity", "dL_dcolor", "dL_dcov3D", "dL_dtau"))
 
 
+@pytest.mark.parametrize("scale_modifier,active_degree", [(0.7, 1), (1.3, 2)])
+def test_scale_modifier_and_partial_sh_degree(ref, scale_modifier, active_degree):
+    """scale_modifier != 1 (applied in the forward covariance; the reference's dL/dscale ignores it, B-quirk) and an active
+    SH degree below the allocated one (16 coefficients stored, D = 1 or 2: gaussian_renderer/__init__.py:68)."""
+    sc = _scene("sh3", bg=True)
+    sc["scale_modifier"] = scale_modifier
+    sc["sh_degree"] = active_degree
+    dc, dd = _grads(sc)
+    r = ref.forward(sc)
+    rb = ref.backward(sc, dc, dd)
+    o = run_ours(sc, dc, dd)
+    _check_exact_binning(o, r)
+    _check_images(o, r)
+    _check_grads(o, rb)
+    nz = np.abs(np.asarray(rb["dL_dsh"]).reshape(o["dL_dsh"].shape)).reshape(o["dL_dsh"].shape[0], 16, 3)
+    assert np.all(nz[:, (active_degree + 1) ** 2:, :] == 0) and np.all(o["dL_dsh"].reshape(-1, 16, 3)[:, (active_degree + 1) ** 2:, :] == 0)
+
+
 def test_empty_and_all_culled(ref):
     sc = _scene("small")
     sc["means3D"] = sc["means3D"].copy()
