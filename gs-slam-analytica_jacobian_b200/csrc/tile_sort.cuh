@@ -217,17 +217,18 @@ __device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out)
 	return np;
 }
 
-// Sorts the segment of one tile.  smem: keys[2][cap] | vals[2][cap] | cnt[NT/32][512] | base[512] | red[64]
+// Sorts one segment of n >= 2 (depth bits, id) pairs: seg[0..n) (global) -> out[0..n) ids in (depth, id) order; alt is a
+// same-sized global scratch (ping-pong partner), both may be overwritten.  Segments up to cap_smem entries are sorted in
+// shared memory, longer ones by chunked passes through seg / alt.
+// smem: keys[2][cap] | vals[2][cap] | cnt[NT/32][512] | base[512] | red[64]
 template <int NT>
-__device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, uint2* __restrict__ pairs,
-                                          uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list, unsigned capacity,
-                                          int cap_smem, int id_bits, GeomHeader* hdr, uint32_t* sm,
-                                          uint32_t* ids_out = nullptr, int ids_cap = 0)
+__device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __restrict__ alt, uint32_t* __restrict__ out, int n,
+                                             int cap_smem, int id_bits, uint32_t* sm, uint32_t* ids_out, int ids_cap)
 {
-	// sorted ids go to point_list (global) and, when the caller wants to keep consuming them (fused sort + render),
-	// also to ids_out[0 .. ids_cap) in shared memory (a region this function's scratch does not use while emitting)
-	auto emit = [&](int i, unsigned first, uint32_t v) {
-		point_list[first + i] = v;
+	// sorted ids go to `out` (global) and, when the caller wants to keep consuming them (fused sort + render), also to
+	// ids_out[0 .. ids_cap) in shared memory (a region this function's scratch does not use while emitting)
+	auto emit = [&](int i, uint32_t v) {
+		out[i] = v;
 		if (ids_out && i < ids_cap) ids_out[i] = v;
 	};
 	constexpr int NW = NT / 32;
@@ -237,24 +238,6 @@ __device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, 
 	uint32_t* s_base = s_cnt + NW * kMaxBins;
 	uint32_t* s_red = s_base + kMaxBins;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-	const uint2 range = ranges[tile];
-	unsigned start = range.x, end = range.y;
-	if (end > capacity) {      // un-synchronised forward ran out of workspace: stay inside it, flag, caller re-runs
-		end = capacity;
-		if (tid == 0) {
-			hdr->overflow = 1;
-			ranges[tile] = make_uint2(min(start, capacity), capacity);   // the render kernels stay in bounds too
-		}
-		if (start >= end) return;
-	}
-	const int n = (int)(end - start);
-	if (n == 0) return;
-	const uint2* seg = pairs + start;
-	if (n == 1) {
-		if (tid == 0) emit(0, start, seg[0].y);
-		return;
-	}
 	const bool in_smem = n <= cap_smem;
 
 	// min / max depth key of the tile -> the digits that matter
@@ -304,13 +287,13 @@ __device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, 
 		} else {
 			// list beyond the shared-memory capacity: the same passes through the global ping-pong buffers.  The original
 			// order is not needed again: the general sort below starts with the id digits.
-			uint2* A = pairs + start;
-			uint2* B = pairs_alt + start;
+			uint2* A = seg;
+			uint2* B = alt;
 			for (int p = 0; p < np; p++) {
 				radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, fp[p], s_cnt, s_base);
 				uint2* t = A; A = B; B = t;
 			}
-			if (A != pairs + start) {      // keep the data in `pairs` so that the general sort finds it there
+			if (A != seg) {      // keep the data in `seg` so that the general sort finds it there
 				for (int i = tid; i < n; i += NT) B[i] = A[i];
 				__syncthreads();
 				A = B;
@@ -318,7 +301,7 @@ __device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, 
 			K = &A->x; V = &A->y; stride = 2;
 		}
 		if (finish_by_transposition<NT>(K, V, stride, n, in_smem ? 24 : 8)) {
-			for (int i = tid; i < n; i += NT) emit(i, start, V[(size_t)i * stride]);
+			for (int i = tid; i < n; i += NT) emit(i, V[(size_t)i * stride]);
 			return;
 		}
 		__syncthreads();
@@ -335,19 +318,56 @@ __device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, 
 			cur ^= 1;
 		}
 		const uint32_t* V = s_vals + cur * cap_smem;
-		for (int i = tid; i < n; i += NT) emit(i, start, V[i]);
+		for (int i = tid; i < n; i += NT) emit(i, V[i]);
 	} else {
-		uint2* A = pairs + start;
-		uint2* B = pairs_alt + start;
+		uint2* A = seg;
+		uint2* B = alt;
 		for (int p = 0; p < ni + nd; p++) {
 			const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
 			radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, f, s_cnt, s_base);
 			uint2* t = A; A = B; B = t;
 		}
-		for (int i = tid; i < n; i += NT) emit(i, start, A[i].y);
+		for (int i = tid; i < n; i += NT) emit(i, A[i].y);
 	}
 }
 
+
+
+// Sorts the segment of one tile (range handling + sort_segment).
+// (A split of lists beyond the shared-memory capacity into depth sub-ranges sorted one after the other was measured on
+// the 3 M-Gaussian shape, lists of ~12 k entries: no gain -- a sub-sort costs ~15 us of barrier-separated phases whatever
+// its length, so sequential sub-sorts inside one CTA lose what the shared-memory passes win.)
+template <int NT>
+__device__ __forceinline__ void sort_tile(int tile, uint2* __restrict__ ranges, uint2* __restrict__ pairs,
+                                          uint2* __restrict__ pairs_alt, uint32_t* __restrict__ point_list, unsigned capacity,
+                                          int cap_smem, int id_bits, GeomHeader* hdr, uint32_t* sm,
+                                          uint32_t* ids_out = nullptr, int ids_cap = 0)
+{
+	const int tid = threadIdx.x;
+	const uint2 range = ranges[tile];
+	unsigned start = range.x, end = range.y;
+	if (end > capacity) {      // un-synchronised forward ran out of workspace: stay inside it, flag, caller re-runs
+		end = capacity;
+		if (tid == 0) {
+			hdr->overflow = 1;
+			ranges[tile] = make_uint2(min(start, capacity), capacity);   // the render kernels stay in bounds too
+		}
+		if (start >= end) return;
+	}
+	const int n = (int)(end - start);
+	if (n == 0) return;
+	uint2* seg = pairs + start;
+	uint32_t* out = point_list + start;
+	if (n == 1) {
+		if (tid == 0) {
+			const uint32_t v = seg[0].y;
+			out[0] = v;
+			if (ids_out && ids_cap > 0) ids_out[0] = v;
+		}
+		return;
+	}
+	sort_segment<NT>(seg, pairs_alt + start, out, n, cap_smem, id_bits, sm, ids_out, ids_cap);
+}
 
 __host__ inline size_t sort_smem_bytes(int cap_smem, int threads)
 {
