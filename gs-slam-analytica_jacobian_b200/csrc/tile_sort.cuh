@@ -115,20 +115,24 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 	}
 }
 
-// Single-chunk variant for segments of at most NT * ITEMS pairs held in shared memory: the digit histogram falls
-// out of the ranking (per-warp counters), so there is no separate counting sweep and no atomics.
+// Single-chunk variant for segments of at most NT * ITEMS pairs held in shared memory: the digit histogram falls out of
+// the ranking (per-warp counters), so there is no separate counting sweep and no atomics.  Digits are at most
+// kFastDigitBits = 8 bits wide, so that (a) one thread owns one digit in the scan phases (NT >= 256) and (b) two passes
+// use disjoint column halves of the counter rows (half = 0 / 1), which the caller zeroes ONCE before the first pass.
+// Four barrier-separated phases: rank | per-digit totals + warp scan | cross-warp prefix | scatter.
+constexpr int kFastDigitBits = 8;
 template <int NT, int ITEMS>
 __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout, int n,
-                                                 uint32_t kmin, Field f, uint32_t* s_cnt /*[NT/32][kMaxBins]*/,
-                                                 uint32_t* s_base /*[kMaxBins]*/)
+                                                 uint32_t kmin, Field f, int half, uint32_t* s_cnt /*[NT/32][kMaxBins]*/,
+                                                 uint32_t* s_base /*[kMaxBins]*/, uint32_t* s_wsum /*[32]*/)
 {
 	constexpr int NW = NT / 32;
+	static_assert(NT >= (1 << kFastDigitBits), "one thread per digit");
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int nb = 1 << f.bits;
 	const uint32_t mask = (uint32_t)nb - 1;
 	const uint32_t lt = (1u << lane) - 1;
-	for (int i = tid; i < NW * kMaxBins / 4; i += NT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
-	__syncthreads();
+	uint32_t* cnt = s_cnt + half * (kMaxBins / 2);      // this pass's column half of every counter row
 	uint32_t k[ITEMS], v[ITEMS], rank[ITEMS], dg[ITEMS];
 	const int wbase = warp * (32 * ITEMS) + lane;
 #pragma unroll
@@ -143,32 +147,42 @@ __device__ __forceinline__ void radix_pass_small(const uint32_t* kin, const uint
 		const uint32_t d = (pos < n) ? digit_of(k[i], v[i], kmin, f, mask) : mask;   // padding ranks last in its warp
 		dg[i] = d;
 		const unsigned peers = __match_any_sync(0xffffffffu, d);
-		const uint32_t pre = s_cnt[warp * kMaxBins + d];
+		const uint32_t pre = cnt[warp * kMaxBins + d];
 		__syncwarp();
 		rank[i] = pre + __popc(peers & lt);
-		if (lane == 31 - __clz(peers)) s_cnt[warp * kMaxBins + d] = pre + __popc(peers);
+		if (lane == 31 - __clz(peers)) cnt[warp * kMaxBins + d] = pre + __popc(peers);
 		__syncwarp();
 	}
 	__syncthreads();
-	// per digit: exclusive scan over the warps, total -> s_base (the padding only inflates bin `mask` behind the real keys)
-	for (int d = tid; d < nb; d += NT) {
-		uint32_t total = 0;
+	// thread d: exclusive scan of digit d over the warps, then an inclusive warp scan of the digit totals
+	uint32_t total = 0, incl = 0;
+	if (tid < nb) {
 #pragma unroll 8
 		for (int w = 0; w < NW; w++) {
-			const uint32_t c = s_cnt[w * kMaxBins + d];
-			s_cnt[w * kMaxBins + d] = total;
+			const uint32_t c = cnt[w * kMaxBins + tid];
+			cnt[w * kMaxBins + tid] = total;
 			total += c;
 		}
-		s_base[d] = total;
 	}
+	incl = total;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) s_wsum[warp] = incl;      // (the padding only inflates bin `mask`, behind every real key)
 	__syncthreads();
-	if (warp == 0) scan_bins(s_base, nb, lane);
+	if (tid < nb) {
+		uint32_t before = 0;
+		for (int w = 0; w < warp; w++) before += s_wsum[w];
+		s_base[tid] = before + incl - total;
+	}
 	__syncthreads();
 #pragma unroll
 	for (int i = 0; i < ITEMS; i++) {
 		const int pos = wbase + i * 32;
 		if (pos < n) {
-			const uint32_t dst = s_base[dg[i]] + s_cnt[warp * kMaxBins + dg[i]] + rank[i];
+			const uint32_t dst = s_base[dg[i]] + cnt[warp * kMaxBins + dg[i]] + rank[i];
 			kout[dst] = k[i];
 			vout[dst] = v[i];
 		}
@@ -197,17 +211,17 @@ __device__ __forceinline__ bool finish_by_transposition(uint32_t* K, uint32_t* V
 					}
 				}
 			}
-			__syncthreads();
+			if (par == 0) __syncthreads();
 		}
-		if (!__syncthreads_or(swapped)) return true;
+		if (!__syncthreads_or(swapped)) return true;      // also the barrier behind the odd half-round
 	}
 	return false;
 }
 
-__device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out)
+__device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out, int max_bits = kMaxDigitBits)
 {
 	if (sigbits <= 0) return 0;
-	const int np = (sigbits + kMaxDigitBits - 1) / kMaxDigitBits;
+	const int np = (sigbits + max_bits - 1) / max_bits;
 	const int b = (sigbits + np - 1) / np;
 	for (int p = 0; p < np; p++) {
 		out[p].word = word;
@@ -240,6 +254,10 @@ __device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __r
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const bool in_smem = n <= cap_smem;
 
+	const bool one_chunk = in_smem && n <= NT * kSortItems;
+	// the counters of both single-chunk passes (disjoint column halves) are cleared once, here
+	if (one_chunk)
+		for (int i = tid; i < NW * kMaxBins / 4; i += NT) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
 	// min / max depth key of the tile -> the digits that matter
 	uint32_t kmin = 0xffffffffu, kmax = 0;
 	for (int i = tid; i < n; i += NT) {
@@ -262,14 +280,15 @@ __device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __r
 	Field depth_passes[4], id_passes[4];
 	const int nd = plan_passes(sig, 0, depth_passes);
 	const int ni = plan_passes(id_bits, 1, id_passes);
-	const bool one_chunk = in_smem && n <= NT * kSortItems;
 
-	// Fast path: at most two stable passes over the LEADING 18 key bits, then transposition sweeps settle the low bits
-	// and the id order of equal depths (adjacent by then); falls through to the general sort if they do not converge.
+	// Fast path: at most two stable passes over the LEADING key bits (16 in one shared-memory chunk, 18 otherwise), then
+	// transposition sweeps settle the low bits and the id order of equal depths (adjacent by then); falls through to the
+	// general sort if they do not converge.
 	{
-		const int top = min(sig, 2 * kMaxDigitBits);
+		const int digit_bits = one_chunk ? kFastDigitBits : kMaxDigitBits;
+		const int top = min(sig, 2 * digit_bits);
 		Field fp[2];
-		const int np = plan_passes(top, 0, fp);
+		const int np = plan_passes(top, 0, fp, digit_bits);
 		for (int p = 0; p < np; p++) fp[p].shift += sig - top;
 		uint32_t *K, *V;
 		int stride;
@@ -279,8 +298,8 @@ __device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __r
 				uint32_t *ki = s_keys + cur * cap_smem, *vi = s_vals + cur * cap_smem;
 				uint32_t *ko = s_keys + (cur ^ 1) * cap_smem, *vo = s_vals + (cur ^ 1) * cap_smem;
 				if (!one_chunk) radix_pass<NT>(ki, vi, 1, ko, vo, 1, n, kmin, fp[p], s_cnt, s_base);
-				else if (n <= NT * 4) radix_pass_small<NT, 4>(ki, vi, ko, vo, n, kmin, fp[p], s_cnt, s_base);
-				else radix_pass_small<NT, kSortItems>(ki, vi, ko, vo, n, kmin, fp[p], s_cnt, s_base);
+				else if (n <= NT * 4) radix_pass_small<NT, 4>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
+				else radix_pass_small<NT, kSortItems>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
 				cur ^= 1;
 			}
 			K = s_keys + cur * cap_smem; V = s_vals + cur * cap_smem; stride = 1;
