@@ -6,8 +6,8 @@
 //
 //   (preprocess)  every visible Gaussian adds 1 to the counters of the tiles in its rectangle (integer
 //                 REDs); the last preprocess CTA scans the counters into ranges[tile] and scatter cursors.
-//   1. scatter    every lane walks its own Gaussian's rectangle (large rectangles: the whole warp, 32 tiles per
-//                 step), claims a slot in the tile's segment with an integer atomic and stores (depth bits, id).
+//   1. scatter    four lanes walk each Gaussian's rectangle (large rectangles: the whole warp, 32 tiles per
+//                 step), claim a slot in the tile's segment with an integer atomic and stores (depth bits, id).
 //                 Segments come out contiguous per tile but unordered inside.
 //   2. tile sort  one CTA per tile sorts its segment in shared memory.  Fast path (lists that fit one chunk of
 //                 8 keys per thread): two stable single-chunk radix passes over the LEADING 18 of the depth bits
@@ -30,13 +30,39 @@ namespace gsr {
 namespace {
 
 // ---- 1. scatter -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// 256 Gaussians per CTA, FOUR lanes per Gaussian (1024 threads): the walk over a Gaussian's tile rectangle is a chain
+// of dependent shared-memory atomics / stores per step, so its latency, not its instruction count, sets the pace --
+// four lanes cut the chain from ~30 steps per warp (the largest rectangle among 32 Gaussians) to ~8 and quadruple
+// the warps in flight (phase probe: pass 2 took 6.8 of the kernel's 15 us with one lane per Gaussian).
+constexpr int kScatterLanes = 2;
+constexpr int kScatterGauss = 256;                           // Gaussians per CTA
+constexpr int kScatterThreads = kScatterGauss * kScatterLanes;
+
+// visit the tiles of this thread's share of its Gaussian's rectangle: steps sub, sub + 4, ... of a row-major walk
+// (rectangles above kSoloTiles tiles: the whole warp, for the quad leader's Gaussian)
+template <typename F>
+__device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint32_t hi, int grid_x, uint32_t key, uint32_t id,
+                                                   int sub, F&& f)
+{
+	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, w = (hi & 0xffff) - x0;
+	if (n != 0 && n <= kSoloTiles) {
+		const uint32_t magic = rect_magic(w, n);
+		for (uint32_t i = sub; i < n; i += kScatterLanes) {
+			const uint32_t ty = rect_row(i, w, magic), tx = i - ty * w;
+			f((y0 + ty) * grid_x + (x0 + tx), key, id);
+		}
+	}
+	for_each_tile((n > kSoloTiles && sub == 0) ? n : 0u, lo, hi, grid_x, key, id, f);
+}
+
+__global__ void __launch_bounds__(kScatterThreads, 4)
 scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restrict__ tiles_touched, int grid_x,
                uint32_t* __restrict__ cursor, uint2* __restrict__ pairs, unsigned capacity, GeomHeader* hdr,
                int n_tiles, int use_smem)
 {
 	GSR_PROBE(1, 0);
-	const int idx = blockIdx.x * 256 + threadIdx.x;
+	const int sub = threadIdx.x & (kScatterLanes - 1);
+	const int idx = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
 		n = tiles_touched[idx];
@@ -53,32 +79,23 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 	if (use_smem) {
 		// pass 1: CTA-local tile histogram; then ONE global atomic per (CTA, touched tile) claims a contiguous
 		// slice of the tile's segment (coalesced over consecutive tiles) instead of one atomic per instance
-		for (int t = threadIdx.x; t < n_tiles; t += 256) s_cnt[t] = 0;
+		for (int t = threadIdx.x; t < n_tiles; t += kScatterThreads) s_cnt[t] = 0;
 		__syncthreads();
 		GSR_PROBE(1, 1);
-		for_each_tile(n, lo, hi, grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
+		for_each_tile_quad(n, lo, hi, grid_x, 0u, 0u, sub, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
 		__syncthreads();
 		GSR_PROBE(1, 2);
-		// (four claims in flight per thread: the atomics return values and would otherwise serialise on their latency)
-		for (int t0 = threadIdx.x; t0 < n_tiles; t0 += 4 * 256) {
-			uint32_t c[4], base[4];
-#pragma unroll
-			for (int u = 0; u < 4; u++) { const int t = t0 + u * 256; c[u] = t < n_tiles ? s_cnt[t] : 0u; }
-#pragma unroll
-			for (int u = 0; u < 4; u++) base[u] = c[u] ? atomicAdd(&cursor[t0 + u * 256], c[u]) : 0u;
-#pragma unroll
-			for (int u = 0; u < 4; u++) {
-				const int t = t0 + u * 256;
-				if (t < n_tiles) { s_base[t] = base[u]; s_cnt[t] = 0; }
-			}
+		for (int t = threadIdx.x; t < n_tiles; t += kScatterThreads) {
+			const uint32_t c = s_cnt[t];
+			if (c) s_base[t] = atomicAdd(&cursor[t], c);
+			s_cnt[t] = 0;
 		}
 		__syncthreads();
 	}
 	GSR_PROBE(1, 3);
 	bool overflow = false;
-	// pass 2: claim a slot per (Gaussian, tile) inside the CTA's slice and store the pair.  (Bound by the shared-memory
-	// atomic rate, ~2 cycles per lane and SM; batching the atomics of a lane does not help.)
-	for_each_tile(n, lo, hi, grid_x, key, (uint32_t)idx, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
+	// pass 2: claim a slot per (Gaussian, tile) inside the CTA's slice and store the pair
+	for_each_tile_quad(n, lo, hi, grid_x, key, (uint32_t)idx, sub, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
 		const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
 		if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
 		else overflow = true;
@@ -136,7 +153,7 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 		cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
 		scatter_configured = scatter_smem;
 	}
-	scatter_kernel<<<(s.P + 255) / 256, 256, scatter_smem, stream>>>(
+	scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
 		s.P, g.rec, g.tiles_touched, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
 	if (fuse_sort) return 1;      // the forward compositing kernel sorts its own tile
 	int id_bits = 1;
