@@ -769,7 +769,17 @@ def run_reference(args, rank, world, device):
 
 
 # ----------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner there) must not add lines to stdout: the contract is ONE JSON line.
+    File descriptor 1 is pointed at stderr for the whole run; the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -790,9 +800,9 @@ def main():
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
         if args.workload == "C1_tracking_loop":
-            print(json.dumps(run_tracking_loop_reference(args, device)), flush=True)
+            print(json.dumps(run_tracking_loop_reference(args, device)), file=out, flush=True)
             return 0
-        print(json.dumps(run_reference(args, rank, world, device)), flush=True)
+        print(json.dumps(run_reference(args, rank, world, device)), file=out, flush=True)
         return 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
@@ -809,7 +819,7 @@ def main():
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     return 0
 
 
