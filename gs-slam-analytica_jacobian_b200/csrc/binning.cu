@@ -148,11 +148,8 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	const int tiles = s.grid_x * s.grid_y;
 	const int use_smem = tiles <= 16384 ? 1 : 0;     // 2 x tiles x 4 B of shared memory (1920x1080: 64 KB)
 	const size_t scatter_smem = use_smem ? 2 * (size_t)tiles * sizeof(uint32_t) : 0;
-	static size_t scatter_configured = 48 * 1024;
-	if (scatter_smem > scatter_configured) {
-		cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
-		scatter_configured = scatter_smem;
-	}
+	static SmemAttrCache scatter_attr;
+	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel, scatter_smem, scatter_attr);
 	scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
 		s.P, g.rec, g.tiles_touched, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
 	if (fuse_sort) return 1;      // the forward compositing kernel sorts its own tile
@@ -160,20 +157,13 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	while (id_bits < 32 && (1ll << id_bits) < (long long)s.P) id_bits++;
 	const int use_long = (max_tile_hint <= 0 || max_tile_hint > kSmallChunk) ? 1 : 0;
 	const size_t smem = sort_smem_bytes(cap_smem, kSmallThreads);
-	static size_t configured = 0;
-	if (smem > configured) {
-		cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = smem;
-	}
+	static SmemAttrCache sort_attr, long_attr;
+	ensure_dynamic_smem(tile_sort_kernel, smem, sort_attr);
 	tile_sort_kernel<<<tiles, kSmallThreads, smem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list, (unsigned)R_capacity,
 	                                                         cap_smem, id_bits, g.hdr, use_long);
 	if (!use_long) return 2;
 	const size_t lsmem = sort_smem_bytes(kLongChunk, kLongThreads);
-	static bool long_configured = false;
-	if (!long_configured) {
-		cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-		long_configured = true;
-	}
+	ensure_dynamic_smem(tile_sort_long_kernel, lsmem, long_attr);
 	tile_sort_long_kernel<<<min(tiles, 2 * 148), kLongThreads, lsmem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list,
 	                                                                         (unsigned)R_capacity, id_bits, g.hdr, g.long_tiles);
 	return 3;

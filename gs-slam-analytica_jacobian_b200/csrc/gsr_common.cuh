@@ -132,6 +132,23 @@ __host__ __device__ inline BinView bin_view(void* base, size_t R, size_t tiles)
 	return b;
 }
 
+// Opt-in to more than 48 KB of dynamic shared memory: a per-function, per-DEVICE attribute.  The sizes already granted
+// are remembered per device (a process may drive several GPUs), so the driver call happens once per (kernel, device).
+struct SmemAttrCache {
+	size_t granted[64] = {};
+};
+template <typename Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, size_t bytes, SmemAttrCache& cache)
+{
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& g = cache.granted[dev & 63];
+	if (bytes > g) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+		g = bytes;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------

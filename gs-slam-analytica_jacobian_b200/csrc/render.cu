@@ -230,15 +230,12 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr;
 	fs.id_bits = 1;
 	while (fs.id_bits < 32 && (1ll << fs.id_bits) < (long long)s.P) fs.id_bits++;
-	static bool configured = false;
 	const size_t smem_plain = sizeof(FwdSmem);
 	const size_t smem_fused = sort_smem_bytes(kSmallChunk, 256) > (size_t)kFusedIdsOffset + kFusedIdsCap * 4
 	                              ? sort_smem_bytes(kSmallChunk, 256) : (size_t)kFusedIdsOffset + kFusedIdsCap * 4;
-	if (!configured) {
-		cudaFuncSetAttribute(render_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused);
-		cudaFuncSetAttribute(render_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
-		configured = true;
-	}
+	static SmemAttrCache fused_attr, plain_attr;
+	ensure_dynamic_smem(render_forward_kernel<true>, smem_fused, fused_attr);
+	ensure_dynamic_smem(render_forward_kernel<false>, smem_plain, plain_attr);
 	if (fused_sort && s.P > 0 && R_capacity > 0)
 		render_forward_kernel<true><<<tiles, 256, smem_fused, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
 		                                                                im.final_T, im.n_contrib, out_color, out_depth, out_opacity,

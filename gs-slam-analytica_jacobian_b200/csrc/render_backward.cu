@@ -282,11 +282,8 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
 	const size_t smem = sizeof(BwdSmem);
-	static bool configured = false;   // idempotent attribute, set once per process
-	if (!configured) {
-		cudaFuncSetAttribute(render_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = true;
-	}
+	static SmemAttrCache attr;
+	ensure_dynamic_smem(render_backward_kernel, smem, attr);
 	render_backward_kernel<<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
 	                                                     im.final_T, im.n_contrib, dL_dpix, dL_dpix_depth, g.acc, b.cull_masks);
 }
