@@ -260,25 +260,17 @@ def run_ours(args, rank, world, device):
     tau_check = eng.g_tau.cpu().numpy().copy()
 
     # ---------------- e2e: host buffers, copies inside the timed region ----------------
-    copy_stream = torch.cuda.Stream(device)
-    tau_pin = torch.empty(6, dtype=torch.float32).pin_memory()
-    hdr_pin = torch.empty(2, dtype=torch.int32).pin_memory()
-    hdr_dev = torch.as_tensor(_RawView(eng.geom.data_ptr(), 8), device=device).view(torch.int32)
-    up_done = torch.cuda.Event()
+    # The public call for a host-driven step: RasterEngine.capture_host_step / step_host -- ONE graph holding the H2D of the
+    # pinned camera block and upstream gradients (forked branch, overlaps the forward), forward, backward and the D2H of
+    # dL/dtau + header.  Per step the host writes the next pose into the pinned block, replays, and blocks (the next pose
+    # depends on dL/dtau).
+    cam_step = torch.empty(52, dtype=torch.float32).pin_memory()
+    cam_step.copy_(cams_pin[0])
+    eng.capture_host_step(cam_step, dc_pin, dd_pin)
 
     def e2e_step(i):
-        eng.cam.copy_(cams_pin[i], non_blocking=True)                    # H2D pose (208 B)
-        with torch.cuda.stream(copy_stream):                              # H2D dL/dpixel, overlaps the forward
-            eng.dL_dcolor.copy_(dc_pin, non_blocking=True)
-            eng.dL_ddepth.copy_(dd_pin, non_blocking=True)
-            up_done.record(copy_stream)
-        eng.graph_fwd.replay()
-        stream.wait_event(up_done)
-        eng.graph_bwd.replay()
-        tau_pin.copy_(eng.g_tau, non_blocking=True)                      # D2H result
-        hdr_pin.copy_(hdr_dev, non_blocking=True)
-        stream.synchronize()                                              # the next pose depends on dL/dtau
-        copy_stream.wait_stream(stream)
+        cam_step.copy_(cams_pin[i])            # host -> pinned staging (208 B)
+        return eng.step_host()
 
     for i in range(Wm):
         flush()
@@ -290,7 +282,7 @@ def run_ours(args, rank, world, device):
         flush()
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
-        e2e_step(Wm + i)
+        tau_pin, hdr_pin = e2e_step(Wm + i)
         e2e_s += time.perf_counter() - t0
         assert hdr_pin[1].item() == 0
     barrier()
@@ -346,7 +338,7 @@ def run_ours(args, rank, world, device):
                            % (eng.capacity, "fused into the forward compositing kernel" if fused_sort_active(eng) else "in its own kernels")},
         "e2e": {"value": world * K / emax, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3,
-                "what": "pinned pose block + pinned dL/dcolor,dL/ddepth H2D, dL/dtau + header D2H, host sync every step"},
+                "what": "RasterEngine.step_host: one graph with pinned pose block + pinned dL/dcolor,dL/ddepth H2D, forward, backward, dL/dtau + header D2H; host sync every step"},
         "gpu_launches": launches_per_step * K,
         "launches_per_step": {"kernels": launches_per_step, "graph_launches": 1},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

@@ -28,6 +28,11 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _RawDeviceBytes:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class RasterEngine:
     def __init__(self, gaussians, image_width, image_height, tanfovx, tanfovy, bg, sh_degree=0, scale_modifier=1.0,
                  device="cuda", headroom=1.25):
@@ -201,6 +206,52 @@ class RasterEngine:
             with torch.cuda.graph(self.graph_all):
                 self.launch_forward()
                 self.launch_backward()
+
+    def capture_host_step(self, cam_host, dL_dcolor_host=None, dL_ddepth_host=None):
+        """One CUDA graph for a step driven from HOST buffers: H2D of the pinned 52-float camera block (and, when given,
+        of the pinned upstream gradients, on a forked branch that overlaps the forward), forward, backward, D2H of
+        dL/dtau and the (num_rendered, overflow) header into pinned tensors.  The caller rewrites the pinned inputs in
+        place and calls step_host(): two Python calls per step instead of ten."""
+        for t in (cam_host, dL_dcolor_host, dL_ddepth_host):
+            assert t is None or (t.is_pinned() and t.is_contiguous())
+        if self.binning is None:
+            self.calibrate()
+        self.h_tau = torch.empty(6, dtype=torch.float32).pin_memory()
+        self.h_hdr = torch.empty(2, dtype=torch.int32).pin_memory()
+        hdr_dev = torch.as_tensor(_RawDeviceBytes(self.geom.data_ptr(), 8), device=self.dev).view(torch.int32)
+        self._host_refs = (cam_host, dL_dcolor_host, dL_ddepth_host, hdr_dev)
+        with torch.cuda.device(self.dev):
+            warm = torch.cuda.Stream(self.dev)
+            warm.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(warm):
+                self.launch_forward()
+                self.launch_backward()
+            torch.cuda.current_stream(self.dev).wait_stream(warm)
+            torch.cuda.synchronize(self.dev)
+            side = torch.cuda.Stream(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream(self.dev)
+                self.cam.copy_(cam_host, non_blocking=True)
+                if dL_dcolor_host is not None:
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        self.dL_dcolor.copy_(dL_dcolor_host, non_blocking=True)
+                        if dL_ddepth_host is not None:
+                            self.dL_ddepth.copy_(dL_ddepth_host, non_blocking=True)
+                self.launch_forward()
+                if dL_dcolor_host is not None:
+                    cur.wait_stream(side)
+                self.launch_backward()
+                self.h_tau.copy_(self.g_tau, non_blocking=True)
+                self.h_hdr.copy_(hdr_dev, non_blocking=True)
+            self.graph_host = g
+
+    def step_host(self):
+        """Replay the host-driven step and wait for it; returns (dL_dtau[6] pinned, (num_rendered, overflow) pinned)."""
+        self.graph_host.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.h_tau, self.h_hdr
 
     def step(self, use_graph=True):
         """forward + backward at the current camera / upstream gradients; no host synchronisation."""

@@ -145,3 +145,27 @@ def test_densification_statistics_in_backward_epilogue():
     eng.attach_densification_stats()      # detach: a further backward must leave the statistics alone
     win.iteration((gc, gd))
     np.testing.assert_array_equal(denom.cpu().numpy(), e_den)
+
+
+def test_host_driven_step_graph_matches_resident_step():
+    """RasterEngine.capture_host_step / step_host (pinned camera block + upstream gradients copied inside the graph,
+    results copied back) == the device-resident step at the same pose."""
+    from diff_gaussian_rasterization import scenes as S
+
+    cfg, sc, cams = _scene_and_cams(V=3)
+    dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=4)
+    eng = _engine(sc, cfg)
+    for cam in cams:
+        eng.set_camera(_pack(cam))
+        eng.calibrate()
+    cam_pin = torch.empty(52, dtype=torch.float32).pin_memory()
+    dc_pin, dd_pin = torch.from_numpy(dc).pin_memory(), torch.from_numpy(dd).pin_memory()
+    cam_pin.copy_(_pack(cams[0]).cpu())
+    eng.capture_host_step(cam_pin, dc_pin, dd_pin)
+    for cam in cams:
+        cam_pin.copy_(_pack(cam).cpu())
+        tau, hdr = eng.step_host()
+        ref = run_ours(S.with_camera(sc, cam), dc, dd)
+        assert int(hdr[0]) == ref["num_rendered"] and int(hdr[1]) == 0
+        assert rel_err(tau.numpy(), ref["dL_dtau"]) <= 1e-5
+        assert np.array_equal(eng.color.cpu().numpy(), ref["color"])
