@@ -196,3 +196,31 @@ def test_nosync_capacity_and_overflow():
     np.testing.assert_array_equal(o["color"], base["color"])
     o2 = run_ours(sc, capacity=max(R // 2, 1))          # too small: flagged, not corrupted memory
     assert o2["overflow"] == 1 and o2["num_rendered"] == R
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomised_shapes_vs_reference_kernels(ref, seed):
+    """Seeded sweep over image sizes (ragged and tile-aligned), Gaussian counts, footprint scales, backgrounds and SH
+    degrees: list lengths around every internal boundary (32-entry cull groups, 128/256-entry batches, 16-entry role
+    switches, 2048-entry sort chunks) occur somewhere in the sweep.  Same bars as the fixed cases."""
+    from diff_gaussian_rasterization import scenes as S
+
+    rng = np.random.default_rng(1000 + seed)
+    W, H = int(rng.integers(17, 260)), int(rng.integers(17, 200))
+    if seed % 3 == 0:
+        W, H = (W + 15) // 16 * 16, (H + 15) // 16 * 16
+    deg = int(rng.integers(0, 4))
+    cfg = dict(W=W, H=H, fx=float(rng.uniform(0.6, 1.4) * W), fy=float(rng.uniform(0.6, 1.4) * W), cx=W / 2 + float(rng.uniform(-5, 5)),
+               cy=H / 2 + float(rng.uniform(-5, 5)), P=int(rng.integers(1, 9000)), sh_degree=deg)
+    sc = S.make_scene(cfg, seed=seed)
+    sc["scales"] = (sc["scales"] * float(rng.choice([0.3, 1.0, 3.0, 8.0]))).astype(np.float32)
+    if seed % 2:
+        sc["bg"] = rng.uniform(0, 1, 3).astype(np.float32)
+    dc, dd = S.make_pixel_grads(W, H, seed=seed)
+    r = ref.forward(sc)
+    rb = ref.backward(sc, dc, dd)
+    o = run_ours(sc, dc, dd)
+    assert o["overflow"] == 0
+    _check_exact_binning(o, r)
+    _check_images(o, r)
+    _check_grads(o, rb)
