@@ -149,3 +149,37 @@ class TrackingLoop:
         _, overflow = self.eng.header()
         st = self.pose.status.cpu()
         return int(st[1]), int(st[2]), overflow
+
+
+class MappingWindow:
+    """One mapping iteration over a keyframe window (utils/slam_backend.py:156-232) with the loss of every view computed by
+    the fused kernel right behind its forward: render -> get_loss_mapping + gradients -> backward, views sharded over the
+    ranks by a KeyframeWindow, per-Gaussian gradients accumulated in the backward kernel and summed by one all-reduce.
+    Per view (kept on the owning rank, like the reference keeps them per viewpoint): loss, dL/dexposure (a, b), dL/dtau,
+    and -- through on_view -- radii / n_touched / dL/dmeans2D of the engine.
+    The isotropic scale regulariser (10 * |s - mean(s)|.mean(), :228-230) is a per-Gaussian torch expression outside the
+    rasterizer path; callers add its gradient to the scale part of the flat buffer."""
+
+    def __init__(self, window, gt_colors, gt_depths=None, exposures=None, rgb_boundary_threshold=0.01, alpha=0.95, initialization=False):
+        """gt_colors [V,3,H,W], gt_depths [V,1,H,W] or None (monocular), exposures [V,2] device tensor or None."""
+        self.win, self.eng = window, window.engine
+        self.gt_colors, self.gt_depths, self.exposures = gt_colors, gt_depths, exposures
+        self.kw = dict(rgb_boundary_threshold=rgb_boundary_threshold, alpha=alpha)
+        self.initialization = initialization
+        self.ws = LossWorkspace(self.eng.W, self.eng.H, self.eng.dev)
+        n = max(len(window.views), 1)
+        self.view_sums = torch.zeros((n, 4), dtype=torch.float32, device=self.eng.dev)    # per local view: loss, dL/da, dL/db, 0
+
+    def iteration(self, reduce=True, on_view=None):
+        """Returns (grad_flat summed over all views of all ranks, per-local-view sums [n,4], per-local-view dL/dtau [n,6])."""
+        eng, local = self.eng, {v: i for i, v in enumerate(self.win.views)}
+
+        def upstream(v):
+            expo = None if (self.initialization or self.exposures is None) else self.exposures[v]
+            slam_loss(self.ws, eng.color, eng.depth, eng.opacity, self.gt_colors[v], None if self.gt_depths is None else self.gt_depths[v],
+                      None, expo, tracking=False, dL_dcolor=eng.dL_dcolor, dL_ddepth=eng.dL_ddepth, **self.kw)
+            self.view_sums[local[v]].copy_(self.ws.sums, non_blocking=True)
+            return eng.dL_dcolor, eng.dL_ddepth
+
+        flat = self.win.iteration(upstream, reduce=reduce, on_view=on_view)
+        return flat, self.view_sums, self.win.tau

@@ -146,3 +146,49 @@ def test_tracking_loop_graph_converges_towards_the_target_pose():
     err1 = np.linalg.norm(rt_g[9:] - base[:3, 3])
     assert err1 < 0.35 * err0, (err0, err1)                                 # the pose moved most of the way to the target
     assert rel_err(rt_g, rt_e) <= 1e-3                                       # graph replay == eager launches (fp32 atomics aside)
+
+
+def test_mapping_window_with_fused_loss_matches_per_view_autograd():
+    """MappingWindow (render -> fused mapping loss -> backward, accumulated over the window) == per-view rasterizer calls fed
+    with the autograd gradients of the restated get_loss_mapping (utils/slam_utils.py:92-128), summed like autograd does."""
+    from common import run_ours
+    from diff_gaussian_rasterization import scenes as SC
+    from diff_gaussian_rasterization import slam_ops as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    V = 3
+    cfg = dict(W=208, H=160, fx=190.0, fy=188.0, cx=104.0, cy=80.0, P=6000, sh_degree=0)
+    sc = SC.make_scene(cfg, seed=8)
+    sc["scales"] = sc["scales"] * 2.0
+    cams = [SC.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c) for w2c in SC.arc_poses(V, radius=0.3)]
+    t = SC.to_torch(sc, "cuda")
+    eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                       cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=0)
+    pack = lambda c: RasterEngine.pack_camera(*(torch.from_numpy(c[k]) for k in ("viewmatrix", "projmatrix", "projmatrix_raw", "campos"))).cuda()
+    g = torch.Generator().manual_seed(21)
+    gt_c = torch.rand((V, 3, cfg["H"], cfg["W"]), generator=g).cuda()
+    gt_d = (torch.rand((V, 1, cfg["H"], cfg["W"]), generator=g) * 3).cuda()
+    expo = (torch.randn((V, 2), generator=g) * 0.05).cuda()
+    win = KeyframeWindow(eng, torch.stack([pack(c) for c in cams]))
+    win.calibrate()
+    mw = S.MappingWindow(win, gt_c, gt_d, expo, alpha=0.9)
+    flat, sums, tau = mw.iteration()
+    torch.cuda.synchronize()
+    expect = {k: 0.0 for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations")}
+    for v in range(V):
+        fwd = run_ours(SC.with_camera(sc, cams[v]))
+        img = torch.from_numpy(fwd["color"]).double().requires_grad_(True)
+        dep = torch.from_numpy(fwd["depth"]).double().requires_grad_(True)
+        a, b = expo[v, 0].cpu().double().requires_grad_(True), expo[v, 1].cpu().double().requires_grad_(True)
+        loss = R.loss_mapping(img, dep, gt_c[v].cpu().double(), gt_d[v].cpu().double(), a, b, 0.01, 0.9, False)
+        loss.backward()
+        assert abs(sums[v, 0].item() - loss.item()) <= 1e-5 * abs(loss.item())
+        assert abs(sums[v, 1].item() - a.grad.item()) <= 1e-4 * abs(a.grad.item()) + 1e-9
+        o = run_ours(SC.with_camera(sc, cams[v]), img.grad.float().numpy(), dep.grad.float().numpy())
+        for k in expect:
+            expect[k] = expect[k] + o[k].astype(np.float64)
+        assert rel_err(tau[v].cpu().numpy(), o["dL_dtau"]) <= 1e-4
+    for k, mine in (("dL_dmeans3D", eng.g_means3D), ("dL_dsh", eng.g_sh), ("dL_dopacity", eng.g_opacity), ("dL_dscales", eng.g_scales),
+                    ("dL_drotations", eng.g_rot)):
+        assert rel_err(mine.cpu().numpy(), expect[k]) <= 1e-4, k
