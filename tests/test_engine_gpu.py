@@ -169,3 +169,30 @@ def test_host_driven_step_graph_matches_resident_step():
         assert int(hdr[0]) == ref["num_rendered"] and int(hdr[1]) == 0
         assert rel_err(tau.numpy(), ref["dL_dtau"]) <= 1e-5
         assert np.array_equal(eng.color.cpu().numpy(), ref["color"])
+
+
+def test_fused_sort_survives_lists_longer_than_the_hint():
+    """The engine decides from its calibrated longest-list hint whether the forward kernel sorts its own tiles (lists up to one
+    shared-memory chunk).  If a later pose produces longer lists than the hint promised, the fused kernel must still sort them
+    (general path) -- slower, never wrong."""
+    from diff_gaussian_rasterization import scenes as S
+
+    cfg = dict(W=160, H=128, fx=120.0, fy=120.0, cx=79.5, cy=63.5, P=15000, sh_degree=0)
+    sc = S.make_scene(cfg, seed=6)
+    sc["scales"] = sc["scales"] * 6.0                       # lists of 2-4 k entries
+    cam = S.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], S.base_pose())
+    dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=3)
+    eng = _engine(sc, cfg)
+    eng.set_camera(_pack(cam))
+    eng.dL_dcolor.copy_(torch.from_numpy(dc)); eng.dL_ddepth.copy_(torch.from_numpy(dd))
+    eng.calibrate()
+    assert eng.max_tile_hint > 2048
+    eng.max_tile_hint = 512                                  # a stale, far too small hint -> fused path
+    eng.graph_fwd = eng.graph_bwd = eng.graph_all = None
+    eng.step(use_graph=False)
+    R, ov = eng.header()
+    ref = run_ours(S.with_camera(sc, cam), dc, dd)
+    assert R == ref["num_rendered"] and not ov
+    assert np.array_equal(eng.color.cpu().numpy(), ref["color"])
+    assert rel_err(eng.g_tau.cpu().numpy(), ref["dL_dtau"]) <= 1e-5
+    assert rel_err(eng.g_means3D.cpu().numpy(), ref["dL_dmeans3D"]) <= 1e-5
