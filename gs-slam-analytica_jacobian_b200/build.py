@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    extra += os.environ.get("GSR_EXTRA_NVCC_FLAGS", "").split()      # experiments, e.g. -DGSR_BWD_SLOTS=8
     if os.environ.get("GSR_PHASE_PROBE"):      # diagnostic build (tools/phase_probe.py), never the product
         extra += ["-DGSR_PHASE_PROBE"]
 
