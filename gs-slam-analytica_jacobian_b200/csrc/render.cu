@@ -34,6 +34,7 @@ struct FwdSmem {
 	uint32_t id[2][256];
 	QueueRec queue[8][34];      // per warp: <= 32 survivors of a chunk + one padding record for the 2-way unroll
 	uint32_t tmask[8][32];      // per warp and queue slot: ballot of "still above 0.5 after this blend"
+	uint64_t bar[2];            // GSR_TMA_STAGE: one mbarrier per staging buffer
 };
 
 template <bool COUNT_TOUCHED>
@@ -134,6 +135,33 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	// T only decreases, so once no live pixel of the warp is above 0.5 the n_touched bookkeeping is skipped for good.
 	bool warp_hi_T = __any_sync(kFull, inside);
 
+#ifdef GSR_TMA_STAGE
+	// Staging through the TMA unit: every thread issues ONE 48-byte bulk copy (UBLKCP) for its record and arrives on the
+	// buffer's mbarrier (thread 0 also registers the expected byte count); consumers wait on the barrier's phase, which
+	// also publishes the ids written with ordinary stores -- no cp.async groups, one CTA barrier less per batch.
+	if (threadIdx.x == 0) { mbar_init(&sm.bar[0], 256); mbar_init(&sm.bar[1], 256); mbar_fence_init(); }
+	__syncthreads();
+	auto stage = [&](int b, int buf) {
+		const int i = b * 256 + threadIdx.x;
+		const int cnt_b = min(256, n - b * 256);
+		fence_proxy_async();      // earlier generic-proxy reads of this buffer are ordered before the async writes
+		if (i < n) {
+			const uint32_t id = ids_in_smem ? s_ids[i] : (FUSED_SORT ? __ldcg(point_list + range.x + i) : __ldg(point_list + range.x + i));
+			sm.id[buf][threadIdx.x] = id;
+			tma_bulk_g2s(&sm.rec[buf][threadIdx.x], rec + id, (unsigned)sizeof(GaussRec), &sm.bar[buf]);
+		}
+		if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.bar[buf], (unsigned)cnt_b * (unsigned)sizeof(GaussRec));
+		else mbar_arrive(&sm.bar[buf]);
+	};
+	if (rounds > 0) stage(0, 0);
+
+	int b = 0;
+	for (; b < rounds; b++) {
+		const int buf = b & 1;
+		if (__syncthreads_and(T < 0.f)) break;   // also: everyone is past batch b-1, buffer buf^1 is free
+		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
+		mbar_wait(&sm.bar[buf], (unsigned)((b >> 1) & 1));
+#else
 	auto stage = [&](int b, int buf) {
 		const int i = b * 256 + threadIdx.x;
 		if (i < n) {
@@ -156,6 +184,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		else cp_async_commit();
 		cp_async_wait<1>();
 		__syncthreads();
+#endif
 		const int cnt = min(256, n - b * 256);
 		uint32_t held_mask = 0;
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -203,7 +232,11 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		// behind its last contributor and are never read)
 		if (lane < 8 && (b * 8 + lane) * 32 < n) my_masks[(b * 8 + lane) * 8] = held_mask;   // only this tile's own groups
 	}
+#ifdef GSR_TMA_STAGE
+	if (b < rounds) mbar_wait(&sm.bar[b & 1], (unsigned)((b >> 1) & 1));   // a staged batch nobody consumed: let it land before exit
+#else
 	cp_async_wait<0>();
+#endif
 	if (inside) {
 		const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
 		T = fabsf(T);
