@@ -142,6 +142,33 @@ int gsr_forward_num_rendered(void* geom, void* stream, long long* out, long long
 	return GSR_OK;
 }
 
+static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* geom, void* binning, size_t binning_bytes,
+                               long long capacity, long long R_host, long long max_tile_hint, void* image, size_t image_bytes,
+                               float* out_color, float* out_depth, float* out_opacity, int* n_touched, cudaStream_t st,
+                               bool scatter_done)
+{
+	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
+	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
+	if (capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "more than 2^31 tile instances are not supported");
+	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
+	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles_of(s.W, s.H))) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	if (!out_color || !out_depth || !out_opacity || (s.P > 0 && !n_touched)) return fail(GSR_ERR_ARG, "null output");
+	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
+	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
+	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
+	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
+	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= 2048 && !g_no_fused_sort;
+	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done);
+	stage_mark(2, st);
+	int rc = debug_sync(a, st, "binning");
+	if (rc) return rc;
+	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, (size_t)capacity, st);
+	stage_mark(3, st);
+	g_launches += 1;
+	return debug_sync(a, st, "render");
+}
+
 int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t binning_bytes, long long capacity,
                        long long R_host, long long max_tile_hint, void* image, size_t image_bytes, float* out_color,
                        float* out_depth, float* out_opacity, int* n_touched, void* stream)
@@ -149,27 +176,32 @@ int gsr_forward_render(const gsr_scene* a, void* geom, void* binning, size_t bin
 	gsr::Scene s;
 	int rc = make_scene(a, s);
 	if (rc) return rc;
-	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
-	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
-	if (capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "more than 2^31 tile instances are not supported");
-	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
-	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles_of(s.W, s.H))) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
-	if (!out_color || !out_depth || !out_opacity || (s.P > 0 && !n_touched)) return fail(GSR_ERR_ARG, "null output");
-	cudaStream_t st = (cudaStream_t)stream;
+	return forward_render_impl(a, s, geom, binning, binning_bytes, capacity, R_host, max_tile_hint, image, image_bytes, out_color,
+	                           out_depth, out_opacity, n_touched, (cudaStream_t)stream, false);
+}
+
+int gsr_forward_nosync(const gsr_scene* a, void* geom, size_t geom_bytes, void* binning, size_t binning_bytes, long long capacity,
+                       long long max_tile_hint, void* image, size_t image_bytes, float* out_color, float* out_depth,
+                       float* out_opacity, int* radii, int* n_touched, void* stream)
+{
+	gsr::Scene s;
+	int rc = make_scene(a, s);
+	if (rc) return rc;
 	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	if (!geom || geom_bytes < gsr::geom_bytes(s.P, tiles)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
+	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
+	if (capacity < 0 || !binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	cudaStream_t st = (cudaStream_t)stream;
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
-	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
-	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
-	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= 2048 && !g_no_fused_sort;
-	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st);
-	stage_mark(2, st);
-	rc = debug_sync(a, st, "binning");
+	stage_mark(0, st);
+	const bool scatter_done = gsr::launch_preprocess_forward(s, g, radii, n_touched, st, &b, (size_t)capacity);
+	stage_mark(1, st);
+	if (s.P > 0) g_launches += 1;
+	rc = debug_sync(a, st, "preprocess");
 	if (rc) return rc;
-	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, (size_t)capacity, st);
-	stage_mark(3, st);
-	g_launches += 1;
-	return debug_sync(a, st, "render");
+	return forward_render_impl(a, s, geom, binning, binning_bytes, capacity, -1, max_tile_hint, image, image_bytes, out_color,
+	                           out_depth, out_opacity, n_touched, st, scatter_done);
 }
 
 int gsr_forward_overflowed(void* geom, void* stream, int* overflowed, long long* needed)

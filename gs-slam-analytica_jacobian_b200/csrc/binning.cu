@@ -142,7 +142,7 @@ size_t tile_sort_smem_bytes(int cap_smem) { return sort_smem_bytes(cap_smem, kSm
 // R_capacity: instance capacity of the binning workspace.  cap_smem: longest tile list sorted in shared memory by the
 // 256-thread kernel; max_tile_hint: longest list expected (<= 0: unknown).
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
-                   bool fuse_sort, cudaStream_t stream)
+                   bool fuse_sort, cudaStream_t stream, bool scatter_done)
 {
 	if (s.P == 0 || R_capacity == 0) return 0;
 	const int tiles = s.grid_x * s.grid_y;
@@ -150,9 +150,10 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	const size_t scatter_smem = use_smem ? 2 * (size_t)tiles * sizeof(uint32_t) : 0;
 	static SmemAttrCache scatter_attr;
 	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel, scatter_smem, scatter_attr);
-	scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
+	if (!scatter_done)
+		scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
 		s.P, g.rec, g.tiles_touched, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
-	if (fuse_sort) return 1;      // the forward compositing kernel sorts its own tile
+	if (fuse_sort) return scatter_done ? 0 : 1;      // the forward compositing kernel sorts its own tile
 	int id_bits = 1;
 	while (id_bits < 32 && (1ll << id_bits) < (long long)s.P) id_bits++;
 	const int use_long = (max_tile_hint <= 0 || max_tile_hint > kSmallChunk) ? 1 : 0;

@@ -60,12 +60,14 @@ void launch_slam_loss(const SlamLossArgs& a, void* scratch, cudaStream_t stream)
 void launch_tracking_step(const TrackingStepArgs& a, cudaStream_t stream);
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
-void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream);
+// returns true when it also built the per-tile segments (cooperative fused scatter; needs the binning workspace)
+bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream,
+                               const BinView* bin = nullptr, size_t R_capacity = 0);
 // returns the number of kernels launched; cap_smem = longest tile list the 256-thread sort holds in shared memory,
 // max_tile_hint = longest list expected (<= 0: unknown)
 // fuse_sort: launch only the scatter; the per-tile sort then runs inside the forward compositing kernel
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
-                   bool fuse_sort, cudaStream_t stream);
+                   bool fuse_sort, cudaStream_t stream, bool scatter_done = false);
 size_t tile_sort_smem_bytes(int cap_smem);
 // fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,

@@ -7,6 +7,7 @@
 // cov2D = (W J)^T Vrk^T (W J), eigenvalue radius, double-precision ndc2Pix, getRect) are written
 // with the same association order as the reference + glm 0.9.9 (type_mat3x3.inl:486-518), and are
 // compiled with the same default -fmad contraction.
+#include <cstdlib>
 #include "gsr_params.h"
 
 namespace gsr {
@@ -99,8 +100,20 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 	return make_float3(res[0], res[1], res[2]);
 }
 
+// FUSED_SCATTER (cooperative launch, every CTA resident): the kernel goes on, behind ONE grid-wide barrier, to build the
+// per-tile segments itself -- the Gaussian's rectangle / depth / id are still in registers and the CTA's tile histogram
+// is still in shared memory, so the separate scatter kernel's reload, its recount and the serial last-CTA scan fall away:
+// every CTA scans the (complete) tile counters redundantly, claims its slice of every touched tile with one global
+// atomic, and stores its (depth bits, id) pairs.
+struct FusedScatterArgs {
+	uint2* pairs;          // binning workspace: [capacity] (depth bits, id)
+	unsigned capacity;
+};
+
+template <bool FUSED_SCATTER>
 __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomView g, int* __restrict__ radii,
-                                                                 int* __restrict__ n_touched, int vec_mask, int hist_smem)
+                                                                 int* __restrict__ n_touched, int vec_mask, int hist_smem,
+                                                                 FusedScatterArgs fa)
 {
 	__shared__ __align__(16) float s_mean[768];
 	__shared__ __align__(16) float s_scale[768];
@@ -127,7 +140,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	__syncthreads();
 	GSR_PROBE(0, 1);
 
-	unsigned my_tiles = 0, my_vis = 0, rect_lo = 0, rect_hi = 0;
+	unsigned my_tiles = 0, my_vis = 0, rect_lo = 0, rect_hi = 0, depth_bits = 0;
 	if (idx < s.P) {
 		int out_radius = 0;
 		GaussRec rec;
@@ -233,6 +246,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 					my_vis = 1;
 					rect_lo = rminx | (rminy << 16);
 					rect_hi = rmaxx | (rmaxy << 16);
+					depth_bits = __float_as_uint(depth);
 					rec.q0 = make_float4(pix_x, pix_y, conic.x, conic.y);
 					rec.q1 = make_float4(conic.z, __ldg(s.opacities + idx), depth, rgb.x);
 					rec.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(rect_lo), __uint_as_float(rect_hi));
@@ -282,6 +296,64 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		}
 	}
 	GSR_PROBE(0, 4);
+	if (FUSED_SCATTER) {
+		// ---- grid-wide barrier (single use per launch: the counter is cleared by the memset in front of the kernel) ----
+		__threadfence();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			atomicAdd(&g.hdr->fwd_blocks_done, 1u);
+			while (*reinterpret_cast<volatile unsigned*>(&g.hdr->fwd_blocks_done) < gridDim.x) { }
+			__threadfence();
+		}
+		__syncthreads();
+		// ---- every CTA: exclusive scan of the tile counters -> s_start[tile]; CTA 0 also publishes ranges etc. ----
+		uint32_t* s_start = s_hist + n_tiles;
+		{
+			const int per = (n_tiles + 255) / 256;
+			const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
+			unsigned sum = 0;
+			for (int t = t0; t < t1; t++) sum += __ldcg(&g.tile_count[t]);
+			unsigned inc = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+				if (lane_id() >= o) inc += v;
+			}
+			if (lane_id() == 31) s_red[threadIdx.x >> 5] = inc;
+			__syncthreads();
+			unsigned run = inc - sum;
+			for (int w = 0; w < (int)(threadIdx.x >> 5); w++) run += s_red[w];
+			unsigned mx = 0;
+			for (int t = t0; t < t1; t++) {
+				const unsigned c = __ldcg(&g.tile_count[t]);
+				s_start[t] = run;
+				if (blockIdx.x == 0) {
+					g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+					if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;
+					mx = max(mx, c);
+				}
+				run += c;
+			}
+			if (blockIdx.x == 0 && mx) atomicMax(&g.hdr->max_tile_count, mx);
+		}
+		__syncthreads();
+		// ---- claim this CTA's slice of every tile it touches (tile_cursor counts from 0: cleared by the memset) ----
+		for (int t = threadIdx.x; t < n_tiles; t += 256) {
+			const unsigned c = s_hist[t];
+			if (c) s_start[t] += atomicAdd(&g.tile_cursor[t], c);
+			s_hist[t] = 0;
+		}
+		__syncthreads();
+		// ---- store the pairs ----
+		bool overflow = false;
+		for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, depth_bits, (uint32_t)idx, [&](uint32_t tile, uint32_t key, uint32_t id) {
+			const uint32_t pos = s_start[tile] + atomicAdd(&s_hist[tile], 1u);
+			if (pos < fa.capacity) fa.pairs[pos] = make_uint2(key, id);
+			else overflow = true;
+		});
+		if (overflow) g.hdr->overflow = 1;
+		return;
+	}
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
@@ -343,21 +415,47 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
 
 static inline bool aligned16(const void* p) { return ((size_t)p & 15) == 0; }
 
-void launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream)
+// Returns true when the kernel also built the per-tile segments (fused scatter): only attempted when the caller hands in
+// the binning workspace (no-sync path), the CTA-private histogram fits and every CTA of the grid can be resident at once.
+bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream,
+                               const BinView* bin, size_t R_capacity)
 {
-	// header and the per-tile counters behind it are cleared together
-	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader) + (size_t)s.grid_x * s.grid_y * sizeof(uint32_t), stream);
+	const int tiles = s.grid_x * s.grid_y;
+	// header, the per-tile counters and the claim cursors behind it are cleared together
+	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader) + 2 * align_up((size_t)tiles * sizeof(uint32_t)), stream);
 	if (s.P == 0) {
-		cudaMemsetAsync(g.ranges, 0, (size_t)s.grid_x * s.grid_y * sizeof(uint2), stream);
-		return;
+		cudaMemsetAsync(g.ranges, 0, (size_t)tiles * sizeof(uint2), stream);
+		return false;
 	}
 	int vec_mask = (aligned16(s.means3D) ? 1 : 0) | (aligned16(s.scales) ? 2 : 0) |
 	               (aligned16(s.colors_precomp ? s.colors_precomp : s.shs) ? 4 : 0);
 	// CTA-private tile histogram in shared memory while it fits next to the static arrays (<= 8192 tiles, e.g. 1920x1080)
-	const int tiles = s.grid_x * s.grid_y;
 	const int hist_smem = tiles <= 8192 ? 1 : 0;
-	preprocess_forward_kernel<<<(s.P + 255) / 256, 256, hist_smem ? tiles * sizeof(uint32_t) : 0, stream>>>(
-		s, g, radii, n_touched, vec_mask, hist_smem);
+	const int grid = (s.P + 255) / 256;
+	FusedScatterArgs fa;
+	fa.pairs = bin ? bin->pairs : nullptr;
+	fa.capacity = (unsigned)R_capacity;
+	static const bool no_fuse = getenv("GSR_NO_FUSED_SCATTER") != nullptr;      // A/B switch for measurements
+	if (bin && R_capacity > 0 && tiles <= 4096 && !no_fuse) {
+		const size_t smem = 2 * (size_t)tiles * sizeof(uint32_t);
+		int dev = 0, sms = 0, per_sm = 0, coop = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, preprocess_forward_kernel<true>, 256, smem);
+		if (coop && (long long)per_sm * sms >= grid) {
+			Scene sc = s;
+			GeomView gv = g;
+			int hs = 1;
+			void* args[] = {&sc, &gv, &radii, &n_touched, &vec_mask, &hs, &fa};
+			if (cudaLaunchCooperativeKernel((const void*)preprocess_forward_kernel<true>, dim3(grid), dim3(256), args, smem, stream) == cudaSuccess)
+				return true;
+			cudaGetLastError();      // fall back to the two-kernel path
+		}
+	}
+	preprocess_forward_kernel<false><<<grid, 256, hist_smem ? tiles * sizeof(uint32_t) : 0, stream>>>(s, g, radii, n_touched, vec_mask,
+	                                                                                                 hist_smem, fa);
+	return false;
 }
 
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present, cudaStream_t stream)

@@ -152,12 +152,9 @@ class RasterEngine:
 
     # ---- un-synchronised launches ---------------------------------------------------------------------
     def launch_forward(self):
-        st = self._stream()
-        _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
-                                        _p(self.n_touched), st), "forward_plan")
-        _cabi.check(_L.gsr_forward_render(C.byref(self.scene), _p(self.geom), _p(self.binning), self.bin_bytes,
-                                          self.capacity, -1, self.max_tile_hint, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
-                                          _p(self.opacity), _p(self.n_touched), st), "forward_render")
+        _cabi.check(_L.gsr_forward_nosync(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.binning), self.bin_bytes,
+                                          self.capacity, self.max_tile_hint, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
+                                          _p(self.opacity), _p(self.radii), _p(self.n_touched), self._stream()), "forward_nosync")
 
     def attach_densification_stats(self, xyz_gradient_accum=None, denom=None, max_radii2D=None):
         """fp32 [P] (or [P,1]) device tensors updated in the backward's epilogue for the visible Gaussians of each view:

@@ -112,6 +112,15 @@ int gsr_rasterize_gaussians(const gsr_scene* s, void* geom, size_t geom_bytes, v
                             long long* num_rendered_host, float* out_color, float* out_depth, float* out_opacity,
                             int* radii, int* n_touched, void* stream);
 
+/* Stage A + B in one call for callers that own a pre-sized binning workspace and do not want the host to see
+ * num_rendered (RasterEngine: no synchronisation, graph capturable).  Same results as gsr_forward_plan +
+ * gsr_forward_render(num_rendered_host = -1); knowing the binning workspace up front lets the preprocess kernel build the
+ * per-tile segments itself (cooperative launch, one grid barrier) when every CTA of its grid can be resident at once.
+ * Check gsr_forward_overflowed() afterwards. */
+int gsr_forward_nosync(const gsr_scene* scene, void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes,
+                       long long binning_capacity, long long max_tile_hint, void* image, size_t image_bytes, float* out_color,
+                       float* out_depth, float* out_opacity, int* radii, int* n_touched, void* stream);
+
 /* ---- backward ---- */
 /* Consumes dL/dcolor[3,H,W] and dL/ddepth[1,H,W] only (the reference drops the gradient of the
  * opacity image, __init__.py:114,139-140).  Every output row is written; outputs need no zero fill.
