@@ -127,15 +127,16 @@ def l2_flusher(device):
     return flush
 
 
-def roofline_bytes(P, R, HW, fused_sort=False):
+def roofline_bytes(P, R, HW, fused_sort=False, fused_scatter=False):
     """Algorithmic bytes per stage (SH degree 0).  The 44 B/instance of binning are 12 (write key +
     value) + 24 (one ideal sort pass: 12 read + 12 write) + 8 (key read for the ranges); when the forward compositing
     kernel sorts its own tile (lists <= 2048 entries) the "binning" stage is the scatter alone and the sort + range
     bytes move to "render_forward"."""
     sort = 32 * R if fused_sort else 0
+    scat = 12 * R if fused_scatter else 0       # cooperative preprocess + scatter: the pair writes belong to "preprocess"
     return {
-        "preprocess": (56 + 8 + 44) * P,
-        "binning": 44 * R - sort,
+        "preprocess": (56 + 8 + 44) * P + scat,
+        "binning": 44 * R - sort - scat,
         "render_forward": 44 * R + 28 * HW + sort,
         "render_backward": (44 + 40) * R + 24 * HW + 40 * P,
         "preprocess_backward": (60 + 40 + 68) * P,
@@ -306,11 +307,11 @@ def run_ours(args, rank, world, device):
     names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
     R_mean = float(np.mean(Rs[Wm:]))
     HW = cfg["W"] * cfg["H"]
-    rb = roofline_bytes(cfg["P"], R_mean, HW, fused_sort_active(eng))
+    rb = roofline_bytes(cfg["P"], R_mean, HW, fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], cfg["W"], cfg["H"])))
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2       # dominant single kernel: one of the two composite kernels
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9
-    stages = {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]), "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
+    stages = {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]), "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if (ms > 0 and rb[n] > 0) else None}
               for n, ms in zip(names, stage)}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -484,7 +485,7 @@ def run_window(args, rank, world, device):
         return None
     HW = W * H
     R_view = R_sum / V
-    rb = roofline_bytes(cfg["P"], R_view, HW, fused_sort_active(eng))
+    rb = roofline_bytes(cfg["P"], R_view, HW, fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], W, H)))
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0

@@ -204,6 +204,8 @@ int gsr_forward_nosync(const gsr_scene* a, void* geom, size_t geom_bytes, void* 
 	                           out_depth, out_opacity, n_touched, st, scatter_done);
 }
 
+int gsr_forward_nosync_fuses_scatter(int P, int W, int H) { return gsr::fused_scatter_fits(P, (int)tiles_of(W, H)) ? 1 : 0; }
+
 int gsr_forward_overflowed(void* geom, void* stream, int* overflowed, long long* needed)
 {
 	if (!geom || !overflowed) return fail(GSR_ERR_ARG, "null argument");

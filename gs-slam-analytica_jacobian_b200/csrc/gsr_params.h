@@ -60,6 +60,7 @@ void launch_slam_loss(const SlamLossArgs& a, void* scratch, cudaStream_t stream)
 void launch_tracking_step(const TrackingStepArgs& a, cudaStream_t stream);
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
+bool fused_scatter_fits(int P, int tiles);
 // returns true when it also built the per-tile segments (cooperative fused scatter; needs the binning workspace)
 bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream,
                                const BinView* bin = nullptr, size_t R_capacity = 0);

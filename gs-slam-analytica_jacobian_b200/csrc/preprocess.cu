@@ -415,6 +415,19 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
 
 static inline bool aligned16(const void* p) { return ((size_t)p & 15) == 0; }
 
+// Can the cooperative preprocess + scatter kernel be used for P Gaussians on `tiles` tiles on the current device?
+bool fused_scatter_fits(int P, int tiles)
+{
+	static const bool no_fuse = getenv("GSR_NO_FUSED_SCATTER") != nullptr;      // A/B switch for measurements
+	if (no_fuse || P <= 0 || tiles > 4096) return false;
+	int dev = 0, sms = 0, per_sm = 0, coop = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, preprocess_forward_kernel<true>, 256, 2 * (size_t)tiles * sizeof(uint32_t));
+	return coop && (long long)per_sm * sms >= (P + 255) / 256;
+}
+
 // Returns true when the kernel also built the per-tile segments (fused scatter): only attempted when the caller hands in
 // the binning workspace (no-sync path), the CTA-private histogram fits and every CTA of the grid can be resident at once.
 bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, int* n_touched, cudaStream_t stream,
@@ -435,23 +448,15 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 	FusedScatterArgs fa;
 	fa.pairs = bin ? bin->pairs : nullptr;
 	fa.capacity = (unsigned)R_capacity;
-	static const bool no_fuse = getenv("GSR_NO_FUSED_SCATTER") != nullptr;      // A/B switch for measurements
-	if (bin && R_capacity > 0 && tiles <= 4096 && !no_fuse) {
+	if (bin && R_capacity > 0 && fused_scatter_fits(s.P, tiles)) {
 		const size_t smem = 2 * (size_t)tiles * sizeof(uint32_t);
-		int dev = 0, sms = 0, per_sm = 0, coop = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, preprocess_forward_kernel<true>, 256, smem);
-		if (coop && (long long)per_sm * sms >= grid) {
-			Scene sc = s;
-			GeomView gv = g;
-			int hs = 1;
-			void* args[] = {&sc, &gv, &radii, &n_touched, &vec_mask, &hs, &fa};
-			if (cudaLaunchCooperativeKernel((const void*)preprocess_forward_kernel<true>, dim3(grid), dim3(256), args, smem, stream) == cudaSuccess)
-				return true;
-			cudaGetLastError();      // fall back to the two-kernel path
-		}
+		Scene sc = s;
+		GeomView gv = g;
+		int hs = 1;
+		void* args[] = {&sc, &gv, &radii, &n_touched, &vec_mask, &hs, &fa};
+		if (cudaLaunchCooperativeKernel((const void*)preprocess_forward_kernel<true>, dim3(grid), dim3(256), args, smem, stream) == cudaSuccess)
+			return true;
+		cudaGetLastError();      // fall back to the two-kernel path
 	}
 	preprocess_forward_kernel<false><<<grid, 256, hist_smem ? tiles * sizeof(uint32_t) : 0, stream>>>(s, g, radii, n_touched, vec_mask,
 	                                                                                                 hist_smem, fa);

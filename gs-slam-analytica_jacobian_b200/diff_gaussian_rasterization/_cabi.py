@@ -19,7 +19,7 @@ EXPORTS = (
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
-    "gsr_tracking_step", "gsr_forward_nosync",
+    "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter",
 )
 
 
@@ -74,6 +74,7 @@ def load():
     lib.gsr_forward_num_rendered.argtypes = [vp, vp, C.POINTER(ll), C.POINTER(ll)]
     lib.gsr_forward_render.argtypes = [sp, vp, vp, sz, ll, ll, ll, vp, sz, vp, vp, vp, vp, vp]
     lib.gsr_forward_nosync.argtypes = [sp, vp, sz, vp, sz, ll, ll, vp, sz, vp, vp, vp, vp, vp, vp]
+    lib.gsr_forward_nosync_fuses_scatter.argtypes = [ip, ip, ip]
     lib.gsr_forward_overflowed.argtypes = [vp, vp, C.POINTER(ip), C.POINTER(ll)]
     lib.gsr_rasterize_gaussians.argtypes = [sp, vp, sz, vp, sz, ALLOC_FN, vp, C.POINTER(vp), C.POINTER(ll),
                                             vp, vp, vp, vp, vp, vp]

@@ -121,6 +121,9 @@ int gsr_forward_nosync(const gsr_scene* scene, void* geometry, size_t geometry_b
                        long long binning_capacity, long long max_tile_hint, void* image, size_t image_bytes, float* out_color,
                        float* out_depth, float* out_opacity, int* radii, int* n_touched, void* stream);
 
+/* 1 if gsr_forward_nosync would use the cooperative preprocess + scatter kernel for this shape on the current device */
+int gsr_forward_nosync_fuses_scatter(int P, int W, int H);
+
 /* ---- backward ---- */
 /* Consumes dL/dcolor[3,H,W] and dL/ddepth[1,H,W] only (the reference drops the gradient of the
  * opacity image, __init__.py:114,139-140).  Every output row is written; outputs need no zero fill.

@@ -11,8 +11,8 @@ python bench.py --steps 200 --warmup 5 > $O/bench_ours_$TAG.json 2> $O/bench_our
 cat $O/bench_ours_$TAG.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['stages'], d.get('cpu_baseline'))"
 fi
 python tools/profile_step.py C1_tum_tracking 3 > $O/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 6 -c 10 --csv --log-file $O/launches_$TAG.csv python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_launch_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 5 -c 8 --csv --log-file $O/launches_$TAG.csv python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 python tools/profile_step.py C1_tum_tracking 3 > $O/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 11 -c 5 -f -o $O/prof_$TAG python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 9 -c 4 -f -o $O/prof_$TAG python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"

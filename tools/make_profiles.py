@@ -58,7 +58,7 @@ pipes = ["smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_execut
 with open(os.path.join(P, "%s_ncu_full_C1.md" % prefix), "w") as out:
     out.write("# ncu --set full, C1 (640x480, P=100k, R=1.08M), one un-graphed forward+backward step, B200\n\n")
     out.write("Command (tools/gpu_round.sh): `ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|"
-              "tile_sort|mark)' -s 11 -c 5 python tools/profile_step.py C1_tum_tracking 3`.\n")
+              "tile_sort|mark)' -s 9 -c 4 python tools/profile_step.py C1_tum_tracking 3`.\n")
     out.write("Times under ncu are serialised, cold-cache single launches; the live CUDA-event stage times are in the bench line.\n\n")
     out.write(summary)
     out.write("\n## pipe utilisation (% of peak while active)\n\n| kernel | issue | ALU | FMA | XU (MUFU/conv) | LSU | threads/inst | "
