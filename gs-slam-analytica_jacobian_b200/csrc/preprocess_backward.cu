@@ -127,9 +127,21 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 		float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 		float dscale[3] = {0.f, 0.f, 0.f};
 		float drot[4] = {0.f, 0.f, 0.f, 0.f};
-		const bool visible = radii[idx] > 0;
+		// Every global input of this Gaussian is requested up front, before its visibility is known: the loads are then in
+		// flight together instead of forming the chain radii -> (accumulator, parameters) of two dependent round trips,
+		// which is what bounds this kernel (few warps per SM, one long dependent computation per thread).
+		const int radius = radii[idx];
+		const GaussAcc a = g.acc[idx];
+		const float mx = __ldg(s.means3D + 3 * idx), my = __ldg(s.means3D + 3 * idx + 1), mz = __ldg(s.means3D + 3 * idx + 2);
+		float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+		float sc_in[3] = {0.f, 0.f, 0.f};
+		if (!s.cov3D_precomp) {
+			q_in = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
+#pragma unroll
+			for (int i = 0; i < 3; i++) sc_in[i] = __ldg(s.scales + 3 * idx + i);
+		}
+		const bool visible = radius > 0;
 		if (visible) {
-			const GaussAcc a = g.acc[idx];
 			GaussAcc z;
 			z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
 			g.acc[idx] = z;   // consumed: ready for the next backward without a memset
@@ -139,7 +151,6 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 			const float ddepth = a.a2.y;
 			dcol[0] = a.a2.z; dcol[1] = a.a3.x; dcol[2] = a.a3.y;
 
-			const float mx = s.means3D[3 * idx], my = s.means3D[3 * idx + 1], mz = s.means3D[3 * idx + 2];
 			// ---- 3D covariance (recomputed; reference re-reads geomState.cov3D) ----
 			float c3[6];
 			float sc[3] = {0.f, 0.f, 0.f};
@@ -149,13 +160,13 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 #pragma unroll
 				for (int i = 0; i < 6; i++) c3[i] = s.cov3D_precomp[(size_t)idx * 6 + i];
 			} else {
-				q = reinterpret_cast<const float4*>(s.rotations)[idx];
+				q = q_in;
 				const float r = q.x, x = q.y, y = q.z, zq = q.w;
 				Rq[0][0] = 1.f - 2.f * (y * y + zq * zq); Rq[0][1] = 2.f * (x * y - r * zq); Rq[0][2] = 2.f * (x * zq + r * y);
 				Rq[1][0] = 2.f * (x * y + r * zq); Rq[1][1] = 1.f - 2.f * (x * x + zq * zq); Rq[1][2] = 2.f * (y * zq - r * x);
 				Rq[2][0] = 2.f * (x * zq - r * y); Rq[2][1] = 2.f * (y * zq + r * x); Rq[2][2] = 1.f - 2.f * (x * x + y * y);
 #pragma unroll
-				for (int i = 0; i < 3; i++) sc[i] = s.scale_modifier * s.scales[3 * idx + i];
+				for (int i = 0; i < 3; i++) sc[i] = s.scale_modifier * sc_in[i];
 				float Sg[3][3];
 #pragma unroll
 				for (int aa = 0; aa < 3; aa++)
