@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	GSR_PROBE(0, 4);
 	if (FUSED_SCATTER) {
 		// ---- grid-wide barrier (single use per launch: the counter is cleared by the memset in front of the kernel) ----
-		__threadfence();
 		__syncthreads();
 		if (threadIdx.x == 0) {
+			__threadfence();      // one cumulative release behind the CTA barrier (as in cooperative-groups' grid sync)
 			atomicAdd(&g.hdr->fwd_blocks_done, 1u);
 			while (*reinterpret_cast<volatile unsigned*>(&g.hdr->fwd_blocks_done) < gridDim.x) { }
 			__threadfence();
@@ -354,9 +354,11 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		if (overflow) g.hdr->overflow = 1;
 		return;
 	}
-	__threadfence();
 	__syncthreads();
-	if (threadIdx.x == 0) s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
+	if (threadIdx.x == 0) {
+		__threadfence();      // one cumulative release behind the CTA barrier
+		s_last = (atomicAdd(&g.hdr->fwd_blocks_done, 1u) == gridDim.x - 1);
+	}
 	__syncthreads();
 	GSR_PROBE(0, 5);
 	if (!s_last) return;

@@ -70,9 +70,11 @@ slam_loss_kernel(SlamLossArgs a, float* __restrict__ partials, unsigned* __restr
 		for (int w = 0; w < 8; w++) v += s_red[w][threadIdx.x];
 		partials[blockIdx.x * 4 + threadIdx.x] = v;
 	}
-	__threadfence();
 	__syncthreads();
-	if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	if (threadIdx.x == 0) {
+		__threadfence();      // one cumulative release behind the CTA barrier
+		s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+	}
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence();
