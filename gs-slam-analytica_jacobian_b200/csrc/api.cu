@@ -94,7 +94,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 // lists of 2049..8192 entries are sorted by the long-list kernel, longer ones through global memory
 int pick_cap_smem(long long max_tile_hint)
 {
-	return (max_tile_hint > 0 && max_tile_hint <= 1024) ? 1024 : 2048;
+	return (max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK / 2) ? GSR_SORT_CHUNK / 2 : GSR_SORT_CHUNK;
 }
 
 }  // namespace
@@ -158,7 +158,7 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
-	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= 2048 && !g_no_fused_sort;
+	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK && !g_no_fused_sort;
 	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done);
 	stage_mark(2, st);
 	int rc = debug_sync(a, st, "binning");

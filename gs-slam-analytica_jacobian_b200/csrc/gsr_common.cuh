@@ -7,6 +7,9 @@
 #define GSR_TILE 16            // tile edge in pixels (reference config.h:16-17 BLOCK_X/BLOCK_Y)
 #define GSR_TILE_PIX 256
 #define GSR_ALIGN 256          // carve-up alignment inside workspaces
+#define GSR_SORT_CHUNK 2048    // longest tile list the 256-thread sort handles as one shared-memory chunk (8 keys per thread);
+                               // lists above it are queued for the long-list kernel, lists up to it can be sorted by the
+                               // forward compositing kernel itself
 
 namespace gsr {
 
@@ -40,7 +43,7 @@ struct GeomHeader {
 	unsigned int fwd_blocks_done;
 	unsigned int bwd_blocks_done;
 	unsigned int max_tile_count; // longest per-tile list
-	unsigned int num_long_tiles; // tiles queued for the long-list sort kernel (> 2048 entries)
+	unsigned int num_long_tiles; // tiles queued for the long-list sort kernel (> GSR_SORT_CHUNK entries)
 	unsigned int pad[64 - 7];
 };
 static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");

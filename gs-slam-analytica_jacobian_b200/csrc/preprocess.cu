@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 				s_start[t] = run;
 				if (blockIdx.x == 0) {
 					g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
-					if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;
+					if (c > (unsigned)GSR_SORT_CHUNK) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;
 					mx = max(mx, c);
 				}
 				run += c;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			const unsigned c = (t - t0 < kHold) ? held[t - t0] : __ldcg(&g.tile_count[t]);
 			g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
 			g.tile_cursor[t] = run;
-			if (c > 2048u) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;   // binning.cu: kSmallChunk
+			if (c > (unsigned)GSR_SORT_CHUNK) g.long_tiles[atomicAdd(&g.hdr->num_long_tiles, 1u)] = (uint32_t)t;
 			run += c;
 			mx = max(mx, c);
 		}

@@ -89,7 +89,7 @@ struct FusedSortArgs {
 	GeomHeader* hdr;
 };
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
-constexpr int kFusedIdsCap = 2048;
+constexpr int kFusedIdsCap = GSR_SORT_CHUNK;
 
 template <bool FUSED_SORT>
 __global__ void __launch_bounds__(256, 4)

@@ -12,6 +12,7 @@ constexpr int kMaxDigitBits = 9;
 constexpr int kMaxBins = 1 << kMaxDigitBits;
 constexpr int kSmallThreads = 256, kLongThreads = 512;
 constexpr int kSmallChunk = kSmallThreads * kSortItems;   // 2048
+static_assert(kSmallChunk == GSR_SORT_CHUNK, "the preprocess scan, the API and the sort kernels agree on the chunk length");
 constexpr int kLongChunk = kLongThreads * kSortItems;     // 4096
 
 struct Field {       // which 32-bit word of the pair a pass looks at
