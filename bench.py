@@ -387,13 +387,19 @@ def run_window(args, rank, world, device):
     dc_pin, dd_pin = torch.from_numpy(dc).pin_memory(), torch.from_numpy(dd).pin_memory()
     eng.dL_dcolor.copy_(dc_pin)
     eng.dL_ddepth.copy_(dd_pin)
-    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world)
+    extra = []
+    for _ in range(max(args.engines, 1) - 1):      # further engines over the same Gaussians: views overlap on separate streams
+        e2 = RasterEngine(dict(means3D=eng.g["means3D"], opacities=eng.g["opacities"], shs=eng.g["shs"], scales=eng.g["scales"],
+                               rotations=eng.g["rotations"]), W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
+        e2.dL_dcolor.copy_(dc_pin); e2.dL_ddepth.copy_(dd_pin)
+        extra.append(e2)
+    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world, extra_engines=extra)
     win.calibrate()
     Rs = []
     for v in win.views:
         eng.set_camera(cams_dev[v])
         Rs.append(eng.calibrate())
-    up = lambda v: (eng.dL_dcolor, eng.dL_ddepth)
+    up = (lambda v, e: (e.dL_dcolor, e.dL_ddepth)) if extra else (lambda v: (eng.dL_dcolor, eng.dL_ddepth))
     flush = l2_flusher(device)
     stream = torch.cuda.current_stream(device)
 
@@ -430,10 +436,11 @@ def run_window(args, rank, world, device):
     tau_pin = torch.empty((max(len(win.views), 1), 6), dtype=torch.float32).pin_memory()
     norm_pin = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def up_host(v):
-        eng.dL_dcolor.copy_(dc_pin, non_blocking=True)
-        eng.dL_ddepth.copy_(dd_pin, non_blocking=True)
-        return eng.dL_dcolor, eng.dL_ddepth
+    def up_host(v, e=None):
+        e = eng if e is None else e
+        e.dL_dcolor.copy_(dc_pin, non_blocking=True)
+        e.dL_ddepth.copy_(dd_pin, non_blocking=True)
+        return e.dL_dcolor, e.dL_ddepth
 
     def e2e_step():
         cams_dev.copy_(cams_pin, non_blocking=True)
@@ -499,7 +506,7 @@ def run_window(args, rank, world, device):
                    "views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view,
                    "collective": ("all_reduce(sum) of %d B of packed per-Gaussian gradients per step" % grad_bytes) if reduce else "none",
                    "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
-                   "parallelism": "keyframe-parallel x%d" % world},
+                   "parallelism": "keyframe-parallel x%d, %d engine(s) / stream(s) per GPU" % (world, len(win.engines))},
         "e2e": {"value": K / emax, "unit": "window iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3},
         "gpu_launches": launches_per_step * K,
@@ -780,6 +787,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1_tum_tracking")
     ap.add_argument("--views", type=int, default=0, help="override the window size of C2/C3/C4")
+    ap.add_argument("--engines", type=int, default=2, help="window workloads: engines (streams) the local views are dealt to")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

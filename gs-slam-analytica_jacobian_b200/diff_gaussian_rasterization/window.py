@@ -45,22 +45,31 @@ class KeyframeWindow:
     upstream(v) -> (dL_dcolor[3,H,W], dL_ddepth[1,H,W]) device tensors for view v, called AFTER view v's
     forward so it may depend on engine.color / engine.depth (the loss gradient); or a pair of
     [V,3,H,W] / [V,1,H,W] tensors.
+
+    extra_engines: further RasterEngines over the SAME Gaussians (own workspaces and output buffers).  The local views
+    are then dealt round robin to the engines, each on its own CUDA stream, so that the latency-bound stages of one view
+    (per-Gaussian kernels, scatter, sort) overlap the issue-bound compositing of another; every engine accumulates into
+    its own flat gradient buffer and the buffers are summed into the first engine's before the all-reduce.  With several
+    engines `upstream` is called as upstream(v, engine).
     """
 
-    def __init__(self, engine, cameras, rank=0, world_size=1, group=None):
+    def __init__(self, engine, cameras, rank=0, world_size=1, group=None, extra_engines=()):
         self.engine, self.cameras = engine, cameras
+        self.engines = [engine] + list(extra_engines)
         self.rank, self.world, self.group = rank, world_size, group
         self.views = shard_views(int(cameras.shape[0]), world_size, rank)
         V = len(self.views)
         dev = engine.dev
         self.tau = torch.zeros((V, 6), dtype=torch.float32, device=dev)             # per local view [rho, theta]
         self.num_rendered = [0] * V
+        self.streams = [torch.cuda.Stream(dev) for _ in self.engines] if len(self.engines) > 1 else None
 
     def calibrate(self):
         """Size the binning workspace for the largest local view (one exact plan per view)."""
-        for v in self.views:
-            self.engine.set_camera(self.cameras[v])
-            self.engine.calibrate()
+        for e in self.engines:
+            for v in self.views:
+                e.set_camera(self.cameras[v])
+                e.calibrate()
 
     def iteration(self, upstream, reduce=True, on_view=None):
         """One window iteration.  Returns engine.grad_flat (summed over all views of all ranks when
@@ -68,17 +77,43 @@ class KeyframeWindow:
         eng = self.engine
         if not self.views:
             eng.grad_flat.zero_()        # a rank without views still takes part in the collective
-        for i, v in enumerate(self.views):
-            eng.set_camera(self.cameras[v])
-            eng.launch_forward()
-            if callable(upstream):
-                gc, gd = upstream(v)
-            else:
-                gc, gd = upstream[0][v], upstream[1][v]
-            eng.launch_backward(gc, gd, accumulate=(i > 0))
-            self.tau[i].copy_(eng.g_tau, non_blocking=True)
-            if on_view is not None:
-                on_view(i, v)
+        if self.streams is None:
+            for i, v in enumerate(self.views):
+                eng.set_camera(self.cameras[v])
+                eng.launch_forward()
+                if callable(upstream):
+                    gc, gd = upstream(v)
+                else:
+                    gc, gd = upstream[0][v], upstream[1][v]
+                eng.launch_backward(gc, gd, accumulate=(i > 0))
+                self.tau[i].copy_(eng.g_tau, non_blocking=True)
+                if on_view is not None:
+                    on_view(i, v)
+        else:
+            main = torch.cuda.current_stream(eng.dev)
+            used = [False] * len(self.engines)
+            for st in self.streams:
+                st.wait_stream(main)
+            for i, v in enumerate(self.views):
+                k = i % len(self.engines)
+                e = self.engines[k]
+                with torch.cuda.stream(self.streams[k]):
+                    e.set_camera(self.cameras[v])
+                    e.launch_forward()
+                    if callable(upstream):
+                        gc, gd = upstream(v, e)
+                    else:
+                        gc, gd = upstream[0][v], upstream[1][v]
+                    e.launch_backward(gc, gd, accumulate=used[k])
+                    used[k] = True
+                    self.tau[i].copy_(e.g_tau, non_blocking=True)
+                    if on_view is not None:
+                        on_view(i, v)
+            for st in self.streams:
+                main.wait_stream(st)
+            for k in range(1, len(self.engines)):
+                if used[k]:
+                    eng.grad_flat.add_(self.engines[k].grad_flat)
         if reduce:
             allreduce_window_gradients(eng.grad_flat, self.group)
         return eng.grad_flat

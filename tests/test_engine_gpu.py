@@ -196,3 +196,28 @@ def test_fused_sort_survives_lists_longer_than_the_hint():
     assert np.array_equal(eng.color.cpu().numpy(), ref["color"])
     assert rel_err(eng.g_tau.cpu().numpy(), ref["dL_dtau"]) <= 1e-5
     assert rel_err(eng.g_means3D.cpu().numpy(), ref["dL_dmeans3D"]) <= 1e-5
+
+
+def test_window_with_two_engines_on_two_streams_matches_one_engine():
+    from diff_gaussian_rasterization import scenes as S
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    V = 5
+    cfg, sc, cams = _scene_and_cams(V=V)
+    packed = torch.stack([_pack(c) for c in cams])
+    grads = [S.make_pixel_grads(cfg["W"], cfg["H"], seed=30 + v) for v in range(V)]
+    gc = torch.stack([torch.from_numpy(g[0]) for g in grads]).cuda()
+    gd = torch.stack([torch.from_numpy(g[1]) for g in grads]).cuda()
+    e1 = _engine(sc, cfg)
+    w1 = KeyframeWindow(e1, packed)
+    w1.calibrate()
+    flat1 = w1.iteration((gc, gd)).clone()
+    tau1 = w1.tau.clone()
+    ea, eb = _engine(sc, cfg), _engine(sc, cfg)
+    w2 = KeyframeWindow(ea, packed, extra_engines=[eb])
+    w2.calibrate()
+    for _ in range(2):      # twice: the second iteration must not see leftovers of the first
+        flat2 = w2.iteration((gc, gd))
+        torch.cuda.synchronize()
+        assert rel_err(flat2.cpu().numpy(), flat1.cpu().numpy()) <= 1e-5
+        assert rel_err(w2.tau.cpu().numpy(), tau1.cpu().numpy()) <= 1e-5
