@@ -21,6 +21,9 @@ std::atomic<unsigned long long> g_launches{0};   // kernels launched by this lib
 // optional stage timing (bench.py roofline): CUDA events recorded on the launching stream between stages
 bool g_timing = false;
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
+// lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
+// is sorted completely
+std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
 cudaEvent_t g_ev[7];
 void stage_mark(int i, cudaStream_t st)
 {
@@ -158,12 +161,16 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
-	const bool fuse_sort = max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK && !g_no_fused_sort;
+	// or ANY list length when lists are ordered on demand
+	// (when the longest list expected does not reach the threshold, the plain fused kernel does: it still copes with longer ones)
+	int lazy_min = g_no_fused_sort ? 0 : g_lazy_min.load();
+	if (max_tile_hint > 0 && max_tile_hint <= lazy_min) lazy_min = 0;
+	const bool fuse_sort = !g_no_fused_sort && (lazy_min > 0 || (max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK));
 	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done);
 	stage_mark(2, st);
 	int rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
-	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, (size_t)capacity, st);
+	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st);
 	stage_mark(3, st);
 	g_launches += 1;
 	return debug_sync(a, st, "render");
@@ -329,6 +336,13 @@ int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* ex
 }
 
 unsigned long long gsr_kernel_launch_count(void) { return g_launches.load(); }
+
+int gsr_sort_on_demand(int min_list_length)
+{
+	const int prev = g_lazy_min.load();
+	if (min_list_length >= 0) g_lazy_min.store(min_list_length);
+	return prev;
+}
 
 int gsr_stage_timing(int enable)
 {

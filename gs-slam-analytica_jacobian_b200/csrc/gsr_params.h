@@ -70,9 +70,10 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
                    bool fuse_sort, cudaStream_t stream, bool scatter_done = false);
 size_t tile_sort_smem_bytes(int cap_smem);
-// fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true)
+// fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true);
+// lazy_min > 0: lists longer than lazy_min are ordered on demand, slab by slab, as far as the compositing gets (render.cu)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
-                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, size_t R_capacity,
+                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
                            cudaStream_t stream);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
                             const float* dL_dpix, const float* dL_dpix_depth, cudaStream_t stream);

@@ -34,7 +34,6 @@ struct FwdSmem {
 	uint32_t id[2][256];
 	QueueRec queue[8][34];      // per warp: <= 32 survivors of a chunk + one padding record for the 2-way unroll
 	uint32_t tmask[8][32];      // per warp and queue slot: ballot of "still above 0.5 after this blend"
-	uint64_t bar[2];            // GSR_TMA_STAGE: one mbarrier per staging buffer
 };
 
 template <bool COUNT_TOUCHED>
@@ -75,10 +74,20 @@ __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int 
 	}
 }
 
-// FUSED_SORT: the CTA first sorts its tile's scattered (depth, id) segment (tile_sort.cuh; lists of at most 2048 entries
-// in shared memory, anything else through the general path) and composites straight from the sorted ids it keeps in
-// shared memory.  One launch less, no point_list round trip before the first gather, and the latency-bound sort phases
-// of one CTA overlap the issue-bound blending of the other CTAs on the SM.
+// FUSED_SORT: the CTA sorts its tile's scattered (depth, id) segment itself (tile_sort.cuh) and composites straight from
+// the sorted ids it keeps in shared memory.  One launch less, no point_list round trip before the first gather, and the
+// latency-bound sort phases of one CTA overlap the issue-bound blending of the other CTAs on the SM.
+//
+// ON-DEMAND ORDER (lists above lazy_min entries): front-to-back compositing stops once every pixel of the tile is opaque,
+// typically after a few hundred entries, however long the list is (measured: 37 % of the list at 640x480 / 100 k
+// Gaussians, 13 % at 1200x680 / 500 k, 2 % at 1920x1080 / 3 M).  So the CTA does not sort the list; it SELECTS: a
+// 256-bin histogram over the leading bits of the tile's depth-key range gives, for any bin boundary, the exact list
+// position where that depth slab starts; the entries of the first slab (the fewest bins holding >= kLazyTarget entries)
+// are compacted into shared memory, sorted there into (depth, id) order -- they are exactly the first entries of the
+// reference's list, at the reference's positions -- written to point_list and composited; only if pixels are still open
+// is the next slab selected and sorted.  Positions behind the tile's deepest contributor are never read by the forward
+// or the backward (backward.cu:763), and point_list holds the exact list up to there.  A slab that cannot be sorted in
+// shared memory (one bin above the chunk length) makes the CTA sort the whole list the general way and carry on.
 struct FusedSortArgs {
 	uint2* ranges;
 	uint2* pairs;
@@ -87,11 +96,242 @@ struct FusedSortArgs {
 	unsigned capacity;
 	int id_bits;
 	GeomHeader* hdr;
+	int lazy_min;        // lists longer than this are ordered on demand; <= 0: every list is sorted completely
 };
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
 constexpr int kFusedIdsCap = GSR_SORT_CHUNK;
+constexpr int kLazyBins = 256;            // one thread per bin
+constexpr int kLazyTarget = 512;          // entries a slab should hold at least: two compositing batches
+struct LazySmem {                         // lives behind the sort scratch: survives sorts and compositing
+	uint32_t excl[kLazyBins + 1];         // list position at which bin b starts
+	uint32_t wsum[8];
+	uint32_t red[16];
+	uint32_t b_hi;
+	uint32_t count;
+	// CTA-uniform list state, kept here rather than in registers of the compositing loop
+	uint32_t kmin;                        // smallest depth key of the tile
+	int shift;                            // bin = (key - kmin) >> shift
+	int b_lo;                             // first bin not ordered yet
+	int sorted_end;                       // list positions < sorted_end are final (point_list)
+	int ids_base, ids_cnt;                // s_ids[i] = id at list position ids_base + i, i < ids_cnt
+};
 
-template <bool FUSED_SORT>
+constexpr int kLazyOffset = 51456;        // bytes: behind the sort scratch of one 2048-entry chunk (sort_smem_bytes)
+
+// The helpers below are deliberately NOT inlined: they run once per slab, need the register file for themselves (8 keys
+// per thread in flight) and must not raise the register pressure of the compositing loop around them.  They find the
+// shared-memory carve-up themselves (a pointer parameter would turn every LDS/STS into a generic access).
+//
+// min / max of the segment's depth keys, 256-bin histogram over the leading bits of their range, exclusive scan:
+// lz->excl[b] = list position at which depth bin b starts; then the first slab is selected and sorted (see
+// lazy_sort_slab).  Lists of up to kLazyRegs * 256 entries are read from global memory ONCE and held in registers for the
+// three sweeps (range, histogram, selection); longer ones are re-read (L2).  All 256 threads.
+constexpr int kLazyRegs = 16;
+__device__ __forceinline__ void lazy_choose_slab(LazySmem* lz, int b_lo, uint32_t base, int& b_hi, int& m);
+__device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, int id_bits, uint32_t* __restrict__ list)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint32_t* sm_u32 = reinterpret_cast<uint32_t*>(smem_raw);
+	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset);
+	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
+	uint32_t* s_keys = sm_u32;
+	uint32_t* s_vals = sm_u32 + 2 * kSmallChunk;
+	uint32_t* s_cnt = sm_u32 + 4 * kSmallChunk;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	const bool in_regs = n <= kLazyRegs * 256;
+	uint2 kv[kLazyRegs];
+	uint32_t kmin = 0xffffffffu, kmax = 0;
+	if (in_regs) {
+#pragma unroll
+		for (int u = 0; u < kLazyRegs; u++) {
+			const int i = u * 256 + tid;
+			kv[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
+		}
+#pragma unroll
+		for (int u = 0; u < kLazyRegs; u++)
+			if (u * 256 + tid < n) { kmin = min(kmin, kv[u].x); kmax = max(kmax, kv[u].x); }
+	} else {
+		int i = tid;
+		for (; i + 3 * 256 < n; i += 4 * 256) {
+			uint32_t k[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) k[u] = __ldcg(&seg[i + u * 256].x);
+#pragma unroll
+			for (int u = 0; u < 4; u++) { kmin = min(kmin, k[u]); kmax = max(kmax, k[u]); }
+		}
+		for (; i < n; i += 256) { const uint32_t k = __ldcg(&seg[i].x); kmin = min(kmin, k); kmax = max(kmax, k); }
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		kmin = min(kmin, __shfl_xor_sync(kFull, kmin, o));
+		kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
+	}
+	if (lane == 0) { lz->red[warp] = kmin; lz->red[8 + warp] = kmax; }
+	lz->excl[tid] = 0;
+	if (tid == 0) { lz->b_hi = kLazyBins; lz->count = 0; }
+	// the per-warp digit counters of the slab sort, cleared once for both of its passes
+	for (int i = tid; i < 8 * kMaxBins / 4; i += 256) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+	kmin = lz->red[0]; kmax = lz->red[8];
+#pragma unroll
+	for (int w = 1; w < 8; w++) { kmin = min(kmin, lz->red[w]); kmax = max(kmax, lz->red[8 + w]); }
+	const int sig = (kmax == kmin) ? 0 : 32 - __clz(kmax - kmin);
+	const int shift = max(0, sig - 8);
+	if (in_regs) {
+#pragma unroll
+		for (int u = 0; u < kLazyRegs; u++)
+			if (u * 256 + tid < n) atomicAdd(&lz->excl[(kv[u].x - kmin) >> shift], 1u);
+	} else {
+		int i = tid;
+		for (; i + 3 * 256 < n; i += 4 * 256) {
+			uint32_t k[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) k[u] = __ldcg(&seg[i + u * 256].x);
+#pragma unroll
+			for (int u = 0; u < 4; u++) atomicAdd(&lz->excl[(k[u] - kmin) >> shift], 1u);
+		}
+		for (; i < n; i += 256) atomicAdd(&lz->excl[(__ldcg(&seg[i].x) - kmin) >> shift], 1u);
+	}
+	__syncthreads();
+	const uint32_t c = lz->excl[tid];
+	uint32_t incl = c;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(kFull, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) lz->wsum[warp] = incl;
+	__syncthreads();
+	uint32_t before = 0;
+	for (int w = 0; w < warp; w++) before += lz->wsum[w];
+	lz->excl[tid] = before + incl - c;
+	if (tid == kLazyBins - 1) lz->excl[kLazyBins] = before + incl;
+	if (tid == 0) {
+		lz->kmin = kmin; lz->shift = shift; lz->b_lo = 0;
+		lz->sorted_end = 0; lz->ids_base = 0; lz->ids_cnt = 0;
+	}
+	__syncthreads();
+	// ---- first slab ----
+	int b_hi, m;
+	lazy_choose_slab(lz, 0, 0u, b_hi, m);
+	if (m > kSmallChunk) return false;
+	const uint32_t width = (uint32_t)b_hi;
+	auto place = [&](bool pred, uint2 e) {
+		const unsigned mask = __ballot_sync(kFull, pred);
+		if (mask) {
+			uint32_t pos = 0;
+			if (lane == __ffs(mask) - 1) pos = atomicAdd(&lz->count, (uint32_t)__popc(mask));
+			pos = __shfl_sync(kFull, pos, __ffs(mask) - 1) + __popc(mask & lt);
+			if (pred) { s_keys[pos] = e.x; s_vals[pos] = e.y; }
+		}
+	};
+	if (in_regs) {
+#pragma unroll
+		for (int u = 0; u < kLazyRegs; u++)
+			if (u * 256 < n) place(u * 256 + tid < n && ((kv[u].x - kmin) >> shift) < width, kv[u]);
+	} else {
+		for (int i0 = 0; i0 < n; i0 += 4 * 256) {
+			uint2 e[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int i = i0 + u * 256 + tid;
+				e[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) place(i0 + u * 256 + tid < n && ((e[u].x - kmin) >> shift) < width, e[u]);
+		}
+	}
+	__syncthreads();
+	const unsigned long long span = (unsigned long long)width << shift;
+	const int sig_slab = span <= 1 ? 0 : 64 - __clzll((long long)(span - 1));
+	sort_loaded<256>(m, kSmallChunk, kmin, sig_slab, id_bits, sm_u32, [&](int i, uint32_t v) { list[i] = v; s_ids[i] = v; });
+	if (tid == 0) { lz->b_lo = b_hi; lz->ids_base = 0; lz->ids_cnt = m; lz->sorted_end = m; }
+	return true;
+}
+
+// The slab that starts at bin b_lo / list position base: up to the first bin boundary with at least kLazyTarget entries in
+// front of it (excl is non-decreasing), one bin less if that overshoots a shared-memory chunk.  Needs lz->b_hi == kLazyBins
+// on entry (behind a barrier); two barriers inside.
+__device__ __forceinline__ void lazy_choose_slab(LazySmem* lz, int b_lo, uint32_t base, int& b_hi, int& m)
+{
+	const int j = threadIdx.x + 1;
+	if (j > b_lo) {
+		const uint32_t c = lz->excl[j] - base, cprev = lz->excl[j - 1] - base;
+		if (c >= (uint32_t)kLazyTarget && cprev < (uint32_t)kLazyTarget) lz->b_hi = (uint32_t)j;
+	}
+	__syncthreads();
+	b_hi = (int)lz->b_hi;
+	m = (int)(lz->excl[b_hi] - base);
+	if (m > kSmallChunk && b_hi - 1 > b_lo && lz->excl[b_hi - 1] - base > 0) { b_hi--; m = (int)(lz->excl[b_hi] - base); }
+}
+
+// Selects the next depth slab (bins [b_lo, b_hi), starting at list position sorted_end), compacts its entries into the
+// sort scratch and sorts them: ids -> list[sorted_end ...) (global) and s_ids.  Advances the list state in LazySmem and
+// returns true; returns false when the slab does not fit one shared-memory chunk (nothing written).  All 256 threads.
+__device__ __noinline__ bool lazy_sort_slab(const uint2* seg, int n, int id_bits, uint32_t* __restrict__ list)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint32_t* sm_u32 = reinterpret_cast<uint32_t*>(smem_raw);
+	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset);
+	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
+	const int tid = threadIdx.x, lane = tid & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	uint32_t* s_keys = sm_u32;
+	uint32_t* s_vals = sm_u32 + 2 * kSmallChunk;
+	uint32_t* s_cnt = sm_u32 + 4 * kSmallChunk;
+	const int b_lo = lz->b_lo, shift = lz->shift;
+	const uint32_t base = (uint32_t)lz->sorted_end, kmin = lz->kmin;
+	__syncthreads();      // everyone holds the state before thread 0 touches the fields next to it
+	if (tid == 0) { lz->b_hi = kLazyBins; lz->count = 0; lz->ids_cnt = 0; }
+	for (int i = tid; i < 8 * kMaxBins / 4; i += 256) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+	int b_hi, m;
+	lazy_choose_slab(lz, b_lo, base, b_hi, m);
+	if (m > kSmallChunk) return false;
+	const uint32_t lo = (uint32_t)b_lo, width = (uint32_t)(b_hi - b_lo);
+	for (int i0 = 0; i0 < n; i0 += 4 * 256) {
+		uint2 kv[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int i = i0 + u * 256 + tid;
+			kv[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int i = i0 + u * 256 + tid;
+			const bool pred = i < n && (((kv[u].x - kmin) >> shift) - lo) < width;
+			const unsigned mask = __ballot_sync(kFull, pred);
+			if (mask) {
+				uint32_t pos = 0;
+				if (lane == __ffs(mask) - 1) pos = atomicAdd(&lz->count, (uint32_t)__popc(mask));
+				pos = __shfl_sync(kFull, pos, __ffs(mask) - 1) + __popc(mask & lt);
+				if (pred) { s_keys[pos] = kv[u].x; s_vals[pos] = kv[u].y; }
+			}
+		}
+	}
+	__syncthreads();
+	const uint32_t kmin_slab = kmin + (lo << shift);
+	const unsigned long long span = (unsigned long long)width << shift;
+	const int sig_slab = span <= 1 ? 0 : 64 - __clzll((long long)(span - 1));
+	uint32_t* out = list + base;
+	sort_loaded<256>(m, kSmallChunk, kmin_slab, sig_slab, id_bits, sm_u32, [&](int i, uint32_t v) { out[i] = v; s_ids[i] = v; });
+	if (tid == 0) { lz->b_lo = b_hi; lz->ids_base = (int)base; lz->ids_cnt = m; lz->sorted_end = (int)base + m; }
+	return true;
+}
+
+// the whole list of the tile, sorted the general way (ids -> point_list and, up to ids_cap of them, s_ids)
+__device__ __noinline__ void sort_whole_tile(int tile, FusedSortArgs fs, int ids_cap)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	sort_tile<256>(tile, fs.ranges, fs.pairs, fs.pairs_alt, fs.point_list, fs.capacity, kSmallChunk, fs.id_bits, fs.hdr,
+	               reinterpret_cast<uint32_t*>(smem_raw), ids_cap > 0 ? reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset) : nullptr,
+	               ids_cap);
+}
+
+// MODE 0: point_list holds the sorted lists.  MODE 1: the CTA sorts its whole list first (every list expected to fit one
+// shared-memory chunk; anything longer takes the general path).  MODE 2: lists above fs.lazy_min are ordered on demand.
+template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
@@ -103,15 +343,46 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	static_assert(sizeof(FwdSmem) <= kFusedIdsOffset, "sorted ids must sit behind the compositing overlay");
 	FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 	const uint32_t* s_ids = reinterpret_cast<const uint32_t*>(smem_raw + kFusedIdsOffset);
-	if (FUSED_SORT) {
-		sort_tile<256>((int)blockIdx.x, fs.ranges, fs.pairs, fs.pairs_alt, fs.point_list, fs.capacity, kSmallChunk, fs.id_bits,
-		               fs.hdr, reinterpret_cast<uint32_t*>(smem_raw), reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset),
-		               kFusedIdsCap);
-		__threadfence_block();
-		__syncthreads();      // sorted ids (shared + global) and a possibly clamped range are visible to the whole CTA
-	}
-
+	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
 	const int tile = blockIdx.x;
+
+	constexpr bool FUSED_SORT = MODE != 0;
+	// ---- the tile's list: complete, or ordered on demand (positions < lz->sorted_end are final) ----
+	uint2 range;
+	int n;
+	if (MODE == 2) {
+		range = fs.ranges[tile];
+		n = (int)(range.y - range.x);
+		if (range.y <= fs.capacity && n > fs.lazy_min) {
+			if (!lazy_first_slab(fs.pairs + range.x, n, fs.id_bits, fs.point_list + range.x)) {
+				// the first depth bin alone is beyond the chunk length: sort the whole list the general way
+				sort_whole_tile(tile, fs, 0);
+				if (threadIdx.x == 0) { lz->sorted_end = n; lz->ids_cnt = 0; }
+			}
+			__threadfence_block();
+			__syncthreads();
+		} else {
+			sort_whole_tile(tile, fs, kFusedIdsCap);
+			__threadfence_block();
+			__syncthreads();      // sorted ids (shared + global) and a possibly clamped range are visible to the whole CTA
+			range = __ldcg(&fs.ranges[tile]);
+			n = (int)(range.y - range.x);
+			if (threadIdx.x == 0) { lz->sorted_end = n; lz->ids_base = 0; lz->ids_cnt = min(n, kFusedIdsCap); }
+			__syncthreads();
+		}
+	} else if (MODE == 1) {
+		sort_tile<256>(tile, fs.ranges, fs.pairs, fs.pairs_alt, fs.point_list, fs.capacity, kSmallChunk, fs.id_bits, fs.hdr,
+		               reinterpret_cast<uint32_t*>(smem_raw), reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset), kFusedIdsCap);
+		__threadfence_block();
+		__syncthreads();
+		range = __ldcg(&fs.ranges[tile]);
+		n = (int)(range.y - range.x);
+	} else {
+		range = ranges[tile];
+		n = (int)(range.y - range.x);
+	}
+	const bool ids_in_smem = MODE == 1 && n <= kFusedIdsCap;
+
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -121,10 +392,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	const float pxf = (float)px, pyf = (float)py;
 	const float bx0 = (float)(tile_x * GSR_TILE + (warp & 1) * 8), by0 = (float)(tile_y * GSR_TILE + (warp >> 1) * 4);
 	const float bx1 = bx0 + 7.f, by1 = by0 + 3.f;
-	const uint2 range = FUSED_SORT ? __ldcg(&fs.ranges[tile]) : ranges[tile];
-	const int n = (int)(range.y - range.x);
 	const int rounds = (n + 255) / 256;
-	const bool ids_in_smem = FUSED_SORT && n <= kFusedIdsCap;
 	QueueRec* wq = sm.queue[warp];
 	uint32_t* wmask = sm.tmask[warp];
 	uint32_t* my_masks = cull_masks + cull_mask_base(range.x, (uint32_t)tile) + warp;   // [group of 32 positions][warp]
@@ -135,38 +403,16 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	// T only decreases, so once no live pixel of the warp is above 0.5 the n_touched bookkeeping is skipped for good.
 	bool warp_hi_T = __any_sync(kFull, inside);
 
-#ifdef GSR_TMA_STAGE
-	// Staging through the TMA unit: every thread issues ONE 48-byte bulk copy (UBLKCP) for its record and arrives on the
-	// buffer's mbarrier (thread 0 also registers the expected byte count); consumers wait on the barrier's phase, which
-	// also publishes the ids written with ordinary stores -- no cp.async groups, one CTA barrier less per batch.
-	if (threadIdx.x == 0) { mbar_init(&sm.bar[0], 256); mbar_init(&sm.bar[1], 256); mbar_fence_init(); }
-	__syncthreads();
-	auto stage = [&](int b, int buf) {
-		const int i = b * 256 + threadIdx.x;
-		const int cnt_b = min(256, n - b * 256);
-		fence_proxy_async();      // earlier generic-proxy reads of this buffer are ordered before the async writes
-		if (i < n) {
-			const uint32_t id = ids_in_smem ? s_ids[i] : (FUSED_SORT ? __ldcg(point_list + range.x + i) : __ldg(point_list + range.x + i));
-			sm.id[buf][threadIdx.x] = id;
-			tma_bulk_g2s(&sm.rec[buf][threadIdx.x], rec + id, (unsigned)sizeof(GaussRec), &sm.bar[buf]);
-		}
-		if (threadIdx.x == 0) mbar_arrive_expect_tx(&sm.bar[buf], (unsigned)cnt_b * (unsigned)sizeof(GaussRec));
-		else mbar_arrive(&sm.bar[buf]);
-	};
-	if (rounds > 0) stage(0, 0);
-
-	int b = 0;
-	for (; b < rounds; b++) {
-		const int buf = b & 1;
-		if (__syncthreads_and(T < 0.f)) break;   // also: everyone is past batch b-1, buffer buf^1 is free
-		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
-		mbar_wait(&sm.bar[buf], (unsigned)((b >> 1) & 1));
-#else
 	auto stage = [&](int b, int buf) {
 		const int i = b * 256 + threadIdx.x;
 		if (i < n) {
-			// fused: ids come from shared memory; a list too long for it was written by this CTA -> coherent load
-			const uint32_t id = ids_in_smem ? s_ids[i] : (FUSED_SORT ? __ldcg(point_list + range.x + i) : __ldg(point_list + range.x + i));
+			// fused: ids of the chunk sorted last come from shared memory; older ones were written by this CTA -> coherent load
+			uint32_t id;
+			if (MODE == 2) {
+				const int j = i - lz->ids_base;
+				id = ((unsigned)j < (unsigned)lz->ids_cnt) ? s_ids[j] : __ldcg(point_list + range.x + i);
+			} else if (MODE == 1) id = ids_in_smem ? s_ids[i] : __ldcg(point_list + range.x + i);
+			else id = __ldg(point_list + range.x + i);
 			sm.id[buf][threadIdx.x] = id;
 			const GaussRec* r = rec + id;
 			cp_async16(&sm.rec[buf][threadIdx.x].q0, &r->q0);
@@ -175,68 +421,82 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		}
 		cp_async_commit();
 	};
-	if (rounds > 0) stage(0, 0);
 
-	for (int b = 0; b < rounds; b++) {
-		const int buf = b & 1;
-		if (__syncthreads_and(T < 0.f)) break;   // also: everyone is past batch b-1, buffer buf^1 is free
-		if (b + 1 < rounds) stage(b + 1, buf ^ 1);
-		else cp_async_commit();
-		cp_async_wait<1>();
-		__syncthreads();
-#endif
-		const int cnt = min(256, n - b * 256);
-		uint32_t held_mask = 0;
-		for (int c0 = 0; c0 < cnt; c0 += 32) {
-			if (__all_sync(kFull, T < 0.f)) break;
-			// cull phase: one list entry per lane
-			const int e = c0 + lane;
-			bool keep = false;
-			float4 q0, q1;
-			if (e < cnt) {
-				q0 = sm.rec[buf][e].q0;
-				q1 = sm.rec[buf][e].q1;
-				keep = may_touch(q0, q1, bx0, by0, bx1, by1);
-			}
-			const unsigned mask = __ballot_sync(kFull, keep);
-			if (lane == (c0 >> 5)) held_mask = mask;   // lane j keeps the ballot of chunk j; stored once per batch
-			if (mask == 0) continue;
-			const int nq = __popc(mask);
-			const int pos = __popc(mask & lt);
-			if (keep) {
-				const float4 q2 = sm.rec[buf][e].q2;
-				QueueRec* dst = wq + pos;
-				dst->w0 = q0;
-				dst->w1 = make_float4(q1.x, q1.y, q1.w, q2.x);
-				dst->w2 = make_float4(q2.y, q1.z, __int_as_float(b * 256 + e), __uint_as_float(sm.id[buf][e]));
-			}
-			if (lane == 0) {   // padding record for an odd survivor count: opacity 0 -> alpha 0 -> skipped
-				wq[nq].w0 = make_float4(0.f, 0.f, 0.f, 0.f);
-				wq[nq].w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-			__syncwarp();
-			if (warp_hi_T) {
-				blend_queue<true>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
-				__syncwarp();
-				if (keep) {
-					const unsigned m = wmask[pos];
-					if (m) atomicAdd(&n_touched[__float_as_uint(wq[pos].w2.w)], __popc(m));
+	int b = 0;
+	bool all_done = false;
+	for (;;) {
+		// batches of 256 positions that are completely ordered by now
+		const int sorted_end = (MODE == 2) ? lz->sorted_end : n;
+		const int b_end = (sorted_end >= n) ? rounds : (sorted_end >> 8);
+		if (b < b_end) {
+			stage(b, b & 1);
+			for (; b < b_end; b++) {
+				const int buf = b & 1;
+				if (__syncthreads_and(T < 0.f)) { all_done = true; break; }   // also: everyone is past batch b-1, buffer buf^1 is free
+				if (b + 1 < b_end) stage(b + 1, buf ^ 1);
+				else cp_async_commit();
+				cp_async_wait<1>();
+				__syncthreads();
+				const int cnt = min(256, n - b * 256);
+				uint32_t held_mask = 0;
+				for (int c0 = 0; c0 < cnt; c0 += 32) {
+					if (__all_sync(kFull, T < 0.f)) break;
+					// cull phase: one list entry per lane
+					const int e = c0 + lane;
+					bool keep = false;
+					float4 q0, q1;
+					if (e < cnt) {
+						q0 = sm.rec[buf][e].q0;
+						q1 = sm.rec[buf][e].q1;
+						keep = may_touch(q0, q1, bx0, by0, bx1, by1);
+					}
+					const unsigned mask = __ballot_sync(kFull, keep);
+					if (lane == (c0 >> 5)) held_mask = mask;   // lane j keeps the ballot of chunk j; stored once per batch
+					if (mask == 0) continue;
+					const int nq = __popc(mask);
+					const int pos = __popc(mask & lt);
+					if (keep) {
+						const float4 q2 = sm.rec[buf][e].q2;
+						QueueRec* dst = wq + pos;
+						dst->w0 = q0;
+						dst->w1 = make_float4(q1.x, q1.y, q1.w, q2.x);
+						dst->w2 = make_float4(q2.y, q1.z, __int_as_float(b * 256 + e), __uint_as_float(sm.id[buf][e]));
+					}
+					if (lane == 0) {   // padding record for an odd survivor count: opacity 0 -> alpha 0 -> skipped
+						wq[nq].w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+						wq[nq].w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+					}
+					__syncwarp();
+					if (warp_hi_T) {
+						blend_queue<true>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+						__syncwarp();
+						if (keep) {
+							const unsigned m = wmask[pos];
+							if (m) atomicAdd(&n_touched[__float_as_uint(wq[pos].w2.w)], __popc(m));
+						}
+						warp_hi_T = __any_sync(kFull, T > 0.5f);
+					} else {
+						blend_queue<false>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+					}
+					__syncwarp();   // queue fully consumed before the next chunk overwrites it
 				}
-				warp_hi_T = __any_sync(kFull, T > 0.5f);
-			} else {
-				blend_queue<false>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+				// the backward replays these ballots instead of repeating the cull (chunks this warp skipped stay 0: they lie
+				// behind its last contributor and are never read)
+				if (lane < 8 && (b * 8 + lane) * 32 < n) my_masks[(b * 8 + lane) * 8] = held_mask;   // only this tile's own groups
 			}
-			__syncwarp();   // queue fully consumed before the next chunk overwrites it
+			cp_async_wait<0>();
 		}
-		// the backward replays these ballots instead of repeating the cull (chunks this warp skipped stay 0: they lie
-		// behind its last contributor and are never read)
-		if (lane < 8 && (b * 8 + lane) * 32 < n) my_masks[(b * 8 + lane) * 8] = held_mask;   // only this tile's own groups
+		if (MODE != 2 || all_done || sorted_end >= n) break;
+		// ---- more of the list is needed: order the next depth slab (the staging buffers are idle: scratch again) ----
+		if (__syncthreads_and(T < 0.f)) break;
+		if (!lazy_sort_slab(fs.pairs + range.x, n, fs.id_bits, fs.point_list + range.x)) {
+			// a depth bin beyond the chunk length: sort the whole list the general way (same prefix) and carry on
+			sort_whole_tile(tile, fs, 0);
+			if (threadIdx.x == 0) { lz->sorted_end = n; lz->ids_cnt = 0; }
+		}
+		__threadfence_block();
+		__syncthreads();
 	}
-#ifdef GSR_TMA_STAGE
-	if (b < rounds) mbar_wait(&sm.bar[b & 1], (unsigned)((b >> 1) & 1));   // a staged batch nobody consumed: let it land before exit
-#else
-	cp_async_wait<0>();
-#endif
 	if (inside) {
 		const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
 		T = fabsf(T);
@@ -253,7 +513,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 }  // namespace
 
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
-                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, size_t R_capacity,
+                           float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
                            cudaStream_t stream)
 {
 	const int tiles = s.grid_x * s.grid_y;
@@ -263,20 +523,25 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr;
 	fs.id_bits = 1;
 	while (fs.id_bits < 32 && (1ll << fs.id_bits) < (long long)s.P) fs.id_bits++;
+	fs.lazy_min = lazy_min;
 	const size_t smem_plain = sizeof(FwdSmem);
-	const size_t smem_fused = sort_smem_bytes(kSmallChunk, 256) > (size_t)kFusedIdsOffset + kFusedIdsCap * 4
-	                              ? sort_smem_bytes(kSmallChunk, 256) : (size_t)kFusedIdsOffset + kFusedIdsCap * 4;
-	static SmemAttrCache fused_attr, plain_attr;
-	ensure_dynamic_smem(render_forward_kernel<true>, smem_fused, fused_attr);
-	ensure_dynamic_smem(render_forward_kernel<false>, smem_plain, plain_attr);
-	if (fused_sort && s.P > 0 && R_capacity > 0)
-		render_forward_kernel<true><<<tiles, 256, smem_fused, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-		                                                                im.final_T, im.n_contrib, out_color, out_depth, out_opacity,
-		                                                                n_touched, b.cull_masks, fs);
-	else
-		render_forward_kernel<false><<<tiles, 256, smem_plain, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-		                                                                 im.final_T, im.n_contrib, out_color, out_depth, out_opacity,
-		                                                                 n_touched, b.cull_masks, fs);
+	static_assert(kLazyOffset == (4 * kSmallChunk + 8 * kMaxBins + kMaxBins + 64) * 4, "LazySmem sits right behind the sort scratch");
+	static_assert(kFusedIdsOffset + kFusedIdsCap * 4 <= kLazyOffset, "sorted ids end inside the sort scratch");
+	const size_t smem_fused = (kLazyOffset + sizeof(LazySmem) + 15) / 16 * 16;
+	const size_t smem_sort = sort_smem_bytes(kSmallChunk, 256);
+	static SmemAttrCache lazy_attr, fused_attr, plain_attr;
+	ensure_dynamic_smem(render_forward_kernel<2>, smem_fused, lazy_attr);
+	ensure_dynamic_smem(render_forward_kernel<1>, smem_sort, fused_attr);
+	ensure_dynamic_smem(render_forward_kernel<0>, smem_plain, plain_attr);
+#define GSR_FWD_ARGS g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background, im.final_T, im.n_contrib, out_color, out_depth, \
+	out_opacity, n_touched, b.cull_masks, fs
+	if (fused_sort && s.P > 0 && R_capacity > 0) {
+		if (lazy_min > 0) render_forward_kernel<2><<<tiles, 256, smem_fused, stream>>>(GSR_FWD_ARGS);
+		else render_forward_kernel<1><<<tiles, 256, smem_sort, stream>>>(GSR_FWD_ARGS);
+	} else {
+		render_forward_kernel<0><<<tiles, 256, smem_plain, stream>>>(GSR_FWD_ARGS);
+	}
+#undef GSR_FWD_ARGS
 }
 
 }  // namespace gsr

@@ -232,10 +232,65 @@ __device__ __forceinline__ int plan_passes(int sigbits, int word, Field* out, in
 	return np;
 }
 
+// Sorts n >= 2 pairs that already sit in shared memory (buffer 0 of the layout below; n <= cap_smem; the per-warp counters
+// cleared if n <= NT * kSortItems; a CTA barrier behind both) into (depth, id) order and hands the ids to emit(i, id).
+// Every key k satisfies 0 <= k - kmin < 2^sig.
+// smem: keys[2][cap] | vals[2][cap] | cnt[NT/32][512] | base[512] | red[64]
+template <int NT, typename Emit>
+__device__ __forceinline__ void sort_loaded(int n, int cap_smem, uint32_t kmin, int sig, int id_bits, uint32_t* sm, Emit&& emit)
+{
+	constexpr int NW = NT / 32;
+	uint32_t* s_keys = sm;
+	uint32_t* s_vals = sm + 2 * (size_t)cap_smem;
+	uint32_t* s_cnt = sm + 4 * (size_t)cap_smem;
+	uint32_t* s_base = s_cnt + NW * kMaxBins;
+	uint32_t* s_red = s_base + kMaxBins;
+	const int tid = threadIdx.x;
+	const bool one_chunk = n <= NT * kSortItems;
+	int cur = 0;
+	// Fast path: at most two stable passes over the LEADING key bits (16 in one shared-memory chunk, 18 otherwise), then
+	// transposition sweeps settle the low bits and the id order of equal depths (adjacent by then).
+	{
+		const int digit_bits = one_chunk ? kFastDigitBits : kMaxDigitBits;
+		const int top = min(sig, 2 * digit_bits);
+		Field fp[2];
+		const int np = plan_passes(top, 0, fp, digit_bits);
+		for (int p = 0; p < np; p++) fp[p].shift += sig - top;
+		for (int p = 0; p < np; p++) {
+			uint32_t *ki = s_keys + cur * cap_smem, *vi = s_vals + cur * cap_smem;
+			uint32_t *ko = s_keys + (cur ^ 1) * cap_smem, *vo = s_vals + (cur ^ 1) * cap_smem;
+			if (!one_chunk) radix_pass<NT>(ki, vi, 1, ko, vo, 1, n, kmin, fp[p], s_cnt, s_base);
+			else if (n <= NT * 2) radix_pass_small<NT, 2>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
+			else if (n <= NT * 3) radix_pass_small<NT, 3>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
+			else if (n <= NT * 4) radix_pass_small<NT, 4>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
+			else radix_pass_small<NT, kSortItems>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
+			cur ^= 1;
+		}
+		uint32_t *K = s_keys + cur * cap_smem, *V = s_vals + cur * cap_smem;
+		if (finish_by_transposition<NT>(K, V, 1, n, 24)) {
+			for (int i = tid; i < n; i += NT) emit(i, V[i]);
+			return;
+		}
+		__syncthreads();
+	}
+	// The sweeps did not converge (masses of equal depths).  General sort from the permutation at hand: stable LSD passes,
+	// id digits first, then every differing depth bit.
+	Field depth_passes[4], id_passes[4];
+	const int nd = plan_passes(sig, 0, depth_passes);
+	const int ni = plan_passes(id_bits, 1, id_passes);
+	for (int p = 0; p < ni + nd; p++) {
+		const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
+		radix_pass<NT>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, 1, s_keys + (cur ^ 1) * cap_smem,
+		               s_vals + (cur ^ 1) * cap_smem, 1, n, kmin, f, s_cnt, s_base);
+		cur ^= 1;
+	}
+	const uint32_t* V = s_vals + cur * cap_smem;
+	for (int i = tid; i < n; i += NT) emit(i, V[i]);
+}
+
 // Sorts one segment of n >= 2 (depth bits, id) pairs: seg[0..n) (global) -> out[0..n) ids in (depth, id) order; alt is a
 // same-sized global scratch (ping-pong partner), both may be overwritten.  Segments up to cap_smem entries are sorted in
-// shared memory, longer ones by chunked passes through seg / alt.
-// smem: keys[2][cap] | vals[2][cap] | cnt[NT/32][512] | base[512] | red[64]
+// shared memory (sort_loaded), longer ones by chunked passes through seg / alt.
 template <int NT>
 __device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __restrict__ alt, uint32_t* __restrict__ out, int n,
                                              int cap_smem, int id_bits, uint32_t* sm, uint32_t* ids_out, int ids_cap)
@@ -277,78 +332,40 @@ __device__ __forceinline__ void sort_segment(uint2* __restrict__ seg, uint2* __r
 	kmin = s_red[0]; kmax = s_red[32];
 	for (int w = 1; w < NW; w++) { kmin = min(kmin, s_red[w]); kmax = max(kmax, s_red[32 + w]); }
 	const int sig = (kmax == kmin) ? 0 : 32 - __clz(kmax - kmin);
+	if (in_smem) {
+		sort_loaded<NT>(n, cap_smem, kmin, sig, id_bits, sm, emit);
+		return;
+	}
 
+	// List beyond the shared-memory capacity: two stable passes over the leading 18 key bits through the global ping-pong
+	// buffers, transposition sweeps on the global pairs; if they do not converge, the general LSD sort (id digits, then
+	// every differing depth bit) from the permutation at hand.
 	Field depth_passes[4], id_passes[4];
 	const int nd = plan_passes(sig, 0, depth_passes);
 	const int ni = plan_passes(id_bits, 1, id_passes);
-
-	// Fast path: at most two stable passes over the LEADING key bits (16 in one shared-memory chunk, 18 otherwise), then
-	// transposition sweeps settle the low bits and the id order of equal depths (adjacent by then); falls through to the
-	// general sort if they do not converge.
+	uint2* A = seg;
+	uint2* B = alt;
 	{
-		const int digit_bits = one_chunk ? kFastDigitBits : kMaxDigitBits;
-		const int top = min(sig, 2 * digit_bits);
+		const int top = min(sig, 2 * kMaxDigitBits);
 		Field fp[2];
-		const int np = plan_passes(top, 0, fp, digit_bits);
+		const int np = plan_passes(top, 0, fp, kMaxDigitBits);
 		for (int p = 0; p < np; p++) fp[p].shift += sig - top;
-		uint32_t *K, *V;
-		int stride;
-		if (in_smem) {
-			int cur = 0;
-			for (int p = 0; p < np; p++) {
-				uint32_t *ki = s_keys + cur * cap_smem, *vi = s_vals + cur * cap_smem;
-				uint32_t *ko = s_keys + (cur ^ 1) * cap_smem, *vo = s_vals + (cur ^ 1) * cap_smem;
-				if (!one_chunk) radix_pass<NT>(ki, vi, 1, ko, vo, 1, n, kmin, fp[p], s_cnt, s_base);
-				else if (n <= NT * 4) radix_pass_small<NT, 4>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
-				else radix_pass_small<NT, kSortItems>(ki, vi, ko, vo, n, kmin, fp[p], p, s_cnt, s_base, s_red);
-				cur ^= 1;
-			}
-			K = s_keys + cur * cap_smem; V = s_vals + cur * cap_smem; stride = 1;
-		} else {
-			// list beyond the shared-memory capacity: the same passes through the global ping-pong buffers.  The original
-			// order is not needed again: the general sort below starts with the id digits.
-			uint2* A = seg;
-			uint2* B = alt;
-			for (int p = 0; p < np; p++) {
-				radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, fp[p], s_cnt, s_base);
-				uint2* t = A; A = B; B = t;
-			}
-			if (A != seg) {      // keep the data in `seg` so that the general sort finds it there
-				for (int i = tid; i < n; i += NT) B[i] = A[i];
-				__syncthreads();
-				A = B;
-			}
-			K = &A->x; V = &A->y; stride = 2;
+		for (int p = 0; p < np; p++) {
+			radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, fp[p], s_cnt, s_base);
+			uint2* t = A; A = B; B = t;
 		}
-		if (finish_by_transposition<NT>(K, V, stride, n, in_smem ? 24 : 8)) {
-			for (int i = tid; i < n; i += NT) emit(i, V[(size_t)i * stride]);
+		if (finish_by_transposition<NT>(&A->x, &A->y, 2, n, 8)) {
+			for (int i = tid; i < n; i += NT) emit(i, A[i].y);
 			return;
 		}
 		__syncthreads();
 	}
-	// General sort: stable LSD passes, id digits first, then every differing depth bit.
-	if (in_smem) {
-		for (int i = tid; i < n; i += NT) { const uint2 kv = seg[i]; s_keys[i] = kv.x; s_vals[i] = kv.y; }
-		__syncthreads();
-		int cur = 0;
-		for (int p = 0; p < ni + nd; p++) {
-			const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
-			radix_pass<NT>(s_keys + cur * cap_smem, s_vals + cur * cap_smem, 1, s_keys + (cur ^ 1) * cap_smem,
-			               s_vals + (cur ^ 1) * cap_smem, 1, n, kmin, f, s_cnt, s_base);
-			cur ^= 1;
-		}
-		const uint32_t* V = s_vals + cur * cap_smem;
-		for (int i = tid; i < n; i += NT) emit(i, V[i]);
-	} else {
-		uint2* A = seg;
-		uint2* B = alt;
-		for (int p = 0; p < ni + nd; p++) {
-			const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
-			radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, f, s_cnt, s_base);
-			uint2* t = A; A = B; B = t;
-		}
-		for (int i = tid; i < n; i += NT) emit(i, A[i].y);
+	for (int p = 0; p < ni + nd; p++) {
+		const Field f = p < ni ? id_passes[p] : depth_passes[p - ni];
+		radix_pass<NT>(&A->x, &A->y, 2, &B->x, &B->y, 2, n, kmin, f, s_cnt, s_base);
+		uint2* t = A; A = B; B = t;
 	}
+	for (int i = tid; i < n; i += NT) emit(i, A[i].y);
 }
 
 

@@ -19,7 +19,7 @@ EXPORTS = (
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
-    "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter",
+    "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand",
 )
 
 
@@ -84,6 +84,7 @@ def load():
     lib.gsr_error_string.restype = C.c_char_p
     lib.gsr_kernel_launch_count.restype = C.c_ulonglong
     lib.gsr_stage_timing.argtypes = [ip]
+    lib.gsr_sort_on_demand.argtypes = [ip]
     lib.gsr_stage_times_ms.argtypes = [C.POINTER(C.c_float)]
     lib.gsr_debug_probe.argtypes = [C.POINTER(C.c_ulonglong), sz]
     lib.gsr_slam_loss_scratch_bytes.restype = sz

@@ -175,6 +175,17 @@ int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* ex
 int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long binning_capacity, void* image,
                        unsigned long long* out);
 
+/* ---- per-tile list order on demand ----
+ * The reference sorts every (tile, depth) key of a view (cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:353-358),
+ * although front-to-back compositing stops reading a tile's list once all its pixels are opaque (forward.cu:497-502) and
+ * the backward starts at the last contributor (backward.cu:763).  By default the forward here orders lists longer than
+ * a threshold only as far as they are read, depth slab by depth slab: point_list then holds the reference's list exactly
+ * up to (at least) each tile's deepest contributor and is unspecified behind it; all outputs and gradients are unchanged.
+ * min_list_length > 0: lists longer than this are ordered on demand; 0: every list is sorted completely (what the
+ * bit-exact list tests compare); < 0: query only.  Process-wide; returns the previous value.  Default 2048 = the
+ * longest list one shared-memory chunk sorts completely (environment: GSR_LAZY_MIN). */
+int gsr_sort_on_demand(int min_list_length);
+
 /* ---- measurement hooks (bench.py) ---- */
 /* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
 unsigned long long gsr_kernel_launch_count(void);

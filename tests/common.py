@@ -44,9 +44,22 @@ def settings_from_scene(sc_t):
         prefiltered=False, debug=bool(sc_t.get("debug", False)))
 
 
-def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None):
+def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, on_demand=0):
     """Run the product path through its C-ABI on `device`; returns outputs, internals and gradients
-    as numpy arrays.  sc: numpy scene dict (diff_gaussian_rasterization.scenes)."""
+    as numpy arrays.  sc: numpy scene dict (diff_gaussian_rasterization.scenes).
+    on_demand: gsr_sort_on_demand threshold for this call -- 0 (default here): every per-tile list is sorted completely,
+    so that the WHOLE point_list can be compared; > 0: lists longer than this are ordered only as far as they are read
+    (the library default is 1024)."""
+    import diff_gaussian_rasterization as dgr
+
+    prev = dgr._L.gsr_sort_on_demand(int(on_demand))
+    try:
+        return _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity)
+    finally:
+        dgr._L.gsr_sort_on_demand(prev)
+
+
+def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity):
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization import scenes as S
 
