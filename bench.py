@@ -143,8 +143,24 @@ def roofline_bytes(P, R, HW, fused_sort=False, fused_scatter=False):
     }
 
 
+def on_demand_min():
+    from diff_gaussian_rasterization import _cabi
+    return 0 if os.environ.get("GSR_NO_FUSED_SORT") else int(_cabi.load().gsr_sort_on_demand(-1))
+
+
 def fused_sort_active(eng):
-    return 0 < eng.max_tile_hint <= 2048 and not os.environ.get("GSR_NO_FUSED_SORT")
+    """the forward compositing kernel orders its own tile: on demand (lists above the threshold) or completely"""
+    if os.environ.get("GSR_NO_FUSED_SORT"):
+        return False
+    return eng.max_tile_hint > on_demand_min() > 0 or 0 < eng.max_tile_hint <= 2048
+
+
+def sort_path(eng):
+    if not fused_sort_active(eng):
+        return "in its own kernels"
+    if eng.max_tile_hint > on_demand_min() > 0:
+        return "inside the forward compositing kernel, on demand (depth slab by depth slab, lists > %d entries)" % on_demand_min()
+    return "fused into the forward compositing kernel"
 
 
 def peaks():
@@ -336,7 +352,7 @@ def run_ours(args, rank, world, device):
                    "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
                    "parallelism": "pose-parallel x%d (one independent tracking stream per GPU, no collective)" % world,
                    "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d; per-tile sort %s"
-                           % (eng.capacity, "fused into the forward compositing kernel" if fused_sort_active(eng) else "in its own kernels")},
+                           % (eng.capacity, sort_path(eng))},
         "e2e": {"value": world * K / emax, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3,
                 "what": "RasterEngine.step_host: one graph with pinned pose block + pinned dL/dcolor,dL/ddepth H2D, forward, backward, dL/dtau + header D2H; host sync every step"},
@@ -506,7 +522,8 @@ def run_window(args, rank, world, device):
                    "views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view,
                    "collective": ("all_reduce(sum) of %d B of packed per-Gaussian gradients per step" % grad_bytes) if reduce else "none",
                    "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
-                   "parallelism": "keyframe-parallel x%d, %d engine(s) / stream(s) per GPU" % (world, len(win.engines))},
+                   "parallelism": "keyframe-parallel x%d, %d engine(s) / stream(s) per GPU" % (world, len(win.engines)),
+                   "path": "KeyframeWindow over RasterEngine(s), no host sync; per-tile lists ordered " + sort_path(eng)},
         "e2e": {"value": K / emax, "unit": "window iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3},
         "gpu_launches": launches_per_step * K,

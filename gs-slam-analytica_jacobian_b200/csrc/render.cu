@@ -81,13 +81,14 @@ __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int 
 // ON-DEMAND ORDER (lists above lazy_min entries): front-to-back compositing stops once every pixel of the tile is opaque,
 // typically after a few hundred entries, however long the list is (measured: 37 % of the list at 640x480 / 100 k
 // Gaussians, 13 % at 1200x680 / 500 k, 2 % at 1920x1080 / 3 M).  So the CTA does not sort the list; it SELECTS: a
-// 256-bin histogram over the leading bits of the tile's depth-key range gives, for any bin boundary, the exact list
+// 1024-bin histogram over the leading bits of the tile's depth-key range gives, for any bin boundary, the exact list
 // position where that depth slab starts; the entries of the first slab (the fewest bins holding >= kLazyTarget entries)
-// are compacted into shared memory, sorted there into (depth, id) order -- they are exactly the first entries of the
-// reference's list, at the reference's positions -- written to point_list and composited; only if pixels are still open
-// is the next slab selected and sorted.  Positions behind the tile's deepest contributor are never read by the forward
-// or the backward (backward.cu:763), and point_list holds the exact list up to there.  A slab that cannot be sorted in
-// shared memory (one bin above the chunk length) makes the CTA sort the whole list the general way and carry on.
+// are placed bin by bin in shared memory (the bin offsets are known: one MSD step) and every entry is ranked against the
+// handful of entries of its own bin on (depth, id) -- barrier-free and exact; rank + bin offset is the entry's position in
+// the reference's list.  The ids go to point_list and are composited; only if pixels are still open is the next slab
+// selected and ordered.  Positions behind the tile's deepest contributor are never read by the forward or the backward
+// (backward.cu:763), and point_list holds the exact list up to there.  A slab that cannot be ordered this way (a bin above
+// kRankMax entries: masses of equal depths) makes the CTA sort the whole list the general way and carry on.
 struct FusedSortArgs {
 	uint2* ranges;
 	uint2* pairs;
@@ -100,14 +101,15 @@ struct FusedSortArgs {
 };
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
 constexpr int kFusedIdsCap = GSR_SORT_CHUNK;
-constexpr int kLazyBins = 256;            // one thread per bin
+constexpr int kLazyBins = 1024;           // depth bins over the tile's key range: four per thread
 constexpr int kLazyTarget = 512;          // entries a slab should hold at least: two compositing batches
+constexpr int kRankMax = 256;             // longest depth bin ordered by all-pairs ranking
 struct LazySmem {                         // lives behind the sort scratch: survives sorts and compositing
 	uint32_t excl[kLazyBins + 1];         // list position at which bin b starts
 	uint32_t wsum[8];
 	uint32_t red[16];
 	uint32_t b_hi;
-	uint32_t count;
+	uint32_t big;                         // the slab holds a bin above kRankMax entries
 	// CTA-uniform list state, kept here rather than in registers of the compositing loop
 	uint32_t kmin;                        // smallest depth key of the tile
 	int shift;                            // bin = (key - kmin) >> shift
@@ -117,28 +119,72 @@ struct LazySmem {                         // lives behind the sort scratch: surv
 };
 
 constexpr int kLazyOffset = 51456;        // bytes: behind the sort scratch of one 2048-entry chunk (sort_smem_bytes)
+constexpr int kLazyCursorOffset = 32768;  // bytes: per-bin placement cursors of the slab being built (scratch, inside the overlay)
 
-// The helpers below are deliberately NOT inlined: they run once per slab, need the register file for themselves (8 keys
-// per thread in flight) and must not raise the register pressure of the compositing loop around them.  They find the
-// shared-memory carve-up themselves (a pointer parameter would turn every LDS/STS into a generic access).
-//
-// min / max of the segment's depth keys, 256-bin histogram over the leading bits of their range, exclusive scan:
-// lz->excl[b] = list position at which depth bin b starts; then the first slab is selected and sorted (see
-// lazy_sort_slab).  Lists of up to kLazyRegs * 256 entries are read from global memory ONCE and held in registers for the
-// three sweeps (range, histogram, selection); longer ones are re-read (L2).  All 256 threads.
+// The helpers below are deliberately NOT inlined: they run once per slab, need the register file for themselves and must
+// not raise the register pressure of the compositing loop around them.  They find the shared-memory carve-up themselves (a
+// pointer parameter would turn every LDS/STS into a generic access).
+
+// The slab that starts at bin b_lo / list position base: up to the first bin boundary with at least kLazyTarget entries in
+// front of it (excl is non-decreasing), one bin less if that overshoots a shared-memory chunk.  Needs lz->b_hi == kLazyBins
+// and lz->big == 0 on entry (behind a barrier); one barrier inside, lz->big is valid behind the caller's next one.
+__device__ __forceinline__ void lazy_choose_slab(LazySmem* lz, int b_lo, uint32_t base, int& b_hi, int& m)
+{
+	uint32_t e[5];
+#pragma unroll
+	for (int u = 0; u < 5; u++) e[u] = lz->excl[4 * threadIdx.x + u];
+#pragma unroll
+	for (int u = 1; u < 5; u++) {
+		const int j = 4 * (int)threadIdx.x + u;
+		if (j > b_lo && e[u] - base >= (uint32_t)kLazyTarget && e[u - 1] - base < (uint32_t)kLazyTarget) lz->b_hi = (uint32_t)j;
+	}
+	__syncthreads();
+	b_hi = (int)lz->b_hi;
+	m = (int)(lz->excl[b_hi] - base);
+	if (m > kSmallChunk && b_hi - 1 > b_lo && lz->excl[b_hi - 1] - base > 0) { b_hi--; m = (int)(lz->excl[b_hi] - base); }
+#pragma unroll
+	for (int u = 1; u < 5; u++) {
+		const int j = 4 * (int)threadIdx.x + u;
+		if (j > b_lo && j <= b_hi && e[u] - e[u - 1] > (uint32_t)kRankMax) lz->big = 1;
+	}
+}
+
+// Orders a slab whose m entries sit in s_keys / s_vals grouped by depth bin (bin b at [excl[b] - base, excl[b + 1] - base),
+// unordered inside): every thread ranks its entries against the other entries of their bin on (depth, id) -- exact, no
+// barriers, bins hold a handful of entries.  The rank is the final list position: ids -> out (global) and s_ids.
+__device__ __forceinline__ void rank_sort_bins(const LazySmem* lz, int m, uint32_t base, uint32_t kmin, int shift,
+                                               const uint32_t* s_keys, const uint32_t* s_vals, uint32_t* __restrict__ out,
+                                               uint32_t* s_ids)
+{
+	for (int p = threadIdx.x; p < m; p += 256) {
+		const uint32_t k = s_keys[p], v = s_vals[p];
+		const uint32_t bin = (k - kmin) >> shift;
+		const uint32_t s0 = lz->excl[bin] - base, s1 = lz->excl[bin + 1] - base;
+		uint32_t rank = s0;
+		for (uint32_t j = s0; j < s1; j++) {
+			const uint32_t kj = s_keys[j], vj = s_vals[j];
+			rank += (kj < k || (kj == k && vj < v)) ? 1u : 0u;
+		}
+		out[rank] = v;
+		s_ids[rank] = v;
+	}
+}
+
+// First visit of a list: min / max of its depth keys, 1024-bin histogram over the leading bits of their range, exclusive
+// scan (lz->excl[b] = list position at which depth bin b starts); then the first slab is selected, placed bin by bin and
+// ordered.  Lists of up to kLazyRegs * 256 entries are read from global memory ONCE and held in registers for the three
+// sweeps (range, histogram, placement); longer ones are re-read (L2).  Returns false when the slab cannot be ordered this
+// way (a bin above kRankMax entries: masses of equal depths).  All 256 threads.
 constexpr int kLazyRegs = 16;
-__device__ __forceinline__ void lazy_choose_slab(LazySmem* lz, int b_lo, uint32_t base, int& b_hi, int& m);
-__device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, int id_bits, uint32_t* __restrict__ list)
+__device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, uint32_t* __restrict__ list)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint32_t* sm_u32 = reinterpret_cast<uint32_t*>(smem_raw);
+	uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem_raw);
+	uint32_t* s_vals = s_keys + 2 * kSmallChunk;
+	uint32_t* s_cursor = reinterpret_cast<uint32_t*>(smem_raw + kLazyCursorOffset);
 	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset);
 	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
-	uint32_t* s_keys = sm_u32;
-	uint32_t* s_vals = sm_u32 + 2 * kSmallChunk;
-	uint32_t* s_cnt = sm_u32 + 4 * kSmallChunk;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const unsigned lt = (1u << lane) - 1u;
 	const bool in_regs = n <= kLazyRegs * 256;
 	uint2 kv[kLazyRegs];
 	uint32_t kmin = 0xffffffffu, kmax = 0;
@@ -168,16 +214,15 @@ __device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, int id_bit
 		kmax = max(kmax, __shfl_xor_sync(kFull, kmax, o));
 	}
 	if (lane == 0) { lz->red[warp] = kmin; lz->red[8 + warp] = kmax; }
-	lz->excl[tid] = 0;
-	if (tid == 0) { lz->b_hi = kLazyBins; lz->count = 0; }
-	// the per-warp digit counters of the slab sort, cleared once for both of its passes
-	for (int i = tid; i < 8 * kMaxBins / 4; i += 256) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+	reinterpret_cast<uint4*>(lz->excl)[tid] = make_uint4(0, 0, 0, 0);
+	reinterpret_cast<uint4*>(s_cursor)[tid] = make_uint4(0, 0, 0, 0);
+	if (tid == 0) { lz->b_hi = kLazyBins; lz->big = 0; }
 	__syncthreads();
 	kmin = lz->red[0]; kmax = lz->red[8];
 #pragma unroll
 	for (int w = 1; w < 8; w++) { kmin = min(kmin, lz->red[w]); kmax = max(kmax, lz->red[8 + w]); }
 	const int sig = (kmax == kmin) ? 0 : 32 - __clz(kmax - kmin);
-	const int shift = max(0, sig - 8);
+	const int shift = max(0, sig - 10);
 	if (in_regs) {
 #pragma unroll
 		for (int u = 0; u < kLazyRegs; u++)
@@ -194,42 +239,42 @@ __device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, int id_bit
 		for (; i < n; i += 256) atomicAdd(&lz->excl[(__ldcg(&seg[i].x) - kmin) >> shift], 1u);
 	}
 	__syncthreads();
-	const uint32_t c = lz->excl[tid];
-	uint32_t incl = c;
+	{   // exclusive scan of the bin counts: four consecutive bins per thread
+		const uint4 c = reinterpret_cast<uint4*>(lz->excl)[tid];
+		const uint32_t sum = c.x + c.y + c.z + c.w;
+		uint32_t incl = sum;
 #pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		const uint32_t t = __shfl_up_sync(kFull, incl, o);
-		if (lane >= o) incl += t;
-	}
-	if (lane == 31) lz->wsum[warp] = incl;
-	__syncthreads();
-	uint32_t before = 0;
-	for (int w = 0; w < warp; w++) before += lz->wsum[w];
-	lz->excl[tid] = before + incl - c;
-	if (tid == kLazyBins - 1) lz->excl[kLazyBins] = before + incl;
-	if (tid == 0) {
-		lz->kmin = kmin; lz->shift = shift; lz->b_lo = 0;
-		lz->sorted_end = 0; lz->ids_base = 0; lz->ids_cnt = 0;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t t = __shfl_up_sync(kFull, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) lz->wsum[warp] = incl;
+		__syncthreads();
+		uint32_t before = incl - sum;
+		for (int w = 0; w < warp; w++) before += lz->wsum[w];
+		reinterpret_cast<uint4*>(lz->excl)[tid] = make_uint4(before, before + c.x, before + c.x + c.y, before + c.x + c.y + c.z);
+		if (tid == 255) lz->excl[kLazyBins] = before + sum;
+		if (tid == 0) {
+			lz->kmin = kmin; lz->shift = shift; lz->b_lo = 0;
+			lz->sorted_end = 0; lz->ids_base = 0; lz->ids_cnt = 0;
+		}
 	}
 	__syncthreads();
 	// ---- first slab ----
 	int b_hi, m;
 	lazy_choose_slab(lz, 0, 0u, b_hi, m);
-	if (m > kSmallChunk) return false;
+	__syncthreads();
+	if (m > kSmallChunk || lz->big) return false;
 	const uint32_t width = (uint32_t)b_hi;
-	auto place = [&](bool pred, uint2 e) {
-		const unsigned mask = __ballot_sync(kFull, pred);
-		if (mask) {
-			uint32_t pos = 0;
-			if (lane == __ffs(mask) - 1) pos = atomicAdd(&lz->count, (uint32_t)__popc(mask));
-			pos = __shfl_sync(kFull, pos, __ffs(mask) - 1) + __popc(mask & lt);
-			if (pred) { s_keys[pos] = e.x; s_vals[pos] = e.y; }
-		}
-	};
 	if (in_regs) {
 #pragma unroll
-		for (int u = 0; u < kLazyRegs; u++)
-			if (u * 256 < n) place(u * 256 + tid < n && ((kv[u].x - kmin) >> shift) < width, kv[u]);
+		for (int u = 0; u < kLazyRegs; u++) {
+			const uint32_t bin = (kv[u].x - kmin) >> shift;
+			if (u * 256 + tid < n && bin < width) {
+				const uint32_t pos = lz->excl[bin] + atomicAdd(&s_cursor[bin], 1u);
+				s_keys[pos] = kv[u].x; s_vals[pos] = kv[u].y;
+			}
+		}
 	} else {
 		for (int i0 = 0; i0 < n; i0 += 4 * 256) {
 			uint2 e[4];
@@ -239,83 +284,62 @@ __device__ __noinline__ bool lazy_first_slab(const uint2* seg, int n, int id_bit
 				e[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
 			}
 #pragma unroll
-			for (int u = 0; u < 4; u++) place(i0 + u * 256 + tid < n && ((e[u].x - kmin) >> shift) < width, e[u]);
-		}
-	}
-	__syncthreads();
-	const unsigned long long span = (unsigned long long)width << shift;
-	const int sig_slab = span <= 1 ? 0 : 64 - __clzll((long long)(span - 1));
-	sort_loaded<256>(m, kSmallChunk, kmin, sig_slab, id_bits, sm_u32, [&](int i, uint32_t v) { list[i] = v; s_ids[i] = v; });
-	if (tid == 0) { lz->b_lo = b_hi; lz->ids_base = 0; lz->ids_cnt = m; lz->sorted_end = m; }
-	return true;
-}
-
-// The slab that starts at bin b_lo / list position base: up to the first bin boundary with at least kLazyTarget entries in
-// front of it (excl is non-decreasing), one bin less if that overshoots a shared-memory chunk.  Needs lz->b_hi == kLazyBins
-// on entry (behind a barrier); two barriers inside.
-__device__ __forceinline__ void lazy_choose_slab(LazySmem* lz, int b_lo, uint32_t base, int& b_hi, int& m)
-{
-	const int j = threadIdx.x + 1;
-	if (j > b_lo) {
-		const uint32_t c = lz->excl[j] - base, cprev = lz->excl[j - 1] - base;
-		if (c >= (uint32_t)kLazyTarget && cprev < (uint32_t)kLazyTarget) lz->b_hi = (uint32_t)j;
-	}
-	__syncthreads();
-	b_hi = (int)lz->b_hi;
-	m = (int)(lz->excl[b_hi] - base);
-	if (m > kSmallChunk && b_hi - 1 > b_lo && lz->excl[b_hi - 1] - base > 0) { b_hi--; m = (int)(lz->excl[b_hi] - base); }
-}
-
-// Selects the next depth slab (bins [b_lo, b_hi), starting at list position sorted_end), compacts its entries into the
-// sort scratch and sorts them: ids -> list[sorted_end ...) (global) and s_ids.  Advances the list state in LazySmem and
-// returns true; returns false when the slab does not fit one shared-memory chunk (nothing written).  All 256 threads.
-__device__ __noinline__ bool lazy_sort_slab(const uint2* seg, int n, int id_bits, uint32_t* __restrict__ list)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint32_t* sm_u32 = reinterpret_cast<uint32_t*>(smem_raw);
-	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset);
-	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
-	const int tid = threadIdx.x, lane = tid & 31;
-	const unsigned lt = (1u << lane) - 1u;
-	uint32_t* s_keys = sm_u32;
-	uint32_t* s_vals = sm_u32 + 2 * kSmallChunk;
-	uint32_t* s_cnt = sm_u32 + 4 * kSmallChunk;
-	const int b_lo = lz->b_lo, shift = lz->shift;
-	const uint32_t base = (uint32_t)lz->sorted_end, kmin = lz->kmin;
-	__syncthreads();      // everyone holds the state before thread 0 touches the fields next to it
-	if (tid == 0) { lz->b_hi = kLazyBins; lz->count = 0; lz->ids_cnt = 0; }
-	for (int i = tid; i < 8 * kMaxBins / 4; i += 256) reinterpret_cast<uint4*>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
-	__syncthreads();
-	int b_hi, m;
-	lazy_choose_slab(lz, b_lo, base, b_hi, m);
-	if (m > kSmallChunk) return false;
-	const uint32_t lo = (uint32_t)b_lo, width = (uint32_t)(b_hi - b_lo);
-	for (int i0 = 0; i0 < n; i0 += 4 * 256) {
-		uint2 kv[4];
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const int i = i0 + u * 256 + tid;
-			kv[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
-		}
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const int i = i0 + u * 256 + tid;
-			const bool pred = i < n && (((kv[u].x - kmin) >> shift) - lo) < width;
-			const unsigned mask = __ballot_sync(kFull, pred);
-			if (mask) {
-				uint32_t pos = 0;
-				if (lane == __ffs(mask) - 1) pos = atomicAdd(&lz->count, (uint32_t)__popc(mask));
-				pos = __shfl_sync(kFull, pos, __ffs(mask) - 1) + __popc(mask & lt);
-				if (pred) { s_keys[pos] = kv[u].x; s_vals[pos] = kv[u].y; }
+			for (int u = 0; u < 4; u++) {
+				const uint32_t bin = (e[u].x - kmin) >> shift;
+				if (i0 + u * 256 + tid < n && bin < width) {
+					const uint32_t pos = lz->excl[bin] + atomicAdd(&s_cursor[bin], 1u);
+					s_keys[pos] = e[u].x; s_vals[pos] = e[u].y;
+				}
 			}
 		}
 	}
 	__syncthreads();
-	const uint32_t kmin_slab = kmin + (lo << shift);
-	const unsigned long long span = (unsigned long long)width << shift;
-	const int sig_slab = span <= 1 ? 0 : 64 - __clzll((long long)(span - 1));
-	uint32_t* out = list + base;
-	sort_loaded<256>(m, kSmallChunk, kmin_slab, sig_slab, id_bits, sm_u32, [&](int i, uint32_t v) { out[i] = v; s_ids[i] = v; });
+	rank_sort_bins(lz, m, 0u, kmin, shift, s_keys, s_vals, list, s_ids);
+	if (tid == 0) { lz->b_lo = b_hi; lz->ids_base = 0; lz->ids_cnt = m; lz->sorted_end = m; }
+	return true;
+}
+
+// Later visits: selects the next depth slab (bins [b_lo, b_hi), starting at list position sorted_end), places its entries
+// bin by bin in the scratch and orders them: ids -> list[sorted_end ...) (global) and s_ids.  Advances the list state in
+// LazySmem and returns true; false when the slab cannot be ordered this way (nothing written).  All 256 threads.
+__device__ __noinline__ bool lazy_next_slab(const uint2* seg, int n, uint32_t* __restrict__ list)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem_raw);
+	uint32_t* s_vals = s_keys + 2 * kSmallChunk;
+	uint32_t* s_cursor = reinterpret_cast<uint32_t*>(smem_raw + kLazyCursorOffset);
+	uint32_t* s_ids = reinterpret_cast<uint32_t*>(smem_raw + kFusedIdsOffset);
+	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
+	const int tid = threadIdx.x;
+	const int b_lo = lz->b_lo, shift = lz->shift;
+	const uint32_t base = (uint32_t)lz->sorted_end, kmin = lz->kmin;
+	__syncthreads();      // everyone holds the state before thread 0 touches the fields next to it
+	if (tid == 0) { lz->b_hi = kLazyBins; lz->big = 0; lz->ids_cnt = 0; }
+	reinterpret_cast<uint4*>(s_cursor)[tid] = make_uint4(0, 0, 0, 0);
+	__syncthreads();
+	int b_hi, m;
+	lazy_choose_slab(lz, b_lo, base, b_hi, m);
+	__syncthreads();
+	if (m > kSmallChunk || lz->big) return false;
+	const uint32_t lo = (uint32_t)b_lo, width = (uint32_t)(b_hi - b_lo);
+	for (int i0 = 0; i0 < n; i0 += 4 * 256) {
+		uint2 e[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int i = i0 + u * 256 + tid;
+			e[u] = (i < n) ? __ldcg(&seg[i]) : make_uint2(0xffffffffu, 0u);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const uint32_t bin = (e[u].x - kmin) >> shift;
+			if (i0 + u * 256 + tid < n && bin - lo < width) {
+				const uint32_t pos = lz->excl[bin] - base + atomicAdd(&s_cursor[bin], 1u);
+				s_keys[pos] = e[u].x; s_vals[pos] = e[u].y;
+			}
+		}
+	}
+	__syncthreads();
+	rank_sort_bins(lz, m, base, kmin, shift, s_keys, s_vals, list + base, s_ids);
 	if (tid == 0) { lz->b_lo = b_hi; lz->ids_base = (int)base; lz->ids_cnt = m; lz->sorted_end = (int)base + m; }
 	return true;
 }
@@ -347,6 +371,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	const int tile = blockIdx.x;
 
 	constexpr bool FUSED_SORT = MODE != 0;
+	GSR_PROBE(3, 0);
 	// ---- the tile's list: complete, or ordered on demand (positions < lz->sorted_end are final) ----
 	uint2 range;
 	int n;
@@ -354,7 +379,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		range = fs.ranges[tile];
 		n = (int)(range.y - range.x);
 		if (range.y <= fs.capacity && n > fs.lazy_min) {
-			if (!lazy_first_slab(fs.pairs + range.x, n, fs.id_bits, fs.point_list + range.x)) {
+			if (!lazy_first_slab(fs.pairs + range.x, n, fs.point_list + range.x)) {
 				// the first depth bin alone is beyond the chunk length: sort the whole list the general way
 				sort_whole_tile(tile, fs, 0);
 				if (threadIdx.x == 0) { lz->sorted_end = n; lz->ids_cnt = 0; }
@@ -382,6 +407,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		n = (int)(range.y - range.x);
 	}
 	const bool ids_in_smem = MODE == 1 && n <= kFusedIdsCap;
+	GSR_PROBE(3, 1);
 
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -486,17 +512,20 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 			}
 			cp_async_wait<0>();
 		}
+		GSR_PROBE(3, 2);
 		if (MODE != 2 || all_done || sorted_end >= n) break;
 		// ---- more of the list is needed: order the next depth slab (the staging buffers are idle: scratch again) ----
 		if (__syncthreads_and(T < 0.f)) break;
-		if (!lazy_sort_slab(fs.pairs + range.x, n, fs.id_bits, fs.point_list + range.x)) {
+		if (!lazy_next_slab(fs.pairs + range.x, n, fs.point_list + range.x)) {
 			// a depth bin beyond the chunk length: sort the whole list the general way (same prefix) and carry on
 			sort_whole_tile(tile, fs, 0);
 			if (threadIdx.x == 0) { lz->sorted_end = n; lz->ids_cnt = 0; }
 		}
 		__threadfence_block();
 		__syncthreads();
+		GSR_PROBE(3, 3);
 	}
+	GSR_PROBE(3, 4);
 	if (inside) {
 		const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
 		T = fabsf(T);
@@ -543,5 +572,7 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	}
 #undef GSR_FWD_ARGS
 }
+
+GSR_PROBE_READER(probe_read_render)
 
 }  // namespace gsr

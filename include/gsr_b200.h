@@ -182,8 +182,8 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
  * a threshold only as far as they are read, depth slab by depth slab: point_list then holds the reference's list exactly
  * up to (at least) each tile's deepest contributor and is unspecified behind it; all outputs and gradients are unchanged.
  * min_list_length > 0: lists longer than this are ordered on demand; 0: every list is sorted completely (what the
- * bit-exact list tests compare); < 0: query only.  Process-wide; returns the previous value.  Default 2048 = the
- * longest list one shared-memory chunk sorts completely (environment: GSR_LAZY_MIN). */
+ * bit-exact list tests compare); < 0: query only.  Process-wide; returns the previous value.  Default 256
+ * (environment: GSR_LAZY_MIN). */
 int gsr_sort_on_demand(int min_list_length);
 
 /* ---- measurement hooks (bench.py) ---- */
@@ -193,7 +193,7 @@ unsigned long long gsr_kernel_launch_count(void);
  * forward+backward: {preprocess, binning, render_forward, render_backward, preprocess_backward} */
 int gsr_stage_timing(int enable);
 int gsr_stage_times_ms(float* out5);
-/* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3][4096][8] %globaltimer table
+/* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3 or 4][4096][8] %globaltimer table
  * (kernel, CTA, phase) to the host; returns an error in the product build, which carries no probes */
 int gsr_debug_probe(unsigned long long* out, size_t bytes);
 

@@ -32,10 +32,11 @@ for _ in range(5):
     eng.step()
 torch.cuda.synchronize()
 L = _cabi.load()
-buf = np.zeros((3, 4096, 8), np.uint64)
+buf = np.zeros((4, 4096, 8), np.uint64)
 _cabi.check(L.gsr_debug_probe(buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.nbytes), "probe")
-nblk = min(4096, (cfg["P"] + 255) // 256)
-for k, (kname, nph) in enumerate((("preprocess_forward", 7), ("scatter", 5), ("preprocess_backward", 4))):
+tiles = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
+for k, (kname, nph) in enumerate((("preprocess_forward", 7), ("scatter", 5), ("preprocess_backward", 4), ("render_forward", 5))):
+    nblk = min(4096, tiles if k == 3 else (cfg["P"] + 255) // 256)
     tb = buf[k, :nblk, :nph].astype(np.int64)
     t0 = tb[:, 0].min()
     print("== %s: %d CTAs; columns = phase boundary, rows = min / median / max over CTAs [us since first CTA start]" % (kname, nblk))
@@ -44,3 +45,33 @@ for k, (kname, nph) in enumerate((("preprocess_forward", 7), ("scatter", 5), ("p
         col = col[col > 0] - t0
         if col.size:
             print("   phase %d: n=%4d  min %7.2f  med %7.2f  max %7.2f" % (ph, col.size, col.min() / 1e3, np.median(col) / 1e3, col.max() / 1e3))
+
+# render forward: per-CTA durations of its phases (0 start, 1 list ready [sort / first slab], 2 end of the first run of
+# batches, 3 a further slab ordered, 4 compositing finished)
+tb = buf[3, :min(4096, tiles), :5].astype(np.int64)
+ok = tb[:, 0] > 0
+d01 = (tb[ok, 1] - tb[ok, 0]) / 1e3
+d12 = (tb[ok, 2] - tb[ok, 1]) / 1e3
+d04 = (tb[ok, 4] - tb[ok, 0]) / 1e3
+more = (tb[ok, 3] > tb[ok, 0]).mean()
+print("render_forward per CTA [us]: list ready med %.2f p90 %.2f | first run of batches med %.2f p90 %.2f | whole CTA med %.2f p90 %.2f | CTAs that ordered a further slab: %.1f %%"
+      % (np.median(d01), np.percentile(d01, 90), np.median(d12), np.percentile(d12, 90), np.median(d04), np.percentile(d04, 90), 100 * more))
+
+# scheduling headroom of the compositing kernel: greedy list scheduling of the measured CTA durations on the resident slots
+import heapq
+
+
+def makespan(durs, slots):
+    h = [0.0] * slots
+    heapq.heapify(h)
+    for d in durs:
+        t = heapq.heappop(h)
+        heapq.heappush(h, t + d)
+    return max(h)
+
+
+dur = d04
+slots = 148 * 4
+print("render_forward scheduling: %d CTAs, sum/slots = %.1f us, max CTA %.1f us, makespan in launch order %.1f us, longest first %.1f us, measured span %.1f us"
+      % (dur.size, dur.sum() / slots, dur.max(), makespan(list(dur), slots), makespan(sorted(dur, reverse=True), slots),
+         (tb[ok, 4].max() - tb[ok, 0].min()) / 1e3))
