@@ -22,6 +22,7 @@ std::atomic<unsigned long long> g_launches{0};   // kernels launched by this lib
 // optional stage timing (bench.py roofline): CUDA events recorded on the launching stream between stages
 bool g_timing = false;
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
+const bool g_no_pdl = getenv("GSR_NO_PDL") != nullptr;                 // A/B switch: no programmatic dependent launches
 // lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
 // is sorted completely
 std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
@@ -91,6 +92,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.prefiltered = a->prefiltered;
 	s.accumulate_grads = a->accumulate_grads;
 	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
+	s.overlap_forward = a->overlap_forward;
 	return GSR_OK;
 }
 
@@ -273,13 +275,14 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
 	stage_mark(4, st);
-	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, st);
+	// (with stage timing the event record sits between the two kernels: plain ordering)
+	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, s.overlap_forward != 0 && !g_timing && !a->debug && !g_no_pdl, st);
 	stage_mark(5, st);
 	g_launches += 2;
 	rc = debug_sync(a, st, "render backward");
 	if (rc) return rc;
 	gsr::launch_preprocess_backward(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
-	                                dL_drotations, dL_dcov3D, dL_dtau, st);
+	                                dL_drotations, dL_dcov3D, dL_dtau, !g_timing && !a->debug && !g_no_pdl, st);
 	stage_mark(6, st);
 	return debug_sync(a, st, "preprocess backward");
 }

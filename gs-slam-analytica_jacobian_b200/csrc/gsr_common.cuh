@@ -56,6 +56,8 @@ struct GeomView {
 	GeomHeader* hdr;
 	uint32_t* tile_count;    // [tiles]  instances per tile (integer REDs in the preprocess); zeroed with the header
 	uint32_t* tile_cursor;   // [tiles]  write cursor of the scatter pass (starts at ranges[tile].x)
+	uint32_t* tile_done;     // [tiles]  1 once the forward compositing CTA of the tile has published its results (cleared with the
+	                         //          header): lets a backward launched as a programmatic dependent start tile by tile
 	uint2* ranges;           // [tiles]  (start, end) of every tile's list inside point_list
 	uint32_t* long_tiles;    // [tiles]  ids of the tiles whose lists go to the long-list sort kernel
 	GaussRec* rec;           // [P]
@@ -68,7 +70,7 @@ struct GeomView {
 __host__ __device__ inline size_t geom_bytes(size_t P, size_t tiles)
 {
 	size_t s = sizeof(GeomHeader);
-	s += align_up(tiles * 4) * 3 + align_up(tiles * 8);
+	s += align_up(tiles * 4) * 4 + align_up(tiles * 8);
 	s += align_up(P * sizeof(GaussRec));
 	s += align_up(P * sizeof(GaussAcc));
 	s += align_up(P * 4);
@@ -84,6 +86,7 @@ __host__ __device__ inline GeomView geom_view(void* base, size_t P, size_t tiles
 	g.hdr = (GeomHeader*)p; p += sizeof(GeomHeader);
 	g.tile_count = (uint32_t*)p; p += align_up(tiles * 4);      // directly behind the header: one memset clears both
 	g.tile_cursor = (uint32_t*)p; p += align_up(tiles * 4);
+	g.tile_done = (uint32_t*)p; p += align_up(tiles * 4);
 	g.ranges = (uint2*)p; p += align_up(tiles * 8);
 	g.long_tiles = (uint32_t*)p; p += align_up(tiles * 4);
 	g.rec = (GaussRec*)p; p += align_up(P * sizeof(GaussRec));
@@ -236,6 +239,22 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
 	             : "memory");
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// once every CTA of its predecessor has executed launch_dependents (or exited); grid_dependency_wait blocks until the
+// predecessor has completed and its memory is visible.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // cp.async 16-byte global->shared (LDGSTS), used to stage gathered Gaussian records

@@ -22,6 +22,7 @@ struct Scene {
 	int grid_x, grid_y;
 	int prefiltered;
 	int accumulate_grads;
+	int overlap_forward;          // backward: launch the compositing backward as programmatic dependent of the forward before it
 	float* densify_grad_accum;    // [P] or null
 	float* densify_denom;         // [P] or null
 	float* max_radii2D;           // [P] or null
@@ -76,11 +77,11 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
                            float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
                            cudaStream_t stream);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
-                            const float* dL_dpix, const float* dL_dpix_depth, cudaStream_t stream);
+                            const float* dL_dpix, const float* dL_dpix_depth, bool overlap_forward, cudaStream_t stream);
 void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,
                                 float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
                                 float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dtau,
-                                cudaStream_t stream);
+                                bool behind_render_backward, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present, cudaStream_t stream);
 
 }  // namespace gsr

@@ -436,8 +436,8 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
                                const BinView* bin, size_t R_capacity)
 {
 	const int tiles = s.grid_x * s.grid_y;
-	// header, the per-tile counters and the claim cursors behind it are cleared together
-	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader) + 2 * align_up((size_t)tiles * sizeof(uint32_t)), stream);
+	// header, the per-tile counters, the claim cursors and the tile-done flags behind it are cleared together
+	cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader) + 3 * align_up((size_t)tiles * sizeof(uint32_t)), stream);
 	if (s.P == 0) {
 		cudaMemsetAsync(g.ranges, 0, (size_t)tiles * sizeof(uint2), stream);
 		return false;

@@ -131,7 +131,6 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 		// flight together instead of forming the chain radii -> (accumulator, parameters) of two dependent round trips,
 		// which is what bounds this kernel (few warps per SM, one long dependent computation per thread).
 		const int radius = radii[idx];
-		const GaussAcc a = g.acc[idx];
 		const float mx = __ldg(s.means3D + 3 * idx), my = __ldg(s.means3D + 3 * idx + 1), mz = __ldg(s.means3D + 3 * idx + 2);
 		float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
 		float sc_in[3] = {0.f, 0.f, 0.f};
@@ -140,6 +139,11 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 #pragma unroll
 			for (int i = 0; i < 3; i++) sc_in[i] = __ldg(s.scales + 3 * idx + i);
 		}
+		// Launched as a programmatic dependent of the compositing backward, this CTA may be resident while that kernel still
+		// runs: its own inputs are on their way; the accumulators are read behind the dependency (L2-coherent loads).
+		pdl_wait();
+		GaussAcc a;
+		a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
 		const bool visible = radius > 0;
 		if (visible) {
 			GaussAcc z;
@@ -414,14 +418,23 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,
                                 float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors, float* dL_dopacity,
                                 float* dL_dscales, float* dL_drotations, float* dL_dcov3D, float* dL_dtau,
-                                cudaStream_t stream)
+                                bool behind_render_backward, cudaStream_t stream)
 {
 	if (s.P == 0) {
 		cudaMemsetAsync(dL_dtau, 0, 6 * sizeof(float), stream);
 		return;
 	}
-	preprocess_backward_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors,
-	                                                                  dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D, dL_dtau);
+	// behind_render_backward: programmatic dependent of the compositing backward launched just before on this stream -- the
+	// CTAs move in during that kernel's tail, fetch their inputs and wait (griddepcontrol.wait) for its accumulators
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((s.P + 255) / 256); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = behind_render_backward ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, preprocess_backward_kernel, s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity,
+	                   dL_dscales, dL_drotations, dL_dcov3D, dL_dtau);
 }
 
 GSR_PROBE_READER(probe_read_preprocess_backward)

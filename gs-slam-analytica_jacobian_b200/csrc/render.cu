@@ -97,6 +97,7 @@ struct FusedSortArgs {
 	unsigned capacity;
 	int id_bits;
 	GeomHeader* hdr;
+	uint32_t* tile_done;
 	int lazy_min;        // lists longer than this are ordered on demand; <= 0: every list is sorted completely
 };
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
@@ -363,6 +364,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
                       float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched,
                       uint32_t* __restrict__ cull_masks, FusedSortArgs fs)
 {
+	pdl_launch_dependents();      // a backward launched as programmatic dependent may move in as soon as every tile has a CTA
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	static_assert(sizeof(FwdSmem) <= kFusedIdsOffset, "sorted ids must sit behind the compositing overlay");
 	FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
@@ -537,6 +539,9 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		out_depth[pix] = D;
 		out_opacity[pix] = 1 - T;
 	}
+	// publish the tile: everything the backward reads of it (final_T, n_contrib, point_list, cull_masks) is written
+	__syncthreads();
+	if (threadIdx.x == 0) st_release_u32(fs.tile_done + tile, 1u);      // cumulative: orders the CTA's writes behind the barrier
 }
 
 }  // namespace
@@ -549,7 +554,7 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	if (tiles == 0) return;
 	FusedSortArgs fs;
 	fs.ranges = g.ranges; fs.pairs = b.pairs; fs.pairs_alt = b.pairs_alt; fs.point_list = b.point_list;
-	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr;
+	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr; fs.tile_done = g.tile_done;
 	fs.id_bits = 1;
 	while (fs.id_bits < 32 && (1ll << fs.id_bits) < (long long)s.P) fs.id_bits++;
 	fs.lazy_min = lazy_min;

@@ -148,12 +148,19 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
-                       GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks)
+                       GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks, const uint32_t* __restrict__ tile_done)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
 	const int tile = blockIdx.x;
+	pdl_launch_dependents();      // the per-Gaussian backward may move in (and fetch its inputs) during this kernel's tail
+	// Launched as a programmatic dependent of the forward compositing kernel (RasterEngine.step) this CTA may be running
+	// while forward CTAs of other tiles still are: wait for ITS tile (a flag the forward CTA releases behind its last
+	// write; always set in a normally ordered launch) and read what the forward wrote with L2-coherent loads only.
+	if (threadIdx.x == 0)
+		while (ld_acquire_u32(tile_done + tile) == 0) __nanosleep(200);
+	__syncthreads();
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -161,14 +168,14 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	pixel_of_thread(tile_x, tile_y, px, py);
 	const bool inside = px < W && py < H;
 	const float bx0 = (float)(tile_x * GSR_TILE + (warp & 1) * 8), by0 = (float)(tile_y * GSR_TILE + (warp >> 1) * 4);
-	const uint2 range = ranges[tile];
+	const uint2 range = __ldcg(ranges + tile);
 	const size_t pix = (size_t)W * py + px, HW = (size_t)H * W;
 
 	PixelState s;
 	s.pxf = (float)px; s.pyf = (float)py;
-	const float T_final = inside ? final_T[pix] : 0.f;
+	const float T_final = inside ? __ldcg(final_T + pix) : 0.f;
 	s.T = T_final;
-	s.last_contributor = inside ? (int)n_contrib[pix] : 0;
+	s.last_contributor = inside ? (int)__ldcg(n_contrib + pix) : 0;
 	s.dp0 = s.dp1 = s.dp2 = s.dpd = 0.f;
 	if (inside) {
 		s.dp0 = dL_dpix[pix]; s.dp1 = dL_dpix[HW + pix]; s.dp2 = dL_dpix[2 * HW + pix];
@@ -204,7 +211,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 			const int t = i / 3, part = i - 3 * t;
 			const int pos = hi - 1 - t;
 			if (pos >= 0 && pos < (int)top) {
-				const uint32_t id = __ldg(point_list + range.x + pos);
+				const uint32_t id = __ldcg(point_list + range.x + pos);
 				if (part == 0) sm.id[buf][t] = id;
 				cp_async16(&sm.rec[buf][t].q0 + part, &rec[id].q0 + part);
 			}
@@ -225,7 +232,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		uint32_t fetched = 0;
 		{
 			const int g = (hi >> 5) - 1 - lane;
-			if (lane < kBatch / 32 && g >= 0 && g * 32 < (int)warp_top) fetched = __ldg(my_masks + (size_t)g * 8);
+			if (lane < kBatch / 32 && g >= 0 && g * 32 < (int)warp_top) fetched = __ldcg(my_masks + (size_t)g * 8);
 		}
 		cp_async_wait<1>();
 		__syncthreads();
@@ -277,15 +284,23 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 }  // namespace
 
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
-                            const float* dL_dpix, const float* dL_dpix_depth, cudaStream_t stream)
+                            const float* dL_dpix, const float* dL_dpix_depth, bool overlap_forward, cudaStream_t stream)
 {
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
 	const size_t smem = sizeof(BwdSmem);
 	static SmemAttrCache attr;
 	ensure_dynamic_smem(render_backward_kernel, smem, attr);
-	render_backward_kernel<<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background,
-	                                                     im.final_T, im.n_contrib, dL_dpix, dL_dpix_depth, g.acc, b.cull_masks);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = overlap_forward ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, render_backward_kernel, (const uint2*)g.ranges, (const uint32_t*)b.point_list, (const GaussRec*)g.rec, s.W, s.H,
+	                   s.grid_x, s.background, (const float*)im.final_T, (const uint32_t*)im.n_contrib, dL_dpix, dL_dpix_depth, g.acc,
+	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done);
 }
 
 }  // namespace gsr

@@ -15,6 +15,7 @@ loop (utils/slam_frontend.py:163, 100 iterations on one frozen map) or a mapping
 All compute goes through the C-ABI (include/gsr_b200.h); torch only owns memory and streams.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -101,11 +102,13 @@ class RasterEngine:
         base = self.cam.data_ptr()
         s.viewmatrix, s.projmatrix, s.projmatrix_raw, s.campos = base, base + 64, base + 128, base + 192
         s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
-        s.prefiltered, s.debug, s.accumulate_grads = 0, 0, 0
+        s.prefiltered, s.debug, s.accumulate_grads, s.overlap_forward = 0, 0, 0, 0
         s.densify_grad_accum = s.densify_denom = s.max_radii2D = None
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.last_num_rendered = None
+        # step(): the compositing backward overlaps the tail of the compositing forward (GSR_NO_OVERLAP=1: plain order)
+        self.overlap = not os.environ.get("GSR_NO_OVERLAP")
 
     # ---- camera ---------------------------------------------------------------------------------------
     @staticmethod
@@ -167,12 +170,16 @@ class RasterEngine:
         self._densify_refs = (xyz_gradient_accum, denom, max_radii2D)      # keep the tensors alive
         self.graph_fwd = self.graph_bwd = self.graph_all = None
 
-    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False):
+    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False):
         """dL_dcolor / dL_ddepth default to the engine's own buffers; accumulate=True adds this view's
-        per-Gaussian gradients into grad_flat (mapping window) instead of overwriting."""
+        per-Gaussian gradients into grad_flat (mapping window) instead of overwriting.
+        overlap_forward=True: ONLY directly behind launch_forward() on the same stream, with upstream gradients that were
+        complete before it -- the compositing backward then starts tile by tile behind the compositing forward
+        (programmatic dependent launch + per-tile flags, gsr_scene.overlap_forward) instead of waiting for its tail."""
         gc = self.dL_dcolor if dL_dcolor is None else dL_dcolor
         gd = self.dL_ddepth if dL_ddepth is None else dL_ddepth
         self.scene.accumulate_grads = 1 if accumulate else 0
+        self.scene.overlap_forward = 1 if (overlap_forward and self.overlap) else 0
         try:
             _cabi.check(_L.gsr_rasterize_gaussians_backward(
                 C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
@@ -180,6 +187,7 @@ class RasterEngine:
                 _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov), _p(self.g_tau), self._stream()), "backward")
         finally:
             self.scene.accumulate_grads = 0
+            self.scene.overlap_forward = 0
 
     def capture(self):
         """Capture forward, backward and forward+backward CUDA graphs over the persistent buffers."""
@@ -202,7 +210,7 @@ class RasterEngine:
             self.graph_all = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_all):
                 self.launch_forward()
-                self.launch_backward()
+                self.launch_backward(overlap_forward=True)
 
     def capture_host_step(self, cam_host, dL_dcolor_host=None, dL_ddepth_host=None):
         """One CUDA graph for a step driven from HOST buffers: H2D of the pinned 52-float camera block (and, when given,
@@ -239,7 +247,8 @@ class RasterEngine:
                 self.launch_forward()
                 if dL_dcolor_host is not None:
                     cur.wait_stream(side)
-                self.launch_backward()
+                # the backward depends on the copies by a full edge and on the forward by a programmatic one
+                self.launch_backward(overlap_forward=True)
                 self.h_tau.copy_(self.g_tau, non_blocking=True)
                 self.h_hdr.copy_(hdr_dev, non_blocking=True)
             self.graph_host = g
@@ -261,7 +270,7 @@ class RasterEngine:
                 self.calibrate()
             with torch.cuda.device(self.dev):
                 self.launch_forward()
-                self.launch_backward()
+                self.launch_backward(overlap_forward=True)
 
     def header(self):
         """(num_rendered, overflow) of the last forward -- synchronises."""

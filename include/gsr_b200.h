@@ -73,6 +73,13 @@ typedef struct gsr_scene {
 	float* densify_grad_accum;   /* [P]  += || dL/dmeans2D[:2] ||   (xyz_gradient_accum) */
 	float* densify_denom;        /* [P]  += 1                       (denom) */
 	float* max_radii2D;          /* [P]   = max(., radii)           (max_radii2D) */
+	int overlap_forward;         /* backward only: set ONLY when this call directly follows, on the same stream, the forward
+	                                (gsr_forward_render / gsr_forward_nosync) of the same workspaces, and dL_dout_color /
+	                                dL_dout_depth were complete before that forward was launched.  The compositing backward is
+	                                then launched as a programmatic dependent of the compositing forward (CUDA programmatic
+	                                stream serialization) and starts tile by tile behind it -- per-tile release/acquire flags
+	                                in the geometry workspace order the data -- instead of waiting for the forward's tail.
+	                                0 (default): plain stream order. */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
