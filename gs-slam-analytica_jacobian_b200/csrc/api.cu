@@ -93,6 +93,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.accumulate_grads = a->accumulate_grads;
 	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
 	s.overlap_forward = a->overlap_forward;
+	s.upstream_ready = a->upstream_ready;
 	return GSR_OK;
 }
 

@@ -22,6 +22,7 @@ struct Scene {
 	int grid_x, grid_y;
 	int prefiltered;
 	int accumulate_grads;
+	const unsigned int* upstream_ready;   // backward: optional device word, non-zero once dL/dpixel are in place
 	int overlap_forward;          // backward: launch the compositing backward as programmatic dependent of the forward before it
 	float* densify_grad_accum;    // [P] or null
 	float* densify_denom;         // [P] or null

@@ -148,7 +148,8 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
-                       GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks, const uint32_t* __restrict__ tile_done)
+                       GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks, const uint32_t* __restrict__ tile_done,
+                       const uint32_t* __restrict__ upstream_ready, GeomHeader* __restrict__ hdr)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -158,8 +159,16 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	// Launched as a programmatic dependent of the forward compositing kernel (RasterEngine.step) this CTA may be running
 	// while forward CTAs of other tiles still are: wait for ITS tile (a flag the forward CTA releases behind its last
 	// write; always set in a normally ordered launch) and read what the forward wrote with L2-coherent loads only.
-	if (threadIdx.x == 0)
-		while (ld_acquire_u32(tile_done + tile) == 0) __nanosleep(200);
+	// upstream_ready (optional): a word that whoever delivers dL/dpixel sets behind the data (e.g. the last of the host-to-device
+	// copies of a step on another stream): the dependency on it then need not be a full edge in front of this kernel.
+	// The spins are bounded (~1 s): a flag that never comes is reported through the header, not by hanging the GPU.
+	if (threadIdx.x == 0) {
+		int spins = 0;
+		while (ld_acquire_u32(tile_done + tile) == 0 && ++spins < (1 << 22)) __nanosleep(200);
+		if (upstream_ready)
+			while (ld_acquire_u32(upstream_ready) == 0 && ++spins < (1 << 22)) __nanosleep(200);
+		if (spins >= (1 << 22)) hdr->overflow = 2;
+	}
 	__syncthreads();
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,7 +309,7 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	cfg.numAttrs = overlap_forward ? 1 : 0;
 	cudaLaunchKernelEx(&cfg, render_backward_kernel, (const uint2*)g.ranges, (const uint32_t*)b.point_list, (const GaussRec*)g.rec, s.W, s.H,
 	                   s.grid_x, s.background, (const float*)im.final_T, (const uint32_t*)im.n_contrib, dL_dpix, dL_dpix_depth, g.acc,
-	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done);
+	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done, (const uint32_t*)s.upstream_ready, g.hdr);
 }
 
 }  // namespace gsr

@@ -32,7 +32,7 @@ class GsrScene(C.Structure):
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
         ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
-        ("overlap_forward", C.c_int),
+        ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p),
     ]
 
 

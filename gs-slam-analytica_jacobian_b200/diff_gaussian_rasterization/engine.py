@@ -103,6 +103,7 @@ class RasterEngine:
         s.viewmatrix, s.projmatrix, s.projmatrix_raw, s.campos = base, base + 64, base + 128, base + 192
         s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
         s.prefiltered, s.debug, s.accumulate_grads, s.overlap_forward = 0, 0, 0, 0
+        s.upstream_ready = None
         s.densify_grad_accum = s.densify_denom = s.max_radii2D = None
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
@@ -170,7 +171,7 @@ class RasterEngine:
         self._densify_refs = (xyz_gradient_accum, denom, max_radii2D)      # keep the tensors alive
         self.graph_fwd = self.graph_bwd = self.graph_all = None
 
-    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False):
+    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False, upstream_ready=None):
         """dL_dcolor / dL_ddepth default to the engine's own buffers; accumulate=True adds this view's
         per-Gaussian gradients into grad_flat (mapping window) instead of overwriting.
         overlap_forward=True: ONLY directly behind launch_forward() on the same stream, with upstream gradients that were
@@ -180,6 +181,7 @@ class RasterEngine:
         gd = self.dL_ddepth if dL_ddepth is None else dL_ddepth
         self.scene.accumulate_grads = 1 if accumulate else 0
         self.scene.overlap_forward = 1 if (overlap_forward and self.overlap) else 0
+        self.scene.upstream_ready = None if upstream_ready is None else upstream_ready.data_ptr()
         try:
             _cabi.check(_L.gsr_rasterize_gaussians_backward(
                 C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
@@ -188,6 +190,7 @@ class RasterEngine:
         finally:
             self.scene.accumulate_grads = 0
             self.scene.overlap_forward = 0
+            self.scene.upstream_ready = None
 
     def capture(self):
         """Capture forward, backward and forward+backward CUDA graphs over the persistent buffers."""
@@ -234,21 +237,35 @@ class RasterEngine:
             torch.cuda.current_stream(self.dev).wait_stream(warm)
             torch.cuda.synchronize(self.dev)
             side = torch.cuda.Stream(self.dev)
+            # the upstream gradients arrive on a side branch; a 4-byte copy queued behind them sets a device word the backward
+            # waits for ON THE DEVICE, so that the branch joins behind the backward and the backward keeps its programmatic
+            # (tile by tile) dependency on the forward
+            flagged = dL_dcolor_host is not None and self.overlap
+            if flagged:
+                self.h_one = torch.ones(1, dtype=torch.int32).pin_memory()
+                self.up_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 cur = torch.cuda.current_stream(self.dev)
                 self.cam.copy_(cam_host, non_blocking=True)
+                if flagged:
+                    self.up_flag.zero_()
                 if dL_dcolor_host is not None:
                     side.wait_stream(cur)
                     with torch.cuda.stream(side):
                         self.dL_dcolor.copy_(dL_dcolor_host, non_blocking=True)
                         if dL_ddepth_host is not None:
                             self.dL_ddepth.copy_(dL_ddepth_host, non_blocking=True)
+                        if flagged:
+                            self.up_flag.copy_(self.h_one, non_blocking=True)
                 self.launch_forward()
-                if dL_dcolor_host is not None:
+                if flagged:
+                    self.launch_backward(overlap_forward=True, upstream_ready=self.up_flag)
                     cur.wait_stream(side)
-                # the backward depends on the copies by a full edge and on the forward by a programmatic one
-                self.launch_backward(overlap_forward=True)
+                else:
+                    if dL_dcolor_host is not None:
+                        cur.wait_stream(side)
+                    self.launch_backward()
                 self.h_tau.copy_(self.g_tau, non_blocking=True)
                 self.h_hdr.copy_(hdr_dev, non_blocking=True)
             self.graph_host = g

@@ -80,6 +80,14 @@ typedef struct gsr_scene {
 	                                stream serialization) and starts tile by tile behind it -- per-tile release/acquire flags
 	                                in the geometry workspace order the data -- instead of waiting for the forward's tail.
 	                                0 (default): plain stream order. */
+	const unsigned int* upstream_ready; /* backward only, optional (null = off): a device word that is non-zero once
+	                                dL_dout_color / dL_dout_depth are in place -- e.g. written by a 4-byte host-to-device copy
+	                                queued behind the copies of the gradients on another stream.  The compositing backward
+	                                waits for it on the device, so that this dependency need not be a full edge in front of
+	                                the kernel (which would undo overlap_forward).  The caller clears the word before the
+	                                forward of the step and joins the other stream behind the backward.  If the word (or a
+	                                tile flag) does not arrive within about a second the kernel gives up and sets the
+	                                header's overflow word to 2 (gsr_forward_overflowed). */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
