@@ -71,9 +71,12 @@ class KeyframeWindow:
                 e.set_camera(self.cameras[v])
                 e.calibrate()
 
-    def iteration(self, upstream, reduce=True, on_view=None):
+    def iteration(self, upstream, reduce=True, on_view=None, upstream_precomputed=False):
         """One window iteration.  Returns engine.grad_flat (summed over all views of all ranks when
-        reduce=True).  on_view(local_index, view) can read the engine's per-view outputs."""
+        reduce=True).  on_view(local_index, view) can read the engine's per-view outputs.
+        upstream_precomputed=True: the upstream gradients do not depend on this iteration's renders and upstream() launches
+        nothing -- every view's compositing backward then starts tile by tile behind its forward
+        (RasterEngine.launch_backward(overlap_forward=True))."""
         eng = self.engine
         if not self.views:
             eng.grad_flat.zero_()        # a rank without views still takes part in the collective
@@ -85,7 +88,7 @@ class KeyframeWindow:
                     gc, gd = upstream(v)
                 else:
                     gc, gd = upstream[0][v], upstream[1][v]
-                eng.launch_backward(gc, gd, accumulate=(i > 0))
+                eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed)
                 self.tau[i].copy_(eng.g_tau, non_blocking=True)
                 if on_view is not None:
                     on_view(i, v)
@@ -104,7 +107,7 @@ class KeyframeWindow:
                         gc, gd = upstream(v, e)
                     else:
                         gc, gd = upstream[0][v], upstream[1][v]
-                    e.launch_backward(gc, gd, accumulate=used[k])
+                    e.launch_backward(gc, gd, accumulate=used[k], overlap_forward=upstream_precomputed)
                     used[k] = True
                     self.tau[i].copy_(e.g_tau, non_blocking=True)
                     if on_view is not None:
