@@ -182,34 +182,58 @@ __device__ __forceinline__ uint32_t rect_row(uint32_t i, uint32_t w, uint32_t ma
 }
 
 // Visit every tile of the rectangles held by the lanes of a warp (n = tile count of this lane's Gaussian, 0 = none;
-// lo/hi = packed rectangle).  Rectangles of up to kSoloTiles tiles are walked by their own lane (all lanes in
-// parallel, a handful of iterations); the rare large ones are walked by the whole warp, 32 tiles per step.
-// f(tile, key, id) is called once per (Gaussian, tile) with the owner's key / id.  Must be called by all 32 lanes.
+// lo/hi = packed rectangle).  f(tile, key, id) is called once per (Gaussian, tile) with the owner's key / id.  Must be
+// called by all 32 lanes.
+//
+// Load-balanced expansion: the rectangles of the 32 lanes hold anything from 1 to thousands of tiles, so a walk "every
+// lane its own rectangle" runs as long as the largest one while most lanes idle (measured at 3 M Gaussians / 1920x1080,
+// 34 tiles per Gaussian: 117 warp instructions per Gaussian and pass).  Instead the non-empty rectangles are compacted to
+// the low lanes, their tile counts prefix-summed, and the warp walks the concatenated instance range 32 instances per
+// step: lane k of a step finds its segment from a bit mask of the segment starts inside the step's window (one
+// redux.or + popc), fetches the segment's parameters by shuffle and derives its tile from the offset inside the segment.
 constexpr uint32_t kSoloTiles = 32;
 template <typename F>
 __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t hi, int grid_x, uint32_t key, uint32_t id, F&& f)
 {
-	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
-	if (n != 0 && n <= kSoloTiles) {
-		for (uint32_t y = y0; y < y1; y++) {
-			uint32_t tile = y * grid_x + x0;
-			for (uint32_t x = x0; x < x1; x++, tile++) f(tile, key, id);
-		}
-	}
-	unsigned big = __ballot_sync(0xffffffffu, n > kSoloTiles);
+	constexpr unsigned kAll = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31;
-	while (big) {
-		const int src = __ffs(big) - 1;
-		big &= big - 1;
-		const uint32_t g_lo = __shfl_sync(0xffffffffu, lo, src), g_hi = __shfl_sync(0xffffffffu, hi, src);
-		const uint32_t g_n = __shfl_sync(0xffffffffu, n, src);
-		const uint32_t g_key = __shfl_sync(0xffffffffu, key, src), g_id = __shfl_sync(0xffffffffu, id, src);
-		const uint32_t gx0 = g_lo & 0xffff, gy0 = g_lo >> 16, w = (g_hi & 0xffff) - gx0;
-		const uint32_t magic = rect_magic(w, g_n);
-		for (uint32_t i = lane; i < g_n; i += 32) {
-			const uint32_t ty = rect_row(i, w, magic), tx = i - ty * w;
-			f((gy0 + ty) * grid_x + (gx0 + tx), g_key, g_id);
+	const unsigned E = __ballot_sync(kAll, n != 0);
+	if (E == 0) return;
+	// compact the non-empty rectangles to lanes 0 .. m-1 (dense lane r takes the r-th non-empty lane's values)
+	const int m = __popc(E);
+	const int src0 = (int)lane < m ? (int)__fns(E, 0, lane + 1) : 0;
+	uint32_t d_n = __shfl_sync(kAll, n, src0);
+	if ((int)lane >= m) d_n = 0;
+	const uint32_t d_lo = __shfl_sync(kAll, lo, src0), d_hi = __shfl_sync(kAll, hi, src0);
+	const uint32_t d_key = __shfl_sync(kAll, key, src0), d_id = __shfl_sync(kAll, id, src0);
+	const uint32_t x0 = d_lo & 0xffff, y0 = d_lo >> 16, w = (d_hi & 0xffff) - x0;
+	const uint32_t magic = rect_magic(w, d_n);
+	const uint32_t first = y0 * (uint32_t)grid_x + x0;
+	uint32_t inc = d_n;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t t = __shfl_up_sync(kAll, inc, o);
+		if ((int)lane >= o) inc += t;
+	}
+	const uint32_t off = inc - d_n;                           // strictly increasing over the dense lanes
+	const uint32_t total = __shfl_sync(kAll, inc, 31);
+	unsigned before = 0;                                      // segments that start in front of the window
+	for (uint32_t base = 0; base < total; base += 32) {
+		const uint32_t rel = off - base;                      // wraps (>= 32) for segments that started earlier
+		const unsigned starts = __reduce_or_sync(kAll, ((int)lane < m && rel < 32u) ? (1u << rel) : 0u);
+		const unsigned c = before + __popc(starts & (kAll >> (31 - lane)));      // segments starting at or before position base + lane
+		const int src = (int)c - 1;                           // >= 0: position 0 belongs to dense lane 0
+		const uint32_t s_off = __shfl_sync(kAll, off, src);
+		const uint32_t s_w = __shfl_sync(kAll, w, src), s_magic = __shfl_sync(kAll, magic, src);
+		const uint32_t s_first = __shfl_sync(kAll, first, src);
+		const uint32_t s_key = __shfl_sync(kAll, d_key, src), s_id = __shfl_sync(kAll, d_id, src);
+		const uint32_t k = base + lane;
+		if (k < total) {
+			const uint32_t i = k - s_off;
+			const uint32_t ty = rect_row(i, s_w, s_magic), tx = i - ty * s_w;
+			f(s_first + ty * (uint32_t)grid_x + tx, s_key, s_id);
 		}
+		before += __popc(starts);
 	}
 }
 

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			__threadfence();
 		}
 		__syncthreads();
+		GSR_PROBE(0, 5);
 		// ---- every CTA: exclusive scan of the tile counters -> s_start[tile]; CTA 0 also publishes ranges etc. ----
 		uint32_t* s_start = s_hist + n_tiles;
 		{
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			s_hist[t] = 0;
 		}
 		__syncthreads();
+		GSR_PROBE(0, 6);
 		// ---- store the pairs ----
 		bool overflow = false;
 		for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, depth_bits, (uint32_t)idx, [&](uint32_t tile, uint32_t key, uint32_t id) {
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			else overflow = true;
 		});
 		if (overflow) g.hdr->overflow = 1;
+		GSR_PROBE(0, 7);
 		return;
 	}
 	__syncthreads();

@@ -35,7 +35,7 @@ L = _cabi.load()
 buf = np.zeros((4, 4096, 8), np.uint64)
 _cabi.check(L.gsr_debug_probe(buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.nbytes), "probe")
 tiles = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
-for k, (kname, nph) in enumerate((("preprocess_forward", 7), ("scatter", 5), ("preprocess_backward", 4), ("render_forward", 5))):
+for k, (kname, nph) in enumerate((("preprocess_forward", 8), ("scatter", 5), ("preprocess_backward", 4), ("render_forward", 5))):
     nblk = min(4096, tiles if k == 3 else (cfg["P"] + 255) // 256)
     tb = buf[k, :nblk, :nph].astype(np.int64)
     t0 = tb[:, 0].min()
