@@ -94,6 +94,18 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
 	s.overlap_forward = a->overlap_forward;
 	s.upstream_ready = a->upstream_ready;
+	s.has_loss = a->fused_loss != nullptr;
+	if (s.has_loss) {
+		const gsr_fused_loss* l = a->fused_loss;
+		if (!l->gt_color || !l->dL_dcolor || !l->dL_ddepth || !l->sums || !l->scratch || (l->use_depth && !l->gt_depth))
+			return fail(GSR_ERR_ARG, "fused_loss: gt_color, outputs and scratch are required (gt_depth with use_depth)");
+		s.loss.gt_color = l->gt_color; s.loss.gt_depth = l->gt_depth; s.loss.grad_mask = l->grad_mask; s.loss.exposure = l->exposure;
+		s.loss.rgb_boundary_threshold = l->rgb_boundary_threshold; s.loss.alpha = l->alpha;
+		s.loss.use_depth = l->use_depth; s.loss.opacity_weighted = l->opacity_weighted;
+		s.loss.dL_dcolor = l->dL_dcolor; s.loss.dL_ddepth = l->dL_ddepth; s.loss.sums = l->sums;
+		s.loss.partials = (float*)l->scratch;
+		s.loss.ticket = (unsigned*)((float*)l->scratch + 4 * (size_t)s.grid_x * s.grid_y);
+	}
 	return GSR_OK;
 }
 
@@ -310,6 +322,7 @@ int gsr_debug_probe(unsigned long long* out, size_t bytes)
 }
 
 size_t gsr_slam_loss_scratch_bytes(int W, int H) { return gsr::slam_loss_scratch_bytes(W, H); }
+size_t gsr_fused_loss_scratch_bytes(int W, int H) { return (4 * tiles_of(W, H) + 4) * sizeof(float); }
 
 int gsr_slam_loss(int W, int H, const float* color, const float* depth, const float* opacity, const float* gt_color,
                   const float* gt_depth, const unsigned char* grad_mask, const float* exposure, float rgb_boundary_threshold,

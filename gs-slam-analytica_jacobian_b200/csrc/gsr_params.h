@@ -4,6 +4,21 @@
 
 namespace gsr {
 
+// loss evaluated in the epilogue of the forward compositing kernel (gsr_fused_loss)
+struct FusedLoss {
+	const float* gt_color;
+	const float* gt_depth;
+	const unsigned char* grad_mask;
+	const float* exposure;
+	float rgb_boundary_threshold, alpha;
+	int use_depth, opacity_weighted;
+	float* dL_dcolor;
+	float* dL_ddepth;
+	float* sums;
+	float* partials;       // [tiles][4]
+	unsigned* ticket;
+};
+
 struct Scene {
 	int P, D, M, W, H;
 	const float* background;      // [3]
@@ -23,6 +38,8 @@ struct Scene {
 	int prefiltered;
 	int accumulate_grads;
 	const unsigned int* upstream_ready;   // backward: optional device word, non-zero once dL/dpixel are in place
+	bool has_loss;
+	FusedLoss loss;
 	int overlap_forward;          // backward: launch the compositing backward as programmatic dependent of the forward before it
 	float* densify_grad_accum;    // [P] or null
 	float* densify_denom;         // [P] or null

@@ -356,13 +356,16 @@ __device__ __noinline__ void sort_whole_tile(int tile, FusedSortArgs fs, int ids
 
 // MODE 0: point_list holds the sorted lists.  MODE 1: the CTA sorts its whole list first (every list expected to fit one
 // shared-memory chunk; anything longer takes the general path).  MODE 2: lists above fs.lazy_min are ordered on demand.
-template <int MODE>
+// LOSS: the view's SLAM loss (slam_ops.cu slam_loss_kernel, same arithmetic) is evaluated in the epilogue from the pixel values
+// still in registers: dL/dcolor, dL/ddepth and the per-tile partial sums of {loss, dL/da, dL/db}; the last CTA adds the
+// partials in tile order.
+template <int MODE, bool LOSS>
 __global__ void __launch_bounds__(256, 4)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_opacity, int* __restrict__ n_touched,
-                      uint32_t* __restrict__ cull_masks, FusedSortArgs fs)
+                      uint32_t* __restrict__ cull_masks, FusedSortArgs fs, FusedLoss lf)
 {
 	pdl_launch_dependents();      // a backward launched as programmatic dependent may move in as soon as every tile has a CTA
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -539,6 +542,71 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 		out_depth[pix] = D;
 		out_opacity[pix] = 1 - T;
 	}
+	if (LOSS) {
+		const int HW = H * W;
+		float loss = 0.f, ga = 0.f, gb = 0.f;
+		if (inside) {
+			const int p = W * py + px;
+			const float ea = lf.exposure ? __expf(lf.exposure[0]) : 1.f;       // image_ab = exp(a) * image + b
+			const float eb = lf.exposure ? lf.exposure[1] : 0.f;
+			const float inv_rgb = 1.f / (3.f * (float)HW), inv_d = 1.f / (float)HW;
+			const float w_rgb = lf.use_depth ? lf.alpha : 1.f, w_d = 1.f - lf.alpha;
+			const float gt[3] = {lf.gt_color[p], lf.gt_color[HW + p], lf.gt_color[2 * HW + p]};
+			float m = (gt[0] + gt[1] + gt[2] > lf.rgb_boundary_threshold) ? 1.f : 0.f;
+			if (lf.grad_mask) m *= lf.grad_mask[p] ? 1.f : 0.f;
+			const float op = 1 - T;
+			const float wgt = lf.opacity_weighted ? op : 1.f;
+			const float c[3] = {C0 + T * bg[0], C1 + T * bg[1], C2 + T * bg[2]};
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++) {
+				const float iab = ea * c[ch] + eb;
+				const float d = iab * m - gt[ch] * m;
+				loss += w_rgb * inv_rgb * wgt * fabsf(d);
+				const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+				const float g_iab = w_rgb * inv_rgb * wgt * m * sgn;
+				lf.dL_dcolor[ch * HW + p] = g_iab * ea;
+				ga += g_iab * ea * c[ch];
+				gb += g_iab;
+			}
+			float gd = 0.f;
+			if (lf.use_depth) {
+				const float gtd = lf.gt_depth[p];
+				float dm = (gtd > 0.01f) ? 1.f : 0.f;
+				if (lf.opacity_weighted) dm *= (op > 0.95f) ? 1.f : 0.f;
+				const float dd = D * dm - gtd * dm;
+				loss += w_d * inv_d * fabsf(dd);
+				gd = w_d * inv_d * dm * ((dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f));
+			}
+			lf.dL_ddepth[p] = gd;
+		}
+		loss = warp_sum(loss); ga = warp_sum(ga); gb = warp_sum(gb);
+		float* s_red = reinterpret_cast<float*>(sm.tmask);      // idle by now
+		__syncthreads();
+		if (lane == 0) { s_red[warp * 4] = loss; s_red[warp * 4 + 1] = ga; s_red[warp * 4 + 2] = gb; }
+		__syncthreads();
+		if (threadIdx.x < 3) {
+			float v = 0.f;
+#pragma unroll
+			for (int w = 0; w < 8; w++) v += s_red[w * 4 + threadIdx.x];
+			lf.partials[tile * 4 + threadIdx.x] = v;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			s_red[32] = (atomicAdd(lf.ticket, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+		}
+		__syncthreads();
+		if (s_red[32] != 0.f) {      // last CTA: deterministic sum over the tiles, warp k takes component k
+			__threadfence();
+			if (threadIdx.x < 96) {
+				float v = 0.f;
+				for (unsigned t = lane; t < gridDim.x; t += 32) v += __ldcg(&lf.partials[t * 4 + warp]);
+				v = warp_sum(v);
+				if (lane == 0) lf.sums[warp] = v;
+			}
+			if (threadIdx.x == 0) *lf.ticket = 0;
+		}
+	}
 	// publish the tile: everything the backward reads of it (final_T, n_contrib, point_list, cull_masks) is written
 	__syncthreads();
 	if (threadIdx.x == 0) st_release_u32(fs.tile_done + tile, 1u);      // cumulative: orders the CTA's writes behind the barrier
@@ -563,19 +631,27 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	static_assert(kFusedIdsOffset + kFusedIdsCap * 4 <= kLazyOffset, "sorted ids end inside the sort scratch");
 	const size_t smem_fused = (kLazyOffset + sizeof(LazySmem) + 15) / 16 * 16;
 	const size_t smem_sort = sort_smem_bytes(kSmallChunk, 256);
-	static SmemAttrCache lazy_attr, fused_attr, plain_attr;
-	ensure_dynamic_smem(render_forward_kernel<2>, smem_fused, lazy_attr);
-	ensure_dynamic_smem(render_forward_kernel<1>, smem_sort, fused_attr);
-	ensure_dynamic_smem(render_forward_kernel<0>, smem_plain, plain_attr);
-#define GSR_FWD_ARGS g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background, im.final_T, im.n_contrib, out_color, out_depth, \
-	out_opacity, n_touched, b.cull_masks, fs
-	if (fused_sort && s.P > 0 && R_capacity > 0) {
-		if (lazy_min > 0) render_forward_kernel<2><<<tiles, 256, smem_fused, stream>>>(GSR_FWD_ARGS);
-		else render_forward_kernel<1><<<tiles, 256, smem_sort, stream>>>(GSR_FWD_ARGS);
+	static SmemAttrCache attr[6];
+	const int mode = (fused_sort && s.P > 0 && R_capacity > 0) ? (lazy_min > 0 ? 2 : 1) : 0;
+	const size_t smem = mode == 2 ? smem_fused : (mode == 1 ? smem_sort : smem_plain);
+	FusedLoss lf = s.loss;
+#define GSR_FWD_LAUNCH(M, L)                                                                                                      \
+	do {                                                                                                                          \
+		ensure_dynamic_smem(render_forward_kernel<M, L>, smem, attr[2 * M + (L ? 1 : 0)]);                                        \
+		render_forward_kernel<M, L><<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background, \
+		                                                         im.final_T, im.n_contrib, out_color, out_depth, out_opacity,    \
+		                                                         n_touched, b.cull_masks, fs, lf);                                \
+	} while (0)
+	if (s.has_loss) {
+		if (mode == 2) GSR_FWD_LAUNCH(2, true);
+		else if (mode == 1) GSR_FWD_LAUNCH(1, true);
+		else GSR_FWD_LAUNCH(0, true);
 	} else {
-		render_forward_kernel<0><<<tiles, 256, smem_plain, stream>>>(GSR_FWD_ARGS);
+		if (mode == 2) GSR_FWD_LAUNCH(2, false);
+		else if (mode == 1) GSR_FWD_LAUNCH(1, false);
+		else GSR_FWD_LAUNCH(0, false);
 	}
-#undef GSR_FWD_ARGS
+#undef GSR_FWD_LAUNCH
 }
 
 GSR_PROBE_READER(probe_read_render)

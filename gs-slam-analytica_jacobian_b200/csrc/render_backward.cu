@@ -187,8 +187,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	s.last_contributor = inside ? (int)__ldcg(n_contrib + pix) : 0;
 	s.dp0 = s.dp1 = s.dp2 = s.dpd = 0.f;
 	if (inside) {
-		s.dp0 = dL_dpix[pix]; s.dp1 = dL_dpix[HW + pix]; s.dp2 = dL_dpix[2 * HW + pix];
-		s.dpd = dL_dpix_depth[pix];
+		// (L2-coherent: with the loss fused into the forward these are products of the forward CTA of this tile too)
+		s.dp0 = __ldcg(dL_dpix + pix); s.dp1 = __ldcg(dL_dpix + HW + pix); s.dp2 = __ldcg(dL_dpix + 2 * HW + pix);
+		s.dpd = __ldcg(dL_dpix_depth + pix);
 	}
 	sm.dpix[warp][lane] = make_float4(s.dp0, s.dp1, s.dp2, s.dpd);
 	s.c_bg = -T_final * (bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2);

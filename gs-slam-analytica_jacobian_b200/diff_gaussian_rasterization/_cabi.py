@@ -19,8 +19,16 @@ EXPORTS = (
     "gsr_forward_render", "gsr_forward_overflowed", "gsr_rasterize_gaussians", "gsr_rasterize_gaussians_backward",
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
-    "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand",
+    "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand", "gsr_fused_loss_scratch_bytes",
 )
+
+
+class GsrFusedLoss(C.Structure):
+    _fields_ = [
+        ("gt_color", C.c_void_p), ("gt_depth", C.c_void_p), ("grad_mask", C.c_void_p), ("exposure", C.c_void_p),
+        ("rgb_boundary_threshold", C.c_float), ("alpha", C.c_float), ("use_depth", C.c_int), ("opacity_weighted", C.c_int),
+        ("dL_dcolor", C.c_void_p), ("dL_ddepth", C.c_void_p), ("sums", C.c_void_p), ("scratch", C.c_void_p),
+    ]
 
 
 class GsrScene(C.Structure):
@@ -32,7 +40,7 @@ class GsrScene(C.Structure):
         ("scale_modifier", C.c_float), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
         ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
-        ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p),
+        ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p), ("fused_loss", C.POINTER(GsrFusedLoss)),
     ]
 
 
@@ -86,6 +94,8 @@ def load():
     lib.gsr_kernel_launch_count.restype = C.c_ulonglong
     lib.gsr_stage_timing.argtypes = [ip]
     lib.gsr_sort_on_demand.argtypes = [ip]
+    lib.gsr_fused_loss_scratch_bytes.argtypes = [ip, ip]
+    lib.gsr_fused_loss_scratch_bytes.restype = sz
     lib.gsr_stage_times_ms.argtypes = [C.POINTER(C.c_float)]
     lib.gsr_debug_probe.argtypes = [C.POINTER(C.c_ulonglong), sz]
     lib.gsr_slam_loss_scratch_bytes.restype = sz

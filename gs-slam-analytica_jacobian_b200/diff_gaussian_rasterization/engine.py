@@ -155,7 +155,16 @@ class RasterEngine:
         return int(R.value)
 
     # ---- un-synchronised launches ---------------------------------------------------------------------
-    def launch_forward(self):
+    def launch_forward(self, fused_loss=None):
+        """fused_loss: a _cabi.GsrFusedLoss (slam_ops.FusedLoss.struct): the view's SLAM loss and its gradients w.r.t. the
+        rendered images are evaluated in the epilogue of the compositing kernel (no kernel between forward and backward)."""
+        self.scene.fused_loss = None if fused_loss is None else C.pointer(fused_loss)
+        try:
+            self._launch_forward()
+        finally:
+            self.scene.fused_loss = None
+
+    def _launch_forward(self):
         _cabi.check(_L.gsr_forward_nosync(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.binning), self.bin_bytes,
                                           self.capacity, self.max_tile_hint, _p(self.img), self.img_bytes, _p(self.color), _p(self.depth),
                                           _p(self.opacity), _p(self.radii), _p(self.n_touched), self._stream()), "forward_nosync")

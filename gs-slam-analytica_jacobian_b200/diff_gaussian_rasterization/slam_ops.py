@@ -53,6 +53,23 @@ def slam_loss(ws, color, depth, opacity, gt_color, gt_depth=None, grad_mask=None
     return ws.sums
 
 
+class FusedLoss:
+    """The same loss evaluated inside the forward compositing kernel's epilogue (gsr_fused_loss): build once per
+    (workspace, targets), hand `.struct` to RasterEngine.launch_forward(fused_loss=...).  The gradients land in the given
+    dL_dcolor / dL_ddepth (normally the engine's own upstream buffers), the sums in ws.sums."""
+
+    def __init__(self, ws, gt_color, gt_depth=None, grad_mask=None, exposure=None, rgb_boundary_threshold=0.01, alpha=0.95,
+                 tracking=True, dL_dcolor=None, dL_ddepth=None):
+        gc = ws.dL_dcolor if dL_dcolor is None else dL_dcolor
+        gd = ws.dL_ddepth if dL_ddepth is None else dL_ddepth
+        self.scratch = torch.zeros(_L.gsr_fused_loss_scratch_bytes(ws.W, ws.H), dtype=torch.uint8, device=ws.dev)
+        self._keep = (ws, gt_color, gt_depth, grad_mask, exposure, gc, gd)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self.struct = _cabi.GsrFusedLoss(ptr(gt_color), ptr(gt_depth), ptr(grad_mask), ptr(exposure), float(rgb_boundary_threshold),
+                                         float(alpha), 0 if gt_depth is None else 1, 1 if tracking else 0, ptr(gc), ptr(gd),
+                                         ptr(ws.sums), ptr(self.scratch))
+
+
 class PoseState:
     """World-to-camera pose (R row-major, T), exposure (a, b), Adam state and status of one tracked frame, on the device."""
 
@@ -92,21 +109,29 @@ class TrackingLoop:
     """The reference's per-frame tracking loop (utils/slam_frontend.py:129-192) as one CUDA graph per iteration."""
 
     def __init__(self, engine, pose, gt_color, gt_depth=None, grad_mask=None, rgb_boundary_threshold=0.01, alpha=0.95,
-                 lr_rot=0.003, lr_trans=0.001, lr_exposure=0.01, converged_threshold=1e-4):
+                 lr_rot=0.003, lr_trans=0.001, lr_exposure=0.01, converged_threshold=1e-4, fused=True):
+        """fused=True: the loss is evaluated in the forward compositing kernel's epilogue and the backward starts tile by
+        tile behind the forward (three kernels + the pose step per iteration); False: the stand-alone loss kernel."""
         self.eng, self.pose = engine, pose
         self.gt_color, self.gt_depth, self.grad_mask = gt_color, gt_depth, grad_mask
         self.ws = LossWorkspace(engine.W, engine.H, engine.dev)
         self.kw = dict(rgb_boundary_threshold=rgb_boundary_threshold, alpha=alpha)
         self.lrs = (lr_rot, lr_trans, lr_exposure, converged_threshold)
         self.graph = None
+        self.fused = FusedLoss(self.ws, gt_color, gt_depth, grad_mask, pose.exposure, tracking=True, dL_dcolor=engine.dL_dcolor,
+                               dL_ddepth=engine.dL_ddepth, **self.kw) if fused else None
         camera_block_from_pose(pose, engine.cam)
 
     def _iteration(self):
         eng = self.eng
-        eng.launch_forward()
-        slam_loss(self.ws, eng.color, eng.depth, eng.opacity, self.gt_color, self.gt_depth, self.grad_mask, self.pose.exposure,
-                  tracking=True, dL_dcolor=eng.dL_dcolor, dL_ddepth=eng.dL_ddepth, **self.kw)
-        eng.launch_backward()
+        if self.fused is not None:
+            eng.launch_forward(fused_loss=self.fused.struct)
+            eng.launch_backward(overlap_forward=True)
+        else:
+            eng.launch_forward()
+            slam_loss(self.ws, eng.color, eng.depth, eng.opacity, self.gt_color, self.gt_depth, self.grad_mask, self.pose.exposure,
+                      tracking=True, dL_dcolor=eng.dL_dcolor, dL_ddepth=eng.dL_ddepth, **self.kw)
+            eng.launch_backward()
         tracking_step(self.pose, eng.g_tau, self.ws.sums, eng.cam, *self.lrs)
 
     def capture(self):

@@ -41,6 +41,23 @@ extern "C" {
 #define GSR_ERR_WORKSPACE -3  /* a caller-provided workspace is too small */
 #define GSR_ERR_OVERFLOW -4   /* num_rendered exceeded the binning capacity (no-sync mode) */
 
+/* Optional: the SLAM loss of the view evaluated in the epilogue of the forward compositing kernel (the pixel values are
+ * still in registers), see gsr_slam_loss below for the arithmetic (utils/slam_utils.py:56-128).  The forward then also
+ * writes dL_dcolor / dL_ddepth -- the upstream gradients of the backward -- and sums[4] = {loss, dL/da, dL/db, 0}, so that
+ * no kernel stands between forward and backward and the backward may start tile by tile (gsr_scene.overlap_forward). */
+typedef struct gsr_fused_loss {
+	const float* gt_color;          /* [3,H,W] */
+	const float* gt_depth;          /* [1,H,W], read when use_depth != 0 */
+	const unsigned char* grad_mask; /* [H,W] bool or null */
+	const float* exposure;          /* [2] = (a, b) device pointer or null */
+	float rgb_boundary_threshold, alpha;
+	int use_depth, opacity_weighted;
+	float* dL_dcolor;               /* [3,H,W] out */
+	float* dL_ddepth;               /* [1,H,W] out */
+	float* sums;                    /* [4] out */
+	void* scratch;                  /* gsr_fused_loss_scratch_bytes(W, H) bytes, zero-filled ONCE by the caller */
+} gsr_fused_loss;
+
 typedef struct gsr_scene {
 	int P;                       /* number of Gaussians */
 	int D;                       /* active SH degree                      (settings.sh_degree) */
@@ -88,6 +105,8 @@ typedef struct gsr_scene {
 	                                forward of the step and joins the other stream behind the backward.  If the word (or a
 	                                tile flag) does not arrive within about a second the kernel gives up and sets the
 	                                header's overflow word to 2 (gsr_forward_overflowed). */
+	const gsr_fused_loss* fused_loss; /* forward (gsr_forward_render / gsr_forward_nosync) only, optional (null = off):
+	                                host pointer, read during the call */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
@@ -169,6 +188,7 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
  * rasterizer drops it (diff_gaussian_rasterization/__init__.py:114,139-140).
  * scratch: gsr_slam_loss_scratch_bytes() bytes, zero-filled ONCE by the caller, reusable across calls. */
 size_t gsr_slam_loss_scratch_bytes(int W, int H);
+size_t gsr_fused_loss_scratch_bytes(int W, int H);      /* scratch of gsr_fused_loss: per-tile partial sums + ticket */
 int gsr_slam_loss(int W, int H, const float* color, const float* depth, const float* opacity, const float* gt_color,
                   const float* gt_depth, const unsigned char* grad_mask, const float* exposure, float rgb_boundary_threshold,
                   float alpha, int use_depth, int opacity_weighted, float* dL_dcolor, float* dL_ddepth, float* sums,

@@ -192,3 +192,88 @@ def test_mapping_window_with_fused_loss_matches_per_view_autograd():
     for k, mine in (("dL_dmeans3D", eng.g_means3D), ("dL_dsh", eng.g_sh), ("dL_dopacity", eng.g_opacity), ("dL_dscales", eng.g_scales),
                     ("dL_drotations", eng.g_rot)):
         assert rel_err(mine.cpu().numpy(), expect[k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize("mode", ["track_rgbd", "track_mono", "map_rgbd"])
+def test_loss_fused_into_the_forward_epilogue_matches_the_loss_kernel(mode):
+    """gsr_fused_loss: dL/dcolor, dL/ddepth and {loss, dL/da, dL/db} written by the forward compositing kernel's epilogue ==
+    the stand-alone loss kernel run on the images that forward produced; with and without lists ordered on demand."""
+    from diff_gaussian_rasterization import scenes as SC
+    from diff_gaussian_rasterization import slam_ops as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+    import diff_gaussian_rasterization as dgr
+
+    cfg = dict(W=328, H=250, fx=290.0, fy=290.0, cx=163.5, cy=124.5, P=20000, sh_degree=0)      # ragged: 328 = 20.5 tiles
+    sc = SC.make_scene(cfg, seed=5)
+    sc["scales"] = sc["scales"] * 1.5
+    t = SC.to_torch(sc, "cuda")
+    g = torch.Generator().manual_seed(3)
+    gt_c = torch.rand((3, cfg["H"], cfg["W"]), generator=g).cuda()
+    gt_c[:, :20] = 0.0                                                    # below the rgb boundary threshold
+    gt_d = (torch.rand((1, cfg["H"], cfg["W"]), generator=g) * 3).cuda()
+    gt_d[:, -30:] = 0.0                                                   # invalid depth
+    gmask = (torch.rand((cfg["H"], cfg["W"]), generator=g) > 0.3).to(torch.uint8).cuda()
+    expo = torch.tensor([0.03, -0.02], dtype=torch.float32, device="cuda")
+    tracking = mode.startswith("track")
+    depth = None if mode.endswith("mono") else gt_d
+    for lazy_min in (0, 64):
+        prev = dgr._L.gsr_sort_on_demand(lazy_min)
+        try:
+            eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                               cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=0)
+            eng.set_camera(RasterEngine.pack_camera(*(torch.from_numpy(sc[k]) for k in ("viewmatrix", "projmatrix", "projmatrix_raw", "campos"))).cuda())
+            eng.calibrate()
+            ws_f, ws_k = S.LossWorkspace(cfg["W"], cfg["H"]), S.LossWorkspace(cfg["W"], cfg["H"])
+            fl = S.FusedLoss(ws_f, gt_c, depth, gmask if tracking else None, expo, alpha=0.9, tracking=tracking)
+            for rep in range(3):                                          # the ticket must re-arm itself
+                ws_f.dL_dcolor.fill_(7.0); ws_f.dL_ddepth.fill_(7.0); ws_f.sums.fill_(7.0)
+                eng.launch_forward(fused_loss=fl.struct)
+                S.slam_loss(ws_k, eng.color, eng.depth, eng.opacity, gt_c, depth, gmask if tracking else None, expo, alpha=0.9,
+                            tracking=tracking)
+                torch.cuda.synchronize()
+                assert rel_err(ws_f.dL_dcolor.cpu().numpy(), ws_k.dL_dcolor.cpu().numpy()) <= 1e-6
+                assert rel_err(ws_f.dL_ddepth.cpu().numpy(), ws_k.dL_ddepth.cpu().numpy()) <= 1e-6
+                assert rel_err(ws_f.sums.cpu().numpy()[:3], ws_k.sums.cpu().numpy()[:3]) <= 1e-5
+        finally:
+            dgr._L.gsr_sort_on_demand(prev)
+
+
+def test_tracking_loop_with_fused_loss_follows_the_unfused_loop():
+    from diff_gaussian_rasterization import scenes as SC
+    from diff_gaussian_rasterization import slam_ops as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+
+    cfg = dict(W=320, H=240, fx=290.0, fy=290.0, cx=159.5, cy=119.5, P=20000, sh_degree=0)
+    sc = SC.make_scene(cfg, seed=5)
+    sc["scales"] = sc["scales"] * 1.5
+    t = SC.to_torch(sc, "cuda")
+
+    def engine():
+        return RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                            cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=0)
+
+    base = SC.base_pose()
+    target = SC.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], base)
+    eng = engine()
+    eng.set_camera(RasterEngine.pack_camera(*(torch.from_numpy(target[k]) for k in ("viewmatrix", "projmatrix", "projmatrix_raw", "campos"))).cuda())
+    eng.calibrate()
+    eng.launch_forward()
+    gt_color, gt_depth = eng.color.clone(), eng.depth.clone()
+    start = SC.se3_exp([0.01, -0.008, 0.012, 0.004, -0.003, 0.002]) @ base
+    gmask = torch.ones((cfg["H"], cfg["W"]), dtype=torch.uint8, device="cuda")
+
+    def run(fused, use_graph):
+        e = engine()
+        pose = S.PoseState(start[:3, :3], start[:3, 3], target["projmatrix_raw"])
+        loop = S.TrackingLoop(e, pose, gt_color, gt_depth, gmask, alpha=0.9, fused=fused)
+        e.calibrate()
+        n, first, overflow = loop.run(max_iters=40, check_every=40, use_graph=use_graph)
+        assert n == 40 and not overflow
+        return pose.RT.cpu().numpy().astype(np.float64), loop.ws.sums.cpu().numpy(), pose.exposure.cpu().numpy()
+
+    rt_u, sums_u, ex_u = run(False, True)
+    for use_graph in (True, False):
+        rt_f, sums_f, ex_f = run(True, use_graph)
+        assert rel_err(rt_f, rt_u) <= 1e-3
+        assert rel_err(sums_f[:3], sums_u[:3]) <= 5e-2           # the loss after 40 chaotic Adam steps: same ballpark
+        assert rel_err(ex_f, ex_u) <= 5e-2
