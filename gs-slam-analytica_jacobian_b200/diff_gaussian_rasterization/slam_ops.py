@@ -185,8 +185,10 @@ class MappingWindow:
     The isotropic scale regulariser (10 * |s - mean(s)|.mean(), :228-230) is a per-Gaussian torch expression outside the
     rasterizer path; callers add its gradient to the scale part of the flat buffer."""
 
-    def __init__(self, window, gt_colors, gt_depths=None, exposures=None, rgb_boundary_threshold=0.01, alpha=0.95, initialization=False):
-        """gt_colors [V,3,H,W], gt_depths [V,1,H,W] or None (monocular), exposures [V,2] device tensor or None."""
+    def __init__(self, window, gt_colors, gt_depths=None, exposures=None, rgb_boundary_threshold=0.01, alpha=0.95, initialization=False,
+                 fused=None):
+        """gt_colors [V,3,H,W], gt_depths [V,1,H,W] or None (monocular), exposures [V,2] device tensor or None.
+        fused (default: single-engine windows): the loss of every view is evaluated in its forward's epilogue."""
         self.win, self.eng = window, window.engine
         self.gt_colors, self.gt_depths, self.exposures = gt_colors, gt_depths, exposures
         self.kw = dict(rgb_boundary_threshold=rgb_boundary_threshold, alpha=alpha)
@@ -194,6 +196,22 @@ class MappingWindow:
         self.ws = LossWorkspace(self.eng.W, self.eng.H, self.eng.dev)
         n = max(len(window.views), 1)
         self.view_sums = torch.zeros((n, 4), dtype=torch.float32, device=self.eng.dev)    # per local view: loss, dL/da, dL/db, 0
+        self.fused = None
+        if fused is None:
+            fused = len(window.engines) == 1
+        if fused:
+            assert len(window.engines) == 1, "the fused loss writes into the one engine's upstream buffers"
+            self.fused = {}
+            for i, v in enumerate(window.views):
+                expo = None if (initialization or exposures is None) else exposures[v]
+
+                class _Slot:      # a LossWorkspace whose sums are this view's row and whose gradients are the engine's buffers
+                    pass
+                slot = _Slot()
+                slot.W, slot.H, slot.dev, slot.sums = self.eng.W, self.eng.H, self.eng.dev, self.view_sums[i]
+                slot.dL_dcolor, slot.dL_ddepth = self.eng.dL_dcolor, self.eng.dL_ddepth
+                self.fused[v] = FusedLoss(slot, gt_colors[v], None if gt_depths is None else gt_depths[v], None, expo, tracking=False,
+                                          **self.kw)
 
     def iteration(self, reduce=True, on_view=None):
         """Returns (grad_flat summed over all views of all ranks, per-local-view sums [n,4], per-local-view dL/dtau [n,6])."""
@@ -206,5 +224,6 @@ class MappingWindow:
             self.view_sums[local[v]].copy_(self.ws.sums, non_blocking=True)
             return eng.dL_dcolor, eng.dL_ddepth
 
-        flat = self.win.iteration(upstream, reduce=reduce, on_view=on_view)
+        flat = self.win.iteration(upstream, reduce=reduce, on_view=on_view,
+                                  fused_loss=None if self.fused is None else (lambda v: self.fused[v].struct))
         return flat, self.view_sums, self.win.tau

@@ -71,24 +71,31 @@ class KeyframeWindow:
                 e.set_camera(self.cameras[v])
                 e.calibrate()
 
-    def iteration(self, upstream, reduce=True, on_view=None, upstream_precomputed=False):
+    def iteration(self, upstream, reduce=True, on_view=None, upstream_precomputed=False, fused_loss=None):
         """One window iteration.  Returns engine.grad_flat (summed over all views of all ranks when
         reduce=True).  on_view(local_index, view) can read the engine's per-view outputs.
         upstream_precomputed=True: the upstream gradients do not depend on this iteration's renders and upstream() launches
         nothing -- every view's compositing backward then starts tile by tile behind its forward
-        (RasterEngine.launch_backward(overlap_forward=True))."""
+        (RasterEngine.launch_backward(overlap_forward=True)).
+        fused_loss: callable view -> _cabi.GsrFusedLoss writing into the engine's upstream buffers (slam_ops.FusedLoss): the
+        loss of every view is evaluated inside its forward, `upstream` is not called, the backward overlaps the forward
+        (single-engine windows)."""
         eng = self.engine
         if not self.views:
             eng.grad_flat.zero_()        # a rank without views still takes part in the collective
         if self.streams is None:
             for i, v in enumerate(self.views):
                 eng.set_camera(self.cameras[v])
-                eng.launch_forward()
-                if callable(upstream):
-                    gc, gd = upstream(v)
+                if fused_loss is not None:
+                    eng.launch_forward(fused_loss=fused_loss(v))
+                    eng.launch_backward(accumulate=(i > 0), overlap_forward=True)
                 else:
-                    gc, gd = upstream[0][v], upstream[1][v]
-                eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed)
+                    eng.launch_forward()
+                    if callable(upstream):
+                        gc, gd = upstream(v)
+                    else:
+                        gc, gd = upstream[0][v], upstream[1][v]
+                    eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed)
                 self.tau[i].copy_(eng.g_tau, non_blocking=True)
                 if on_view is not None:
                     on_view(i, v)

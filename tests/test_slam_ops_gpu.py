@@ -148,7 +148,8 @@ def test_tracking_loop_graph_converges_towards_the_target_pose():
     assert rel_err(rt_g, rt_e) <= 1e-3                                       # graph replay == eager launches (fp32 atomics aside)
 
 
-def test_mapping_window_with_fused_loss_matches_per_view_autograd():
+@pytest.mark.parametrize("fused", [True, False])
+def test_mapping_window_with_fused_loss_matches_per_view_autograd(fused):
     """MappingWindow (render -> fused mapping loss -> backward, accumulated over the window) == per-view rasterizer calls fed
     with the autograd gradients of the restated get_loss_mapping (utils/slam_utils.py:92-128), summed like autograd does."""
     from common import run_ours
@@ -172,7 +173,7 @@ def test_mapping_window_with_fused_loss_matches_per_view_autograd():
     expo = (torch.randn((V, 2), generator=g) * 0.05).cuda()
     win = KeyframeWindow(eng, torch.stack([pack(c) for c in cams]))
     win.calibrate()
-    mw = S.MappingWindow(win, gt_c, gt_d, expo, alpha=0.9)
+    mw = S.MappingWindow(win, gt_c, gt_d, expo, alpha=0.9, fused=fused)      # loss in the forward's epilogue / stand-alone kernel
     flat, sums, tau = mw.iteration()
     torch.cuda.synchronize()
     expect = {k: 0.0 for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations")}
