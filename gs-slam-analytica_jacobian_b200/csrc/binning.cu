@@ -2,15 +2,18 @@
 // (tile id, float bits of view depth), ties in ascending Gaussian id -- and the per-tile ranges
 // (reference: InclusiveSum + duplicateWithKeys + cub::DeviceRadixSort::SortPairs over 64-bit keys, 6 passes
 // of 24 B/instance + identifyTileRanges, cuda_rasterizer/rasterizer_impl.cu:70-138, 327-368), with a
-// tile-major pipeline of two kernels:
+// tile-major pipeline:
 //
 //   (preprocess)  every visible Gaussian adds 1 to the counters of the tiles in its rectangle (integer
 //                 REDs); the last preprocess CTA scans the counters into ranges[tile] and scatter cursors.
-//   1. scatter    four lanes walk each Gaussian's rectangle (large rectangles: the whole warp, 32 tiles per
-//                 step), claim a slot in the tile's segment with an integer atomic and stores (depth bits, id).
-//                 Segments come out contiguous per tile but unordered inside.
-//   2. tile sort  one CTA per tile sorts its segment in shared memory.  Fast path (lists that fit one chunk of
-//                 8 keys per thread): two stable single-chunk radix passes over the LEADING 18 of the depth bits
+//   1. scatter    two lanes walk each Gaussian's rectangle (large rectangles: the whole warp by load-balanced
+//                 expansion, for_each_tile in gsr_common.cuh), claim a slot in the tile's segment and store (depth
+//                 bits, id).  Segments come out contiguous per tile but unordered inside.
+//   2. order      BY DEFAULT the forward compositing kernel orders each tile's segment itself, on demand and only as
+//                 far as compositing reads it (render.cu); the kernels below run when complete lists
+//                 are asked for (gsr_sort_on_demand(0)) and some list is longer than one shared-memory chunk:
+//                 one CTA per tile sorts its segment in shared memory.  Fast path (lists that fit one chunk of
+//                 8 keys per thread): two stable single-chunk radix passes over the LEADING 16 of the depth bits
 //                 that differ inside the tile (min/max), ranks from warp match.any + per-warp counters (no
 //                 atomics, no counting sweep), then odd-even transposition sweeps on (depth, id) settle the low
 //                 bits and the id order of equal depths.  256-thread CTAs take lists up to 2048 entries; longer
@@ -20,9 +23,8 @@
 //                 stable LSD passes over the id digits, then every differing depth bit.
 //                 The result is the unique (tile, depth, id) order, i.e. the reference's list.
 //
-// HBM/L2 traffic per instance: 8 B scatter + 8 B read + 4 B list write = 20 B (reference: >= 144 B), and the
-// forward needs 4 kernel launches instead of 14.  Every kernel reads num_rendered-dependent quantities from
-// device memory, so the stage runs without the reference's blocking D2H read (rasterizer_impl.cu:331).
+// Every kernel reads num_rendered-dependent quantities from device memory, so the stage runs without the reference's
+// blocking D2H read (rasterizer_impl.cu:331).
 #include "tile_sort.cuh"
 
 namespace gsr {
@@ -30,16 +32,17 @@ namespace gsr {
 namespace {
 
 // ---- 1. scatter -------------------------------------------------------------------------------------
-// 256 Gaussians per CTA, FOUR lanes per Gaussian (1024 threads): the walk over a Gaussian's tile rectangle is a chain
+// 256 Gaussians per CTA, TWO lanes per Gaussian (512 threads): the walk over a Gaussian's tile rectangle is a chain
 // of dependent shared-memory atomics / stores per step, so its latency, not its instruction count, sets the pace --
-// four lanes cut the chain from ~30 steps per warp (the largest rectangle among 32 Gaussians) to ~8 and quadruple
-// the warps in flight (phase probe: pass 2 took 6.8 of the kernel's 15 us with one lane per Gaussian).
+// two lanes halve the chain (the largest rectangle among the warp's Gaussians) and double the warps in flight; four
+// lanes are more than one wave of CTAs at P = 100 k.  One thread per Gaussian with the balanced walk for every
+// rectangle was measured too: 5-8 % slower here (the kernel is bound by its partial-sector stores).
 constexpr int kScatterLanes = 2;
 constexpr int kScatterGauss = 256;                           // Gaussians per CTA
 constexpr int kScatterThreads = kScatterGauss * kScatterLanes;
 
-// visit the tiles of this thread's share of its Gaussian's rectangle: steps sub, sub + 4, ... of a row-major walk
-// (rectangles above kSoloTiles tiles: the whole warp, for the quad leader's Gaussian)
+// visit the tiles of this thread's share of its Gaussian's rectangle: steps sub, sub + kScatterLanes, ... of a row-major
+// walk (rectangles above kSoloTiles tiles: the whole warp, for the leading lane's Gaussian)
 template <typename F>
 __device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint32_t hi, int grid_x, uint32_t key, uint32_t id,
                                                    int sub, F&& f)

@@ -291,39 +291,4 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// ---- TMA (bulk async copy engine) staging: mbarrier + cp.async.bulk, global -> shared -------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-	asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
-{
-	asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-	             "r"(bytes)
-	             : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-	asm volatile(
-		"{ .reg .pred p;\n"
-		"W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@!p bra W; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-		"r"(parity)
-		: "memory");
-}
-// one bulk copy of `bytes` (multiple of 16, both sides 16-byte aligned) by the TMA unit; completion is signalled on `bar`
-__device__ __forceinline__ void tma_bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-		             (unsigned)__cvta_generic_to_shared(smem)),
-	             "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-	             : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 }  // namespace gsr

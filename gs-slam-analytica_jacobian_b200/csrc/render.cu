@@ -74,7 +74,7 @@ __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int 
 	}
 }
 
-// FUSED_SORT: the CTA sorts its tile's scattered (depth, id) segment itself (tile_sort.cuh) and composites straight from
+// MODE 1 / 2: the CTA sorts its tile's scattered (depth, id) segment itself (tile_sort.cuh) and composites straight from
 // the sorted ids it keeps in shared memory.  One launch less, no point_list round trip before the first gather, and the
 // latency-bound sort phases of one CTA overlap the issue-bound blending of the other CTAs on the SM.
 //
@@ -375,7 +375,6 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
 	const int tile = blockIdx.x;
 
-	constexpr bool FUSED_SORT = MODE != 0;
 	GSR_PROBE(3, 0);
 	// ---- the tile's list: complete, or ordered on demand (positions < lz->sorted_end are final) ----
 	uint2 range;
