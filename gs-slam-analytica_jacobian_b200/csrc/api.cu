@@ -23,6 +23,7 @@ std::atomic<unsigned long long> g_launches{0};   // kernels launched by this lib
 bool g_timing = false;
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
 const bool g_no_pdl = getenv("GSR_NO_PDL") != nullptr;                 // A/B switch: no programmatic dependent launches
+const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;         // A/B switch: forward not a programmatic dependent of the preprocess
 // lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
 // is sorted completely
 std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
@@ -186,7 +187,10 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	stage_mark(2, st);
 	int rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
-	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st);
+	// directly behind the cooperative preprocess + scatter (no kernel in between): start inside its tail
+	const bool behind_preprocess = scatter_done && fuse_sort && !g_timing && !a->debug && !g_no_pdl && !g_no_pdl_fwd;
+	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st,
+	                           behind_preprocess);
 	stage_mark(3, st);
 	g_launches += 1;
 	return debug_sync(a, st, "render");

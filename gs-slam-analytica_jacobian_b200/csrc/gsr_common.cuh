@@ -169,11 +169,13 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // Row index i / w inside a tile rectangle without a per-instance integer division: the owning lane computes
-// magic = ceil(2^32 / w) once per Gaussian; umulhi(i, magic) == i / w whenever i * w < 2^32 (guarded by n * w).
+// magic = ceil(2^32 / w) once per Gaussian; umulhi(i, magic) == i / w whenever i * w < 2^32 (guaranteed here by
+// n, w < 2^16).  ceil(2^32 / w) = floor((2^32 - 1) / w) + 1 for every w >= 2, so one 32-bit division does (the 64-bit
+// form was ~13 % of the scatter kernel's instructions at 3 M Gaussians and sits on the latency chain at 100 k).
 __device__ __forceinline__ uint32_t rect_magic(uint32_t w, uint32_t n)
 {
-	if (w < 2 || (unsigned long long)n * w >= (1ull << 32)) return 0;
-	return (uint32_t)(((1ull << 32) + w - 1) / w);
+	if (w < 2 || ((n | w) >> 16) != 0) return 0;
+	return 0xffffffffu / w + 1u;
 }
 __device__ __forceinline__ uint32_t rect_row(uint32_t i, uint32_t w, uint32_t magic)
 {
@@ -235,6 +237,80 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t 
 		}
 		before += __popc(starts);
 	}
+}
+
+// Cooperative vectorised load of ROWS rows of a [P,3] fp32 array (from row0) into shared memory, by the ROWS threads that
+// share threadIdx.x / ROWS: the whole 256-thread CTA (ROWS = 256) or one warp (ROWS = 32, synchronised by __syncwarp only).
+template <int ROWS = 256>
+__device__ __forceinline__ void load_rows3(const float* __restrict__ g, int row0, int P, float* s, bool vec_ok)
+{
+	const int t = threadIdx.x & (ROWS - 1);
+	const int n = max(0, min(ROWS, P - row0)) * 3;
+	const float* src = g + (size_t)row0 * 3;
+	if (vec_ok) {
+		const int n4 = n >> 2;
+		const float4* src4 = reinterpret_cast<const float4*>(src);
+		for (int i = t; i < n4; i += ROWS) reinterpret_cast<float4*>(s)[i] = __ldg(src4 + i);
+		for (int i = (n4 << 2) + t; i < n; i += ROWS) s[i] = __ldg(src + i);
+	} else {
+		for (int i = t; i < n; i += ROWS) s[i] = __ldg(src + i);
+	}
+}
+
+// The same for one warp's 32 rows in two halves, so that the loads can be issued together with the thread's other loads
+// and the shared-memory deposit (which waits for them) comes behind all of them: fetch -> registers, deposit -> shared.
+struct Rows3Regs {
+	float4 v;      // float4 number `lane` of the slice (vector path)
+	float t[3];    // scalar path / tail: elements lane, lane + 32, lane + 64 behind the vector part
+};
+__device__ __forceinline__ Rows3Regs fetch_rows3_warp(const float* __restrict__ g, int row0, int P, bool vec_ok)
+{
+	const int lane = threadIdx.x & 31;
+	const int n = max(0, min(32, P - row0)) * 3;
+	const float* src = g + (size_t)row0 * 3;
+	const int n4 = vec_ok ? (n >> 2) : 0;
+	Rows3Regs r;
+	r.v = lane < n4 ? __ldg(reinterpret_cast<const float4*>(src) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const int i = (n4 << 2) + lane + 32 * k;
+		r.t[k] = i < n ? __ldg(src + i) : 0.f;
+	}
+	return r;
+}
+__device__ __forceinline__ void deposit_rows3_warp(float* s, const Rows3Regs& r, int row0, int P, bool vec_ok)
+{
+	const int lane = threadIdx.x & 31;
+	const int n = max(0, min(32, P - row0)) * 3;
+	const int n4 = vec_ok ? (n >> 2) : 0;
+	if (lane < n4) reinterpret_cast<float4*>(s)[lane] = r.v;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const int i = (n4 << 2) + lane + 32 * k;
+		if (i < n) s[i] = r.t[k];
+	}
+}
+
+// The mirror image: ROWS rows of a [P,3] fp32 array staged in shared memory (row r at s[3r..3r+2]) go out as 16-byte
+// stores (full sectors) instead of three scalar stores per thread at a 12-byte stride.  accumulate: dst += rows (the
+// group owns its rows; views of a window run in stream order).  The caller synchronises the group between filling s and this.
+template <int ROWS = 256>
+__device__ __forceinline__ void store_rows3(float* __restrict__ g, int row0, int P, const float* s, bool vec_ok, bool accumulate)
+{
+	const int t = threadIdx.x & (ROWS - 1);
+	const int n = max(0, min(ROWS, P - row0)) * 3;
+	float* dst = g + (size_t)row0 * 3;
+	const int n4 = vec_ok ? (n >> 2) : 0;
+	float4* dst4 = reinterpret_cast<float4*>(dst);
+	for (int i = t; i < n4; i += ROWS) {
+		float4 v = reinterpret_cast<const float4*>(s)[i];
+		if (accumulate) {
+			const float4 o = dst4[i];
+			v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+		}
+		dst4[i] = v;
+	}
+	for (int i = (n4 << 2) + t; i < n; i += ROWS) dst[i] = accumulate ? dst[i] + s[i] : s[i];
 }
 
 // Optional phase probe (compile with -DGSR_PHASE_PROBE): thread 0 of every CTA records %globaltimer at phase

@@ -93,7 +93,7 @@ size_t tile_sort_smem_bytes(int cap_smem);
 // lazy_min > 0: lists longer than lazy_min are ordered on demand, slab by slab, as far as the compositing gets (render.cu)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
-                           cudaStream_t stream);
+                           cudaStream_t stream, bool behind_preprocess = false);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
                             const float* dL_dpix, const float* dL_dpix_depth, bool overlap_forward, cudaStream_t stream);
 void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,

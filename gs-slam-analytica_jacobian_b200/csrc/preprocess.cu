@@ -44,21 +44,6 @@ __device__ const float kSH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.
 __device__ const float kSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                    -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
-// Block-cooperative vectorised load of a [P,3] fp32 array slice (256 rows) into shared memory.
-__device__ __forceinline__ void load_rows3(const float* __restrict__ g, int row0, int P, float* s, bool vec_ok)
-{
-	const int n = min(256, P - row0) * 3;
-	const float* src = g + (size_t)row0 * 3;
-	if (vec_ok) {
-		const int n4 = n >> 2;
-		const float4* src4 = reinterpret_cast<const float4*>(src);
-		for (int i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(s)[i] = __ldg(src4 + i);
-		for (int i = (n4 << 2) + threadIdx.x; i < n; i += 256) s[i] = __ldg(src + i);
-	} else {
-		for (int i = threadIdx.x; i < n; i += 256) s[i] = __ldg(src + i);
-	}
-}
-
 __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 pos, float3 campos, unsigned& clamped)
 {
 	float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
@@ -306,6 +291,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			__threadfence();
 		}
 		__syncthreads();
+		pdl_launch_dependents();      // a forward compositing kernel launched as programmatic dependent may take its first slots
 		GSR_PROBE(0, 5);
 		// ---- every CTA: exclusive scan of the tile counters -> s_start[tile]; CTA 0 also publishes ranges etc. ----
 		uint32_t* s_start = s_hist + n_tiles;

@@ -99,51 +99,81 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __res
 	return dm;
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
                            float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
-                           float* __restrict__ dL_dcov3D_out, float* __restrict__ dL_dtau)
+                           float* __restrict__ dL_dcov3D_out, float* __restrict__ dL_dtau, int vec_mask)
 {
-	__shared__ float s_view[16], s_proj[16], s_raw[16];
+	// [P,3] arrays pass through shared memory as 32-row slices, one per warp, and cross the memory system as 16-byte
+	// accesses: rows[0] means3D in / dL_dmeans3D out, rows[1] scales in / dL_dscales out, rows[2] dL_dmeans2D, rows[3]
+	// dL_dcolors or dL_dsh (one coefficient).  Three scalar stores per array at a 12-byte stride touch every sector three
+	// times.  Everything up to the pose-gradient reduction is WARP-private (camera matrices included, __syncwarp only): the
+	// warps of a CTA drift apart, one warp's loads overlap another's arithmetic, nobody waits at a CTA barrier for the
+	// slowest warp (ncu at 3 M Gaussians with CTA-wide staging: 10 of 27 stall cycles per issue at barriers).
+	__shared__ __align__(16) float s_rows[4][768];
+	__shared__ float s_mat[8][48];
 	__shared__ float s_tau[8][6];
 	__shared__ bool s_last;
 	GSR_PROBE(2, 0);
-	if (threadIdx.x < 16) {
-		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
-		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
-		s_raw[threadIdx.x] = s.projmatrix_raw[threadIdx.x];
-	}
-	__syncthreads();
-	const float* vm = s_view;
-	const float* pj = s_proj;
-	const int idx = blockIdx.x * 256 + threadIdx.x;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	float mat_v = 0.f, mat_p = 0.f, mat_r = 0.f;
+	if (lane < 16) { mat_v = __ldg(s.viewmatrix + lane); mat_p = __ldg(s.projmatrix + lane); mat_r = __ldg(s.projmatrix_raw + lane); }
+	const int row0 = blockIdx.x * 256 + warp * 32;      // first row of this warp
+	float* const rows0 = s_rows[0] + 96 * warp;
+	float* const rows1 = s_rows[1] + 96 * warp;
+	float* const rows2 = s_rows[2] + 96 * warp;
+	float* const rows3 = s_rows[3] + 96 * warp;
+	// Every global input of this warp's Gaussians is requested up front, before visibility is known and before anything is
+	// consumed: the loads are in flight together instead of forming a chain of dependent round trips (rows -> radii ->
+	// accumulators), which is what bounds this kernel (few warps per SM, one long dependent computation per thread).
+	const Rows3Regs in_mean = fetch_rows3_warp(s.means3D, row0, s.P, vec_mask & 1);
+	Rows3Regs in_scale = {};
+	if (!s.cov3D_precomp) in_scale = fetch_rows3_warp(s.scales, row0, s.P, vec_mask & 2);
+	const float* vm = s_mat[warp];
+	const float* pj = s_mat[warp] + 16;
+	const float* s_raw = s_mat[warp] + 32;
+	const int idx = row0 + lane;
 	float tau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	const bool sh_rows = s.shs && s.M == 1;      // degree 0 (every shipped config): dL_dsh is a [P,3] array too
+	float dmean[3] = {0.f, 0.f, 0.f};
+	float dm2x = 0.f, dm2y = 0.f;
+	float dcol[3] = {0.f, 0.f, 0.f};             // dL_dcolors row, or the dL_dsh row when sh_rows
+	float dscale[3] = {0.f, 0.f, 0.f};
 
-	if (idx < s.P) {
-		float dmean[3] = {0.f, 0.f, 0.f};
-		float dm2x = 0.f, dm2y = 0.f, dopac = 0.f;
-		float dcol[3] = {0.f, 0.f, 0.f};
+	const bool in_range = idx < s.P;
+	int radius = 0;
+	float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (in_range) {
+		radius = radii[idx];
+		if (!s.cov3D_precomp) q_in = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
+	}
+	// Launched as a programmatic dependent of the compositing backward, this CTA may be resident while that kernel still
+	// runs: its own inputs are on their way; the accumulators are read behind the dependency (L2-coherent loads).
+	pdl_wait();
+	GaussAcc a;
+	a.a0 = make_float4(0.f, 0.f, 0.f, 0.f); a.a1 = a.a0; a.a2 = a.a0; a.a3 = a.a0;
+	if (in_range) {
+		a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
+	}
+	// the first consumers of any load: camera matrices and the [P,3] input rows go from registers to this warp's
+	// shared-memory slices (one row per lane)
+	if (lane < 16) { s_mat[warp][lane] = mat_v; s_mat[warp][16 + lane] = mat_p; s_mat[warp][32 + lane] = mat_r; }
+	deposit_rows3_warp(rows0, in_mean, row0, s.P, vec_mask & 1);
+	if (!s.cov3D_precomp) deposit_rows3_warp(rows1, in_scale, row0, s.P, vec_mask & 2);
+	__syncwarp();
+
+	if (in_range) {
+		float dopac = 0.f;
 		float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-		float dscale[3] = {0.f, 0.f, 0.f};
 		float drot[4] = {0.f, 0.f, 0.f, 0.f};
-		// Every global input of this Gaussian is requested up front, before its visibility is known: the loads are then in
-		// flight together instead of forming the chain radii -> (accumulator, parameters) of two dependent round trips,
-		// which is what bounds this kernel (few warps per SM, one long dependent computation per thread).
-		const int radius = radii[idx];
-		const float mx = __ldg(s.means3D + 3 * idx), my = __ldg(s.means3D + 3 * idx + 1), mz = __ldg(s.means3D + 3 * idx + 2);
-		float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+		const float mx = rows0[3 * lane], my = rows0[3 * lane + 1], mz = rows0[3 * lane + 2];
 		float sc_in[3] = {0.f, 0.f, 0.f};
 		if (!s.cov3D_precomp) {
-			q_in = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
 #pragma unroll
-			for (int i = 0; i < 3; i++) sc_in[i] = __ldg(s.scales + 3 * idx + i);
+			for (int i = 0; i < 3; i++) sc_in[i] = rows1[3 * lane + i];
 		}
-		// Launched as a programmatic dependent of the compositing backward, this CTA may be resident while that kernel still
-		// runs: its own inputs are on their way; the accumulators are read behind the dependency (L2-coherent loads).
-		pdl_wait();
-		GaussAcc a;
-		a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
 		const bool visible = radius > 0;
 		if (visible) {
 			GaussAcc z;
@@ -290,7 +320,17 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				tau[4] += ddepth * -pC[0];
 			}
 			// ---- SH (backward.cu:618-619) ----
-			if (s.shs) {
+			if (sh_rows) {
+				// degree 0: colour = C0 * sh + 0.5 does not depend on the view direction (backward.cu:21-145 with deg = 0)
+				if (dL_dcolors) {      // the colour gradient itself is wanted as well (rows[3] carries dL_dsh): direct stores
+					float* d = dL_dcolors + 3 * (size_t)idx;
+					if (s.accumulate_grads) { d[0] += dcol[0]; d[1] += dcol[1]; d[2] += dcol[2]; }
+					else { d[0] = dcol[0]; d[1] = dcol[1]; d[2] = dcol[2]; }
+				}
+				const unsigned cl = g.clamped[idx];
+				dcol[0] = (cl & 1) ? 0.f : bSH_C0 * dcol[0]; dcol[1] = (cl & 2) ? 0.f : bSH_C0 * dcol[1];
+				dcol[2] = (cl & 4) ? 0.f : bSH_C0 * dcol[2];
+			} else if (s.shs) {
 				const unsigned cl = g.clamped[idx];
 				const float dRGB[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
 				const float3 campos = {s.campos[0], s.campos[1], s.campos[2]};
@@ -326,33 +366,28 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				drot[3] = 2 * r * (Gm[0][1] - Gm[1][0]) + 2 * x * (Gm[2][0] + Gm[0][2]) + 2 * y * (Gm[1][2] + Gm[2][1]) - 4 * zq * (Gm[1][1] + Gm[0][0]);
 			}
 		} else if (s.shs && !s.accumulate_grads) {
-			for (int i = 0; i < s.M * 3; i++) dL_dsh[(size_t)idx * s.M * 3 + i] = 0.f;
+			if (!sh_rows) {
+				for (int i = 0; i < s.M * 3; i++) dL_dsh[(size_t)idx * s.M * 3 + i] = 0.f;
+			} else if (dL_dcolors) {
+				dL_dcolors[3 * (size_t)idx] = 0.f; dL_dcolors[3 * (size_t)idx + 1] = 0.f; dL_dcolors[3 * (size_t)idx + 2] = 0.f;
+			}
 		}
-		dL_dmeans2D[3 * idx] = dm2x; dL_dmeans2D[3 * idx + 1] = dm2y; dL_dmeans2D[3 * idx + 2] = 0.f;
 		if (visible) {      // densification statistics (gaussian_model.py:767-771, slam_backend.py:115-121)
 			if (s.densify_grad_accum) s.densify_grad_accum[idx] += sqrtf(dm2x * dm2x + dm2y * dm2y);
 			if (s.densify_denom) s.densify_denom[idx] += 1.f;
 			if (s.max_radii2D) s.max_radii2D[idx] = fmaxf(s.max_radii2D[idx], (float)radii[idx]);
 		}
 		if (!s.accumulate_grads) {
-			dL_dmeans3D[3 * idx] = dmean[0]; dL_dmeans3D[3 * idx + 1] = dmean[1]; dL_dmeans3D[3 * idx + 2] = dmean[2];
 			dL_dopacity[idx] = dopac;
-			if (dL_dcolors) { dL_dcolors[3 * idx] = dcol[0]; dL_dcolors[3 * idx + 1] = dcol[1]; dL_dcolors[3 * idx + 2] = dcol[2]; }
-			if (s.scales) {
-				dL_dscales[3 * idx] = dscale[0]; dL_dscales[3 * idx + 1] = dscale[1]; dL_dscales[3 * idx + 2] = dscale[2];
-				reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
-			}
+			if (s.scales) reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
 			if (dL_dcov3D_out) {
 #pragma unroll
 				for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] = dcov[i];
 			}
 		} else if (visible) {
 			// window accumulation: this thread owns row idx, plain read-modify-write (views run in stream order)
-			dL_dmeans3D[3 * idx] += dmean[0]; dL_dmeans3D[3 * idx + 1] += dmean[1]; dL_dmeans3D[3 * idx + 2] += dmean[2];
 			dL_dopacity[idx] += dopac;
-			if (dL_dcolors) { dL_dcolors[3 * idx] += dcol[0]; dL_dcolors[3 * idx + 1] += dcol[1]; dL_dcolors[3 * idx + 2] += dcol[2]; }
 			if (s.scales) {
-				dL_dscales[3 * idx] += dscale[0]; dL_dscales[3 * idx + 1] += dscale[1]; dL_dscales[3 * idx + 2] += dscale[2];
 				float4 rr = reinterpret_cast<float4*>(dL_drot)[idx];
 				rr.x += drot[0]; rr.y += drot[1]; rr.z += drot[2]; rr.w += drot[3];
 				reinterpret_cast<float4*>(dL_drot)[idx] = rr;
@@ -362,6 +397,26 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] += dcov[i];
 			}
 		}
+	}
+
+	// ---- the [P,3] outputs: rows into shared memory, out as 16-byte stores (rows of culled Gaussians are zero: they are
+	// written when every row is, and adding them in a window accumulation changes nothing) ----
+	__syncwarp();      // every lane has taken its inputs out of rows0, rows1
+	{
+		const int t3 = 3 * lane;
+		rows0[t3] = dmean[0]; rows0[t3 + 1] = dmean[1]; rows0[t3 + 2] = dmean[2];
+		rows1[t3] = dscale[0]; rows1[t3 + 1] = dscale[1]; rows1[t3 + 2] = dscale[2];
+		rows2[t3] = dm2x; rows2[t3 + 1] = dm2y; rows2[t3 + 2] = 0.f;
+		rows3[t3] = dcol[0]; rows3[t3 + 1] = dcol[1]; rows3[t3 + 2] = dcol[2];
+	}
+	__syncwarp();
+	{
+		const bool accum = s.accumulate_grads != 0;
+		store_rows3<32>(dL_dmeans2D, row0, s.P, rows2, vec_mask & 4, false);
+		store_rows3<32>(dL_dmeans3D, row0, s.P, rows0, vec_mask & 8, accum);
+		if (s.scales) store_rows3<32>(dL_dscales, row0, s.P, rows1, vec_mask & 16, accum);
+		if (sh_rows) store_rows3<32>(dL_dsh, row0, s.P, rows3, vec_mask & 32, accum);
+		else if (dL_dcolors) store_rows3<32>(dL_dcolors, row0, s.P, rows3, vec_mask & 64, accum);
 	}
 
 	GSR_PROBE(2, 1);
@@ -433,8 +488,22 @@ void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* ra
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
 	cfg.numAttrs = behind_render_backward ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, preprocess_backward_kernel, s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity,
-	                   dL_dscales, dL_drotations, dL_dcov3D, dL_dtau);
+	auto a16 = [](const void* p) { return ((size_t)p & 15) == 0; };
+	const int vec_mask = (a16(s.means3D) ? 1 : 0) | (a16(s.scales) ? 2 : 0) | (a16(dL_dmeans2D) ? 4 : 0) | (a16(dL_dmeans3D) ? 8 : 0) |
+	                     (a16(dL_dscales) ? 16 : 0) | (a16(dL_dsh) ? 32 : 0) | (a16(dL_dcolors) ? 64 : 0);
+	// CTAs per SM the kernel is compiled for: one wave of latency-bound CTAs runs best without spills at 3 x 8 warps (80
+	// registers); several waves of them gain more from a fourth CTA per SM (64 registers, 48 bytes spilled) -- 3 M Gaussians
+	// 0.54 -> 0.47 ms, 500 k 0.086 -> 0.079 ms, 100 k 0.0166 -> 0.0176 ms.  GSR_PB_MINB overrides (A/B switch).
+	static const int minb_env = getenv("GSR_PB_MINB") ? atoi(getenv("GSR_PB_MINB")) : 0;
+	const int minb = minb_env ? minb_env : (s.P > 3 * 148 * 256 ? 4 : 3);
+#define GSR_PB_LAUNCH(B)                                                                                                          \
+	cudaLaunchKernelEx(&cfg, preprocess_backward_kernel<B>, s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, \
+	                   dL_dscales, dL_drotations, dL_dcov3D, dL_dtau, vec_mask)
+	if (minb == 2) GSR_PB_LAUNCH(2);
+	else if (minb == 4) GSR_PB_LAUNCH(4);
+	else if (minb == 5) GSR_PB_LAUNCH(5);
+	else GSR_PB_LAUNCH(3);
+#undef GSR_PB_LAUNCH
 }
 
 GSR_PROBE_READER(probe_read_preprocess_backward)

@@ -368,6 +368,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
                       uint32_t* __restrict__ cull_masks, FusedSortArgs fs, FusedLoss lf)
 {
 	pdl_launch_dependents();      // a backward launched as programmatic dependent may move in as soon as every tile has a CTA
+	pdl_wait();                   // launched as programmatic dependent of the cooperative preprocess: its lists are complete from here
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	static_assert(sizeof(FwdSmem) <= kFusedIdsOffset, "sorted ids must sit behind the compositing overlay");
 	FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
@@ -615,10 +616,19 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
-                           cudaStream_t stream)
+                           cudaStream_t stream, bool behind_preprocess)
 {
 	const int tiles = s.grid_x * s.grid_y;
 	if (tiles == 0) return;
+	// behind_preprocess: the cooperative preprocess + scatter kernel was launched just before on this stream and releases its
+	// dependents behind its grid barrier: the first forward CTAs are resident (and waiting) when it ends
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(256); cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = behind_preprocess ? 1 : 0;
 	FusedSortArgs fs;
 	fs.ranges = g.ranges; fs.pairs = b.pairs; fs.pairs_alt = b.pairs_alt; fs.point_list = b.point_list;
 	fs.capacity = (unsigned)R_capacity; fs.hdr = g.hdr; fs.tile_done = g.tile_done;
@@ -637,9 +647,10 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 #define GSR_FWD_LAUNCH(M, L)                                                                                                      \
 	do {                                                                                                                          \
 		ensure_dynamic_smem(render_forward_kernel<M, L>, smem, attr[2 * M + (L ? 1 : 0)]);                                        \
-		render_forward_kernel<M, L><<<tiles, 256, smem, stream>>>(g.ranges, b.point_list, g.rec, s.W, s.H, s.grid_x, s.background, \
-		                                                         im.final_T, im.n_contrib, out_color, out_depth, out_opacity,    \
-		                                                         n_touched, b.cull_masks, fs, lf);                                \
+		cfg.dynamicSmemBytes = smem;                                                                                              \
+		cudaLaunchKernelEx(&cfg, render_forward_kernel<M, L>, (const uint2*)g.ranges, (const uint32_t*)b.point_list,              \
+		                   (const GaussRec*)g.rec, s.W, s.H, s.grid_x, (const float*)s.background, im.final_T, im.n_contrib,      \
+		                   out_color, out_depth, out_opacity, n_touched, b.cull_masks, fs, lf);                                   \
 	} while (0)
 	if (s.has_loss) {
 		if (mode == 2) GSR_FWD_LAUNCH(2, true);
