@@ -68,13 +68,13 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 	const int idx = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
-		n = tiles_touched[idx];
-		if (n) {
-			const float4 q2 = rec[idx].q2;
-			lo = __float_as_uint(q2.z);
-			hi = __float_as_uint(q2.w);
-			key = __float_as_uint(rec[idx].q1.z);   // raw float bits of the view-space depth (rasterizer_impl.cu:104)
-		}
+		// one round trip: the rectangle (all zero for a culled Gaussian) gives the tile count itself, tiles_touched is not
+		// read first
+		const float4 q2 = __ldg(&rec[idx].q2);
+		key = __float_as_uint(__ldg(&rec[idx].q1.z));   // raw float bits of the view-space depth (rasterizer_impl.cu:104)
+		lo = __float_as_uint(q2.z);
+		hi = __float_as_uint(q2.w);
+		n = ((hi & 0xffff) - (lo & 0xffff)) * ((hi >> 16) - (lo >> 16));
 	}
 	extern __shared__ uint32_t s_tile[];          // [2][tiles]: CTA-local counts, then claimed bases (use_smem != 0)
 	uint32_t* s_cnt = s_tile;
