@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	__shared__ __align__(16) float s_mean[768];
 	__shared__ __align__(16) float s_scale[768];
 	__shared__ __align__(16) float s_col[768];
-	__shared__ float s_view[16], s_proj[16], s_cam[3];
+	__shared__ float s_view[16], s_proj[16];
 	__shared__ unsigned s_red[16];
 	__shared__ bool s_last;
 	extern __shared__ uint32_t s_hist[];   // [tiles] CTA-private tile histogram (hist_smem != 0)
@@ -117,16 +117,6 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	if (threadIdx.x < 16) {
 		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
 		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
-	} else if (threadIdx.x < 19 && s.campos) {
-		s_cam[threadIdx.x - 16] = s.campos[threadIdx.x - 16];
-	}
-	// the two per-Gaussian scalars / vectors that are not row-staged are requested here, together with the rows, instead of
-	// where the (rarely failing) culls have been passed: one round trip to memory instead of three in a row
-	float4 q_rot = make_float4(0.f, 0.f, 0.f, 0.f);
-	float opac_in = 0.f;
-	if (idx < s.P) {
-		if (!s.cov3D_precomp) q_rot = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
-		opac_in = __ldg(s.opacities + idx);
 	}
 	load_rows3(s.means3D, row0, s.P, s_mean, vec_mask & 1);
 	if (s.scales) load_rows3(s.scales, row0, s.P, s_scale, vec_mask & 2);
@@ -171,7 +161,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 				S.m[0][0] = mod * s_scale[3 * threadIdx.x];
 				S.m[1][1] = mod * s_scale[3 * threadIdx.x + 1];
 				S.m[2][2] = mod * s_scale[3 * threadIdx.x + 2];
-				const float4 q = q_rot;
+				const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
 				const float r = q.x, x = q.y, y = q.z, z = q.w;
 				M3 R;
 				R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
@@ -230,10 +220,10 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 					if (s.colors_precomp) {
 						rgb = make_float3(s_col[3 * threadIdx.x], s_col[3 * threadIdx.x + 1], s_col[3 * threadIdx.x + 2]);
 					} else if (s.M == 1) {
-						const float3 campos = {s_cam[0], s_cam[1], s_cam[2]};
+						const float3 campos = {__ldg(s.campos), __ldg(s.campos + 1), __ldg(s.campos + 2)};
 						rgb = sh_to_rgb(s.D, &s_col[3 * threadIdx.x], p_orig, campos, clamped);
 					} else {
-						const float3 campos = {s_cam[0], s_cam[1], s_cam[2]};
+						const float3 campos = {__ldg(s.campos), __ldg(s.campos + 1), __ldg(s.campos + 2)};
 						rgb = sh_to_rgb(s.D, s.shs + (size_t)idx * s.M * 3, p_orig, campos, clamped);
 					}
 					out_radius = mr;
@@ -243,7 +233,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 					rect_hi = rmaxx | (rmaxy << 16);
 					depth_bits = __float_as_uint(depth);
 					rec.q0 = make_float4(pix_x, pix_y, conic.x, conic.y);
-					rec.q1 = make_float4(conic.z, opac_in, depth, rgb.x);
+					rec.q1 = make_float4(conic.z, __ldg(s.opacities + idx), depth, rgb.x);
 					rec.q2 = make_float4(rgb.y, rgb.z, __uint_as_float(rect_lo), __uint_as_float(rect_hi));
 				}
 			}
