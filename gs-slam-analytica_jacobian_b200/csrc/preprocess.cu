@@ -90,6 +90,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 // is still in shared memory, so the separate scatter kernel's reload, its recount and the serial last-CTA scan fall away:
 // every CTA scans the (complete) tile counters redundantly, claims its slice of every touched tile with one global
 // atomic, and stores its (depth bits, id) pairs.
+constexpr int kFusedMaxTiles = 4096;      // tile counters one CTA scans / claims in registers (16 per thread)
 struct FusedScatterArgs {
 	uint2* pairs;          // binning workspace: [capacity] (depth bits, id)
 	unsigned capacity;
@@ -293,13 +294,29 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		__syncthreads();
 		pdl_launch_dependents();      // a forward compositing kernel launched as programmatic dependent may take its first slots
 		GSR_PROBE(0, 5);
+		// ---- claim this CTA's slice of every tile it touches (tile_cursor counts from 0: cleared by the memset).  The
+		// atomics need nothing of the scan below, so they are issued first and their round trip overlaps the scan's loads;
+		// the fused path takes at most kFusedMaxTiles tiles (fused_scatter_fits), i.e. kPer per thread ----
+		constexpr int kPer = kFusedMaxTiles / 256;
+		unsigned got[kPer];
+#pragma unroll
+		for (int k = 0; k < kPer; k++) {
+			const int t = (int)threadIdx.x + 256 * k;
+			const unsigned c = t < n_tiles ? s_hist[t] : 0u;
+			got[k] = c ? atomicAdd(&g.tile_cursor[t], c) : 0u;
+		}
 		// ---- every CTA: exclusive scan of the tile counters -> s_start[tile]; CTA 0 also publishes ranges etc. ----
 		uint32_t* s_start = s_hist + n_tiles;
 		{
 			const int per = (n_tiles + 255) / 256;
 			const int t0 = min(n_tiles, (int)threadIdx.x * per), t1 = min(n_tiles, t0 + per);
 			unsigned sum = 0;
-			for (int t = t0; t < t1; t++) sum += __ldcg(&g.tile_count[t]);
+			unsigned cnt[kPer];      // this thread's counters stay in registers for the second sweep
+#pragma unroll
+			for (int k = 0; k < kPer; k++) {
+				cnt[k] = (t0 + k < t1) ? __ldcg(&g.tile_count[t0 + k]) : 0u;
+				sum += cnt[k];
+			}
 			unsigned inc = sum;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
@@ -311,8 +328,11 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			unsigned run = inc - sum;
 			for (int w = 0; w < (int)(threadIdx.x >> 5); w++) run += s_red[w];
 			unsigned mx = 0;
-			for (int t = t0; t < t1; t++) {
-				const unsigned c = __ldcg(&g.tile_count[t]);
+#pragma unroll
+			for (int k = 0; k < kPer; k++) {
+				const int t = t0 + k;
+				if (t >= t1) break;
+				const unsigned c = cnt[k];
 				s_start[t] = run;
 				if (blockIdx.x == 0) {
 					g.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
@@ -324,11 +344,10 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 			if (blockIdx.x == 0 && mx) atomicMax(&g.hdr->max_tile_count, mx);
 		}
 		__syncthreads();
-		// ---- claim this CTA's slice of every tile it touches (tile_cursor counts from 0: cleared by the memset) ----
-		for (int t = threadIdx.x; t < n_tiles; t += 256) {
-			const unsigned c = s_hist[t];
-			if (c) s_start[t] += atomicAdd(&g.tile_cursor[t], c);
-			s_hist[t] = 0;
+#pragma unroll
+		for (int k = 0; k < kPer; k++) {
+			const int t = (int)threadIdx.x + 256 * k;
+			if (t < n_tiles) { s_start[t] += got[k]; s_hist[t] = 0; }
 		}
 		__syncthreads();
 		GSR_PROBE(0, 6);
@@ -410,7 +429,7 @@ static inline bool aligned16(const void* p) { return ((size_t)p & 15) == 0; }
 bool fused_scatter_fits(int P, int tiles)
 {
 	static const bool no_fuse = getenv("GSR_NO_FUSED_SCATTER") != nullptr;      // A/B switch for measurements
-	if (no_fuse || P <= 0 || tiles > 4096) return false;
+	if (no_fuse || P <= 0 || tiles > kFusedMaxTiles) return false;
 	int dev = 0, sms = 0, per_sm = 0, coop = 0;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

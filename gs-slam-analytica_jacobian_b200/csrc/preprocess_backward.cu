@@ -151,11 +151,18 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 	}
 	// Launched as a programmatic dependent of the compositing backward, this CTA may be resident while that kernel still
 	// runs: its own inputs are on their way; the accumulators are read behind the dependency (L2-coherent loads).
-	pdl_wait();
+	// kEarlyMath (the one-wave build, MINB == 3: every CTA moves into the tail of the compositing backward): the part of the
+	// arithmetic that needs no gradient -- covariance, projection, Jacobian -- runs BEFORE the dependency is waited for, so
+	// only the gradient half sits behind the compositing backward.  Multi-wave builds keep all loads in one round trip: most
+	// of their CTAs start after that kernel has finished, and a second round trip per CTA costs them more.
+	constexpr bool kEarlyMath = (MINB == 3);
 	GaussAcc a;
 	a.a0 = make_float4(0.f, 0.f, 0.f, 0.f); a.a1 = a.a0; a.a2 = a.a0; a.a3 = a.a0;
-	if (in_range) {
-		a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
+	if (!kEarlyMath) {
+		pdl_wait();
+		if (in_range) {
+			a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
+		}
 	}
 	// the first consumers of any load: camera matrices and the [P,3] input rows go from registers to this warp's
 	// shared-memory slices (one row per lane)
@@ -176,15 +183,6 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 		}
 		const bool visible = radius > 0;
 		if (visible) {
-			GaussAcc z;
-			z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
-			g.acc[idx] = z;   // consumed: ready for the next backward without a memset
-			dm2x = a.a0.x; dm2y = a.a0.y;
-			const float dcx = a.a0.z, dcy = a.a1.x, dcz = a.a1.y;
-			dopac = a.a2.x;
-			const float ddepth = a.a2.y;
-			dcol[0] = a.a2.z; dcol[1] = a.a3.x; dcol[2] = a.a3.y;
-
 			// ---- 3D covariance (recomputed; reference re-reads geomState.cov3D) ----
 			float c3[6];
 			float sc[3] = {0.f, 0.f, 0.f};
@@ -246,6 +244,21 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 			const float denom = ca * cc - cb * cb;
 			float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
 			const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+			// ---- the gradients arriving from the compositing backward ----
+			if (kEarlyMath) {
+				pdl_wait();
+				a.a0 = __ldcg(&g.acc[idx].a0); a.a1 = __ldcg(&g.acc[idx].a1); a.a2 = __ldcg(&g.acc[idx].a2); a.a3 = __ldcg(&g.acc[idx].a3);
+			}
+			{
+				GaussAcc z;
+				z.a0 = make_float4(0.f, 0.f, 0.f, 0.f); z.a1 = z.a0; z.a2 = z.a0; z.a3 = z.a0;
+				g.acc[idx] = z;   // consumed: ready for the next backward without a memset
+			}
+			dm2x = a.a0.x; dm2y = a.a0.y;
+			const float dcx = a.a0.z, dcy = a.a1.x, dcz = a.a1.y;
+			dopac = a.a2.x;
+			const float ddepth = a.a2.y;
+			dcol[0] = a.a2.z; dcol[1] = a.a3.x; dcol[2] = a.a3.y;
 			if (denom2inv != 0.f) {
 				dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
 				dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
@@ -420,6 +433,7 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 	}
 
 	GSR_PROBE(2, 1);
+	if (kEarlyMath) pdl_wait();      // lanes without a visible Gaussian have not waited yet: no CTA ends before its predecessor
 	// ---- block-level 6-vector reduction of the pose gradient ----
 #pragma unroll
 	for (int i = 0; i < 6; i++) tau[i] = warp_sum(tau[i]);
