@@ -59,7 +59,7 @@ __device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint
 }
 
 __global__ void __launch_bounds__(kScatterThreads, 4)
-scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restrict__ tiles_touched, int grid_x,
+scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
                uint32_t* __restrict__ cursor, uint2* __restrict__ pairs, unsigned capacity, GeomHeader* hdr,
                int n_tiles, int use_smem)
 {
@@ -68,8 +68,7 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restri
 	const int idx = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
-		// one round trip: the rectangle (all zero for a culled Gaussian) gives the tile count itself, tiles_touched is not
-		// read first
+		// one round trip: the rectangle (all zero for a culled Gaussian) gives the tile count itself
 		const float4 q2 = __ldg(&rec[idx].q2);
 		key = __float_as_uint(__ldg(&rec[idx].q1.z));   // raw float bits of the view-space depth (rasterizer_impl.cu:104)
 		lo = __float_as_uint(q2.z);
@@ -155,7 +154,7 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel, scatter_smem, scatter_attr);
 	if (!scatter_done)
 		scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
-		s.P, g.rec, g.tiles_touched, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
+		s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
 	if (fuse_sort) return scatter_done ? 0 : 1;      // the forward compositing kernel sorts its own tile
 	int id_bits = 1;
 	while (id_bits < 32 && (1ll << id_bits) < (long long)s.P) id_bits++;
