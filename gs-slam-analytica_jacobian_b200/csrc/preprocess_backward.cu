@@ -9,6 +9,9 @@
 // dL/dtau: warp shuffle -> shared memory -> one partial per CTA -> the last CTA to finish sums the
 // partials in index order, so the result is deterministic (the reference's is not needed to be:
 // it sums a [P,6] tensor).
+// Memory access: every global load of a warp's 32 Gaussians is issued before the first instruction that consumes one;
+// [P,3] arrays cross the memory system as 16-byte accesses through warp-private shared-memory row slices; nothing is
+// CTA-wide before the pose reduction.  3 M Gaussians: 0.21 ms, 3.3 TB/s of DRAM traffic (ncu, profiles/r1k_ncu_full_C4.md).
 #include "gsr_params.h"
 
 namespace gsr {
