@@ -56,7 +56,7 @@ struct GeomView {
 	GeomHeader* hdr;
 	uint32_t* tile_count;    // [tiles]  instances per tile (integer REDs in the preprocess); zeroed with the header
 	uint32_t* tile_cursor;   // [tiles]  write cursor of the scatter pass (starts at ranges[tile].x)
-	uint32_t* tile_done;     // [tiles]  1 once the forward compositing CTA of the tile has published its results (cleared with the
+	uint32_t* tile_done;     // [tiles]  deepest contributor + 1 (never 0) once the forward compositing CTA of the tile has published its results (cleared with the
 	                         //          header): lets a backward launched as a programmatic dependent start tile by tile
 	uint2* ranges;           // [tiles]  (start, end) of every tile's list inside point_list
 	uint32_t* long_tiles;    // [tiles]  ids of the tiles whose lists go to the long-list sort kernel

@@ -607,9 +607,20 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 			if (threadIdx.x == 0) *lf.ticket = 0;
 		}
 	}
-	// publish the tile: everything the backward reads of it (final_T, n_contrib, point_list, cull_masks) is written
+	// publish the tile: everything the backward reads of it (final_T, n_contrib, point_list, cull_masks) is written.  The flag
+	// carries the tile's deepest contributor (+ 1, so that it is never 0): the backward CTA knows how far to walk the list
+	// the moment it has acquired the flag and starts its first gather without waiting for its own n_contrib loads.
+	{
+		const unsigned wtop = __reduce_max_sync(kFull, inside ? (unsigned)(last + 1) : 0u);
+		if (lane == 0) sm.tmask[warp][31] = wtop;      // word 31 of a warp's row: not part of the loss scratch (floats 0..30, 32)
+	}
 	__syncthreads();
-	if (threadIdx.x == 0) st_release_u32(fs.tile_done + tile, 1u);      // cumulative: orders the CTA's writes behind the barrier
+	if (threadIdx.x == 0) {
+		unsigned top = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) top = max(top, sm.tmask[w][31]);
+		st_release_u32(fs.tile_done + tile, top + 1u);      // cumulative: orders the CTA's writes behind the barrier
+	}
 }
 
 }  // namespace

@@ -162,14 +162,19 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	// upstream_ready (optional): a word that whoever delivers dL/dpixel sets behind the data (e.g. the last of the host-to-device
 	// copies of a step on another stream): the dependency on it then need not be a full edge in front of this kernel.
 	// The spins are bounded (~1 s): a flag that never comes is reported through the header, not by hanging the GPU.
+	// The flag's value is the tile's deepest contributor + 1 (the forward CTA knows it): how far the list has to be walked
+	// (backward.cu:763) is known here, and the first gather is on its way before this CTA's own n_contrib loads are back.
 	if (threadIdx.x == 0) {
 		int spins = 0;
-		while (ld_acquire_u32(tile_done + tile) == 0 && ++spins < (1 << 22)) __nanosleep(200);
+		uint32_t v;
+		while ((v = ld_acquire_u32(tile_done + tile)) == 0 && ++spins < (1 << 22)) __nanosleep(200);
 		if (upstream_ready)
 			while (ld_acquire_u32(upstream_ready) == 0 && ++spins < (1 << 22)) __nanosleep(200);
 		if (spins >= (1 << 22)) hdr->overflow = 2;
+		sm.wmax[0] = v ? v - 1u : 0u;
 	}
 	__syncthreads();
+	const uint32_t top = sm.wmax[0];
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -191,24 +196,6 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		s.dp0 = __ldcg(dL_dpix + pix); s.dp1 = __ldcg(dL_dpix + HW + pix); s.dp2 = __ldcg(dL_dpix + 2 * HW + pix);
 		s.dpd = __ldcg(dL_dpix_depth + pix);
 	}
-	sm.dpix[warp][lane] = make_float4(s.dp0, s.dp1, s.dp2, s.dpd);
-	s.c_bg = -T_final * (bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2);
-	s.beta = 0.f;
-	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-	float2* panel = sm.panel[warp];
-	QueueRec* wq = sm.queue[warp];
-
-	// entries behind the tile's deepest contributor can never contribute (backward.cu:763)
-	uint32_t m = (uint32_t)s.last_contributor;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
-	if (lane == 0) sm.wmax[warp] = m;
-	__syncthreads();
-	uint32_t top = 0;
-#pragma unroll
-	for (int w = 0; w < 8; w++) top = max(top, sm.wmax[w]);
-	const uint32_t warp_top = m;   // this warp's deepest contributor
-
 	// The list is walked back to front in groups of 32 positions aligned like the forward's cull chunks, so that the
 	// forward's ballots (cull_masks) can be replayed: batch b covers positions [hi_b - kBatch, hi_b) with
 	// hi_b = top32 - kBatch b (a multiple of 32); smem slot t <-> position hi_b - 1 - t.
@@ -229,6 +216,17 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		cp_async_commit();
 	};
 	if (rounds > 0) stage(0, 0);
+	// (the first consumers of the per-pixel loads come behind the first gather's requests)
+	sm.dpix[warp][lane] = make_float4(s.dp0, s.dp1, s.dp2, s.dpd);
+	s.c_bg = -T_final * (bg[0] * s.dp0 + bg[1] * s.dp1 + bg[2] * s.dp2);
+	s.beta = 0.f;
+	const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+	float2* panel = sm.panel[warp];
+	QueueRec* wq = sm.queue[warp];
+
+	// entries behind the deepest contributor of the tile (top) / of this warp's pixels can never contribute (backward.cu:763)
+	const uint32_t warp_top = __reduce_max_sync(kFull, (uint32_t)s.last_contributor);
+
 
 	int head = 0, qn = 0;   // ring queue: qn entries starting at slot head (head is a multiple of kSlots)
 	for (int b = 0; b < rounds; b++) {
