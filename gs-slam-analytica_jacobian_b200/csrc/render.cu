@@ -359,8 +359,11 @@ __device__ __noinline__ void sort_whole_tile(int tile, FusedSortArgs fs, int ids
 // LOSS: the view's SLAM loss (slam_ops.cu slam_loss_kernel, same arithmetic) is evaluated in the epilogue from the pixel values
 // still in registers: dL/dcolor, dL/ddepth and the per-tile partial sums of {loss, dL/da, dL/db}; the last CTA adds the
 // partials in tile order.
+#ifndef GSR_FWD_MINB
+#define GSR_FWD_MINB 4      // CTAs per SM the forward compositing kernel is compiled for (experiments: GSR_EXTRA_NVCC_FLAGS=-DGSR_FWD_MINB=3)
+#endif
 template <int MODE, bool LOSS>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, GSR_FWD_MINB)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
