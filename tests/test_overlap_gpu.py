@@ -108,3 +108,50 @@ def test_window_views_overlap_their_own_forward():
         torch.cuda.synchronize()
         assert rel_err(f1.cpu().numpy(), f0.cpu().numpy()) <= 2e-5
         assert rel_err(w1.tau.cpu().numpy(), w0.tau.cpu().numpy()) <= 2e-5
+
+
+_CHAIN_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "gs-slam-analytica_jacobian_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch
+from test_overlap_gpu import _engine, _snapshot
+eng, cams, _ = _engine(P=40000, overlap=True)
+out = {}
+for rep in range(3):
+    for i, c in enumerate(cams[:6]):
+        eng.set_camera(c)
+        eng.step(use_graph=bool(rep))          # eager first, then graph replays chasing each other
+        if rep == 2:
+            for k, v in _snapshot(eng).items():
+                out["%s_%d" % (k, i)] = v
+assert eng.header()[1] is False
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_programmatic_launch_chain_matches_serialised_launches(tmp_path):
+    """The whole chain of programmatic dependent launches (preprocess -> compositing forward -> compositing backward ->
+    per-Gaussian backward with its arithmetic in front of the dependency wait) against the same library with every launch
+    fully serialised (GSR_NO_PDL=1, read when the library is loaded: two fresh processes)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env_extra in (("chain", {}), ("serial", {"GSR_NO_PDL": "1"})):
+        env = dict(os.environ)
+        env.pop("GSR_NO_PDL", None)
+        env.update(env_extra)
+        path = str(tmp_path / (name + ".npz"))
+        r = subprocess.run([sys.executable, "-c", _CHAIN_SCRIPT, root, path], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[name] = dict(np.load(path))
+    assert set(res["chain"]) == set(res["serial"]) and len(res["chain"]) == 7 * 6
+    for k, a in res["chain"].items():
+        b = res["serial"][k]
+        if k.split("_")[0] in ("color", "depth", "n"):      # forward products: bit-identical
+            assert np.array_equal(a, b), k
+        else:
+            assert rel_err(a, b) <= 2e-5, k
