@@ -49,9 +49,9 @@ __device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint
 {
 	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, w = (hi & 0xffff) - x0;
 	if (n != 0 && n <= kSoloTiles) {
-		const uint32_t magic = rect_magic(w, n);
+		const float rcp = rect_rcp(w);
 		for (uint32_t i = sub; i < n; i += kScatterLanes) {
-			const uint32_t ty = rect_row(i, w, magic), tx = i - ty * w;
+			const uint32_t ty = rect_row(i, rcp), tx = i - ty * w;
 			f((y0 + ty) * grid_x + (x0 + tx), key, id);
 		}
 	}

@@ -168,19 +168,15 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
-// Row index i / w inside a tile rectangle without a per-instance integer division: the owning lane computes
-// magic = ceil(2^32 / w) once per Gaussian; umulhi(i, magic) == i / w whenever i * w < 2^32 (guaranteed here by
-// n, w < 2^16).  ceil(2^32 / w) = floor((2^32 - 1) / w) + 1 for every w >= 2, so one 32-bit division does (the 64-bit
-// form was ~13 % of the scatter kernel's instructions at 3 M Gaussians and sits on the latency chain at 100 k).
-__device__ __forceinline__ uint32_t rect_magic(uint32_t w, uint32_t n)
+// Row index i / w inside a tile rectangle without a per-instance integer division and without special cases in the walk
+// loops: floor((i + 0.5) / w) evaluated in fp32 as (float(i) + 0.5f) * fl(1 / w).  (i + 0.5) / w is at least 0.5 / w away
+// from the next integer and the two roundings move it by less than (i / w) * 2^-22, so the truncation is exact while a
+// rectangle holds fewer than 2^22 tiles (a 32 k x 32 k image has 2^22 tiles in all); checked exhaustively for w <= 512.
+// The owning lane computes the reciprocal once per Gaussian.
+__device__ __forceinline__ float rect_rcp(uint32_t w) { return __frcp_rn((float)w); }
+__device__ __forceinline__ uint32_t rect_row(uint32_t i, float rcp)
 {
-	if (w < 2 || ((n | w) >> 16) != 0) return 0;
-	return 0xffffffffu / w + 1u;
-}
-__device__ __forceinline__ uint32_t rect_row(uint32_t i, uint32_t w, uint32_t magic)
-{
-	if (w == 1) return i;
-	return magic ? __umulhi(i, magic) : i / w;
+	return (uint32_t)__fmul_rn(__fadd_rn((float)i, 0.5f), rcp);
 }
 
 // Visit every tile of the rectangles held by the lanes of a warp (n = tile count of this lane's Gaussian, 0 = none;
@@ -209,7 +205,7 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t 
 	const uint32_t d_lo = __shfl_sync(kAll, lo, src0), d_hi = __shfl_sync(kAll, hi, src0);
 	const uint32_t d_key = __shfl_sync(kAll, key, src0), d_id = __shfl_sync(kAll, id, src0);
 	const uint32_t x0 = d_lo & 0xffff, y0 = d_lo >> 16, w = (d_hi & 0xffff) - x0;
-	const uint32_t magic = rect_magic(w, d_n);
+	const float rcp = rect_rcp(w);
 	const uint32_t first = y0 * (uint32_t)grid_x + x0;
 	uint32_t inc = d_n;
 #pragma unroll
@@ -226,13 +222,14 @@ __device__ __forceinline__ void for_each_tile(uint32_t n, uint32_t lo, uint32_t 
 		const unsigned c = before + __popc(starts & (kAll >> (31 - lane)));      // segments starting at or before position base + lane
 		const int src = (int)c - 1;                           // >= 0: position 0 belongs to dense lane 0
 		const uint32_t s_off = __shfl_sync(kAll, off, src);
-		const uint32_t s_w = __shfl_sync(kAll, w, src), s_magic = __shfl_sync(kAll, magic, src);
+		const uint32_t s_w = __shfl_sync(kAll, w, src);
+		const float s_rcp = __shfl_sync(kAll, rcp, src);
 		const uint32_t s_first = __shfl_sync(kAll, first, src);
 		const uint32_t s_key = __shfl_sync(kAll, d_key, src), s_id = __shfl_sync(kAll, d_id, src);
 		const uint32_t k = base + lane;
 		if (k < total) {
 			const uint32_t i = k - s_off;
-			const uint32_t ty = rect_row(i, s_w, s_magic), tx = i - ty * s_w;
+			const uint32_t ty = rect_row(i, s_rcp), tx = i - ty * s_w;
 			f(s_first + ty * (uint32_t)grid_x + tx, s_key, s_id);
 		}
 		before += __popc(starts);

@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	}
 	GSR_PROBE(0, 2);
 	// per-tile instance counts (integer REDs): small rectangles lane-parallel, large ones warp-cooperative
-	for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) {
-		if (hist_smem) atomicAdd(&s_hist[tile], 1u);
-		else atomicAdd(&g.tile_count[tile], 1u);
-	});
+	// (two copies of the walk: the choice of the counter array stays out of its loop)
+	if (FUSED_SCATTER || hist_smem) for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_hist[tile], 1u); });
+	else for_each_tile(my_tiles, rect_lo, rect_hi, s.grid_x, 0u, 0u, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&g.tile_count[tile], 1u); });
 	GSR_PROBE(0, 3);
 	// block totals -> header (integer atomics: deterministic); issued BEFORE the histogram flush so that one fence
 	// covers every global update of this CTA
