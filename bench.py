@@ -1,25 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the hot path (BASELINE.json: "fwd+bwd raster iters/s incl. pose
-dL/dtau; % of HBM roofline").
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: "fwd+bwd raster iters/s incl. pose dL/dtau, 1/2/4/8 B200;
+% of HBM roofline").
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C1_tum_tracking]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2_replica_mapping]
 
-A *step* is one tracking iteration of the C1 workload (TUM fr1/desk shape, 640x480,
-100 000 Gaussians, one view): forward rasterization + backward incl. dL/dtau at a pose that changes every
-step; the loss is excluded (dL/dpixel tensors are pre-generated, seed 1).  With N > 1 every rank runs its
-own independent pose stream on the same map (pose-parallel batched tracking, weak scaling, no data-path
-collective -- SURVEY.md §8(e)); value = total iterations of all ranks / max-over-ranks device time.
+Default workload, for EVERY N (the driver must measure the multi-GPU mapping path): C2 = Replica-shaped RGB-D
+mapping, 1200x680, 500 000 Gaussians, 10-keyframe window.  A *step* is one window iteration (utils/slam_backend.py:160-232):
+forward + backward incl. dL/dtau of all 10 views through one replicated map, per-Gaussian gradients summed over the views;
+the loss is excluded from `value` (dL/dpixel tensors are pre-generated, seed 1).  The views are sharded over the N ranks
+(whole keyframes round robin, left-over keyframes split into bands of tile rows, window.py) and the packed gradient buffer
+is summed by ONE NCCL all-reduce inside the timed region: strong scaling, value = window iterations/s of the whole job
+(max-over-ranks device time).  At N = 1 the line also carries `also_C1`: the C1 tracking step (640x480, 100 k Gaussians,
+one view, pose perturbed every step), last round's headline.
 
   value     device-timed (CUDA events per step, L2 flushed between steps) with everything resident in HBM
-  e2e       same step driven from HOST buffers: pinned camera block + pinned dL/dpixel images are copied
-            H2D and dL/dtau + the forward header are copied D2H inside the timed region, host blocks on
-            every step (the next pose depends on dL/dtau)
-  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle port (oracle/gs_oracle.c, OpenMP) on one iteration of the same workload
+  e2e       the same iteration through the public host-driven call: slam_ops.MappingWindow.iteration -- camera blocks of
+            all keyframes copied H2D from pinned memory, loss of every view evaluated in its forward's epilogue (dL/dpixel
+            produced on the device, as a mapping iteration does), backward, all-reduce, per-view losses + dL/dtau + the
+            gradient norm copied D2H; host blocks on every step.  (C1: RasterEngine.step_host, pinned pose + dL/dpixel.)
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json; the per-instance
+            gather terms are charged on the instances the kernels actually consume (R_consumed = sum over tiles of the
+            deepest contributor), not on the whole lists
+  cpu_baseline  the CPU oracle port (oracle/gs_oracle.c, OpenMP) on a bounded sample of the same workload (N = 1 only)
 --impl reference: the reference's own implementation of the path on this box.  The reference path has no
 CPU implementation (it IS a CUDA extension), so this arm drives the UNMODIFIED reference kernels compiled
 for sm_100a (oracle/_ref/libgsref.so) on the GPU, including the zero-fills and the torch.sum its binding
-performs; if that library is absent it times the CPU oracle port instead.
+performs and autograd's accumulation over the views; if that library is absent it times the CPU oracle port instead.
 """
 import argparse
 import ctypes as C
@@ -40,6 +46,23 @@ import torch  # noqa: E402
 
 METRIC = "fwd+bwd raster iters/s incl. pose dL/dtau"
 UNIT = "iters/s"
+WINDOW_METRIC = "fwd+bwd raster window iters/s incl. pose dL/dtau"
+WINDOW_UNIT = "window iters/s"
+DEFAULT_WORKLOAD = "C2_replica_mapping"
+L2_NOTE = "flushed between steps (256 MiB fill, outside the per-step events)"
+
+
+def workload_config(name, V=None):
+    """The `config` object of the JSON line: identical in both arms (the driver compares them)."""
+    import scenes as S
+
+    cfg = S.CONFIGS[name]
+    if name.startswith(("C0", "C1")):
+        what = "1 view/step, pose perturbed every step"
+    else:
+        what = "V=%d views/step over one replicated map, per-Gaussian gradients summed over the views" % (V or cfg["V"])
+    return {"workload": "%s: %dx%d, P=%d Gaussians, SH deg %d, %s" % (name, cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"], what),
+            "l2": L2_NOTE}
 
 
 def log(*a):
@@ -97,7 +120,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------
 def build_workload(name, steps_total, rank, device):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     cfg = S.CONFIGS[name]
@@ -127,20 +150,45 @@ def l2_flusher(device):
     return flush
 
 
-def roofline_bytes(P, R, HW, fused_sort=False, fused_scatter=False):
-    """Algorithmic bytes per stage (SH degree 0).  The 44 B/instance of binning are 12 (write key +
-    value) + 24 (one ideal sort pass: 12 read + 12 write) + 8 (key read for the ranges); when the forward compositing
-    kernel sorts its own tile (lists <= 2048 entries) the "binning" stage is the scatter alone and the sort + range
-    bytes move to "render_forward"."""
-    sort = 32 * R if fused_sort else 0
+def roofline_bytes(P, R, HW, fused_sort=False, fused_scatter=False, R_consumed=None):
+    """Algorithmic bytes per stage (SH degree 0).  The 44 B/instance of binning are 12 (write
+    key + value) + 24 (one ideal sort pass: 12 read + 12 write) + 8 (key read for the ranges); when the forward compositing
+    kernel orders its own tile the "binning" stage is the scatter alone and the ordering bytes move to "render_forward".
+    R_consumed (sum over the tiles of the deepest contributor's list position): front-to-back compositing stops reading a
+    list once the tile is opaque and the backward starts at the last contributor (forward.cu:497-502, backward.cu:763), so
+    the per-instance GATHER terms (44 B forward, 44 + 40 B backward) and the ordering of the consumed prefix are charged on
+    the instances that are actually consumed; only the 8 B/instance selection read (every pair is looked at once to find the
+    front slab) stays on R.  R_consumed=None reproduces the whole-list model of §8(d)."""
+    Rc = R if R_consumed is None else R_consumed
+    if fused_sort:
+        order = (32 * R) if R_consumed is None else (8 * R + 24 * Rc)     # selection read of every pair + one ideal pass over the prefix
+    else:
+        order = 0
     scat = 12 * R if fused_scatter else 0       # cooperative preprocess + scatter: the pair writes belong to "preprocess"
     return {
         "preprocess": (56 + 8 + 44) * P + scat,
-        "binning": 44 * R - sort - scat,
-        "render_forward": 44 * R + 28 * HW + sort,
-        "render_backward": (44 + 40) * R + 24 * HW + 40 * P,
+        "binning": 44 * R - (32 * R if fused_sort else 0) - scat,
+        "render_forward": 44 * Rc + 28 * HW + order,
+        "render_backward": (44 + 40) * Rc + 24 * HW + 40 * P,
         "preprocess_backward": (60 + 40 + 68) * P,
     }
+
+
+def consumed_instances(eng):
+    """R_consumed of the engine's last forward: sum over the tiles of the deepest contributor (max n_contrib of the tile)."""
+    from common import dev_view
+    from diff_gaussian_rasterization import _cabi
+
+    L = _cabi.load()
+    ptrs = (C.c_ulonglong * 8)()
+    L.gsr_debug_pointers(eng.P, eng.W, eng.H, C.c_void_p(eng.geom.data_ptr()), C.c_void_p(eng.binning.data_ptr()), eng.capacity,
+                         C.c_void_p(eng.img.data_ptr()), ptrs)
+    W, H = eng.W, eng.H
+    nc = dev_view(ptrs[6], W * H * 4, torch.int32, eng.dev).view(H, W)
+    gy, gx = (H + 15) // 16, (W + 15) // 16
+    pad = torch.zeros((gy * 16, gx * 16), dtype=torch.int32, device=eng.dev)
+    pad[:H, :W] = nc
+    return int(pad.view(gy, 16, gx, 16).amax(dim=(1, 3)).sum().item())
 
 
 def on_demand_min():
@@ -171,7 +219,9 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_oracle_iters_per_s(sc, dc, dd, max_seconds=30.0):
+def cpu_oracle_iters_per_s(sc, dc, dd, max_seconds=30.0, views_per_iter=1):
+    """The CPU oracle port on full forward+backward passes of ONE view of the workload; a window iteration of V views is
+    V such passes (views_per_iter), so the sample is bounded to a few views and scaled."""
     from oracle.gs_oracle import Oracle
 
     o = Oracle(np.float32)
@@ -186,8 +236,11 @@ def cpu_oracle_iters_per_s(sc, dc, dd, max_seconds=30.0):
         if el > 10.0 or n >= 3 or el + el / n > max_seconds:
             break
     threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return n / el, threads, "%d full fwd+bwd iteration(s) of the same workload (P=%d, %dx%d), fp32 oracle, OpenMP" % (
+    what = "%d full fwd+bwd pass(es) over one view of the same workload (P=%d, %dx%d), fp32 oracle, OpenMP" % (
         n, sc["means3D"].shape[0], sc["image_width"], sc["image_height"])
+    if views_per_iter > 1:
+        what += "; a window iteration is %d such views: value = views/s / %d" % (views_per_iter, views_per_iter)
+    return n / el / views_per_iter, threads, what
 
 
 def script_c0_baseline():
@@ -220,7 +273,7 @@ def script_c0_baseline():
 # ----------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, device):
     from diff_gaussian_rasterization import _cabi
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     L = _cabi.load()
@@ -323,10 +376,24 @@ def run_ours(args, rank, world, device):
     names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
     R_mean = float(np.mean(Rs[Wm:]))
     HW = cfg["W"] * cfg["H"]
-    rb = roofline_bytes(cfg["P"], R_mean, HW, fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], cfg["W"], cfg["H"])))
+    # instances the compositing kernels consume (deepest contributor per tile), averaged over a few poses of the timed region
+    Rc = []
+    for i in range(min(K, 8)):
+        eng.set_camera(cams_dev[Wm + i])
+        eng.launch_forward()
+        Rc.append(consumed_instances(eng))
+    R_cons = float(np.mean(Rc))
+    fs_on, fsc_on = fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], cfg["W"], cfg["H"]))
+    rb = roofline_bytes(cfg["P"], R_mean, HW, fs_on, fsc_on, R_consumed=R_cons)
+    rb_full = roofline_bytes(cfg["P"], R_mean, HW, fs_on, fsc_on)
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2       # dominant single kernel: one of the two composite kernels
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9
+    # the same pose as the reference arm's check.dL_dtau_last: the last timed step
+    eng.set_camera(cams_dev[Wm + K - 1])
+    eng.step()
+    torch.cuda.synchronize(device)
+    tau_last = [float(x) for x in eng.g_tau.cpu().numpy()]
     stages = {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]), "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if (ms > 0 and rb[n] > 0) else None}
               for n, ms in zip(names, stage)}
     traffic = None
@@ -346,13 +413,11 @@ def run_ours(args, rank, world, device):
         "metric": METRIC, "value": world * K / (tmax * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": tmax / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload + ": %dx%d, P=%d Gaussians, SH deg %d, 1 view/step, pose perturbed every step"
-                   % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"]),
-                   "num_rendered_mean": R_mean, "tiles": ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16),
-                   "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
-                   "parallelism": "pose-parallel x%d (one independent tracking stream per GPU, no collective)" % world,
-                   "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d; per-tile sort %s"
-                           % (eng.capacity, sort_path(eng))},
+        "config": workload_config(args.workload),
+        "details": {"num_rendered_mean": R_mean, "num_consumed_mean": R_cons, "tiles": ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16),
+                    "parallelism": "pose-parallel x%d (one independent tracking stream per GPU, no collective)" % world,
+                    "path": "RasterEngine: CUDA graph of forward+backward, no host sync, capacity %d; per-tile sort %s"
+                            % (eng.capacity, sort_path(eng))},
         "e2e": {"value": world * K / emax, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3,
                 "what": "RasterEngine.step_host: one graph with pinned pose block + pinned dL/dcolor,dL/ddepth H2D, forward, backward, dL/dtau + header D2H; host sync every step"},
@@ -361,33 +426,24 @@ def run_ours(args, rank, world, device):
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
+                     "byte_model": "gather terms on consumed instances (R_consumed = %.0f of R = %.0f)" % (R_cons, R_mean),
+                     "frac_whole_list_model": round(rb_full[names[dom]] / (stage[dom] * 1e-3) / 1e9 / peak, 4),
                      "whole_step": {"alg_bytes": int(sum(rb.values())), "frac": round(sum(rb.values()) / (tmax / K * 1e-3) / 1e9 / peak, 4)},
                      "stages": stages},
-        "clocks": clocks,
+        "clocks": clocks, "check": {"dL_dtau_last": tau_last},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                 "script_C0": script_c0_baseline()}
     return line
 
 
-def run_window(args, rank, world, device):
-    """Mapping-window / candidate-pose workloads (C2, C3, C4): V views over one replicated map, sharded by view
-    across the ranks.  One step = forward+backward of ALL V views; per-Gaussian gradients are
-    accumulated in the backward kernel and summed over ranks by ONE all-reduce (NCCL over NVLink) per step for the
-    mapping shapes; the candidate-pose batch (C3) needs no collective.  Strong scaling: total work is fixed."""
-    from diff_gaussian_rasterization import _cabi
-    from diff_gaussian_rasterization import scenes as S
-    from diff_gaussian_rasterization.engine import RasterEngine
-    from diff_gaussian_rasterization.window import KeyframeWindow
+def window_inputs(name, V):
+    """Scene, packed camera blocks [V,52] and pre-generated upstream gradients of a window workload (both arms)."""
+    import scenes as S
 
-    L = _cabi.load()
-    K, Wm = args.steps, args.warmup
-    name = args.workload
     cfg = S.CONFIGS[name]
-    V = args.views or cfg["V"]
-    reduce = not name.startswith("C3")
     sc = S.make_scene(name, seed=0)
     W, H = cfg["W"], cfg["H"]
     poses = S.noisy_poses(V, seed=2) if name.startswith("C3") else S.arc_poses(V, radius=0.5, seed=2)
@@ -395,27 +451,46 @@ def run_window(args, rank, world, device):
                                      c["campos"], [0.0]]).astype(np.float32)
                      for c in (S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c) for w2c in poses)])
     dc, dd = S.make_pixel_grads(W, H, seed=1)
+    return cfg, sc, cams, dc, dd
+
+
+def run_window(args, rank, world, device):
+    """Mapping-window / candidate-pose workloads (C2, C3, C4): V views over one replicated map, sharded over the ranks
+    (window.py: whole views round robin, left-over views split into bands of tile rows).  One step =
+    forward+backward of ALL V views; per-Gaussian gradients are accumulated in the backward kernel and summed over ranks by
+    ONE all-reduce (NCCL over NVLink) per step for the mapping shapes; the candidate-pose batch (C3) needs no collective.
+    Strong scaling: total work is fixed."""
+    from diff_gaussian_rasterization import _cabi
+    import scenes as S
+    from diff_gaussian_rasterization import slam_ops as SO
+    from diff_gaussian_rasterization.engine import RasterEngine
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    L = _cabi.load()
+    K, Wm = args.steps, args.warmup
+    name = args.workload
+    V = args.views or S.CONFIGS[name]["V"]
+    reduce = not name.startswith("C3")
+    cfg, sc, cams, dc, dd = window_inputs(name, V)
+    W, H = cfg["W"], cfg["H"]
     t = S.to_torch(sc, device)
-    eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
-                       W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
+    mk = lambda **kw: RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                                   W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device,
+                                   tau_slots=max(64, V), **kw)
+    eng = mk()
     cams_dev = torch.from_numpy(cams).to(device)
     cams_pin = torch.from_numpy(cams).pin_memory()
-    dc_pin, dd_pin = torch.from_numpy(dc).pin_memory(), torch.from_numpy(dd).pin_memory()
-    eng.dL_dcolor.copy_(dc_pin)
-    eng.dL_ddepth.copy_(dd_pin)
-    extra = []
-    for _ in range(max(args.engines, 1) - 1):      # further engines over the same Gaussians: views overlap on separate streams
-        e2 = RasterEngine(dict(means3D=eng.g["means3D"], opacities=eng.g["opacities"], shs=eng.g["shs"], scales=eng.g["scales"],
-                               rotations=eng.g["rotations"]), W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device)
-        e2.dL_dcolor.copy_(dc_pin); e2.dL_ddepth.copy_(dd_pin)
-        extra.append(e2)
-    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world, extra_engines=extra)
+    gc_dev, gd_dev = torch.from_numpy(dc).to(device), torch.from_numpy(dd).to(device)      # ONE resident copy, read by every view
+    # further engines over the same Gaussians: units overlap on separate streams, all add into ONE gradient buffer (REDs)
+    n_units_max = -(-V // world) + 1
+    extra = [mk(grad_flat=eng.grad_flat) for _ in range(min(max(args.engines, 1), n_units_max) - 1)]
+    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world, extra_engines=extra, split=not args.no_split)
     win.calibrate()
     Rs = []
-    for v in win.views:
-        eng.set_camera(cams_dev[v])
+    for (v, y0, y1) in win.units:
+        eng.set_camera(cams_dev[v]); eng.set_band(y0, y1)
         Rs.append(eng.calibrate())
-    up = (lambda v, e: (e.dL_dcolor, e.dL_ddepth)) if extra else (lambda v: (eng.dL_dcolor, eng.dL_ddepth))
+    up = (lambda v, e: (gc_dev, gd_dev)) if extra else (lambda v: (gc_dev, gd_dev))
     flush = l2_flusher(device)
     stream = torch.cuda.current_stream(device)
 
@@ -443,34 +518,67 @@ def run_window(args, rank, world, device):
     barrier()
     clocks = sampler.stop()
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
-    _, overflow = eng.header()
-    assert not overflow
-    gnorm_check = float(eng.grad_flat.double().norm())
+    for e in win.engines:
+        _, overflow = e.header()
+        assert not overflow
+    gnorm_check = float(eng.grad_flat[:eng.grad_flat.numel() - 8 * eng.tau_slots].double().norm())
+    tau_last = [float(x) for x in win.tau_all[V - 1].cpu().numpy()] if reduce or world == 1 else None
+    # the collective alone (same buffer, device-timed): what part of the step it is
+    coll_ms = 0.0
+    if reduce and world > 1:
+        probe = torch.zeros_like(eng.grad_flat)
+        for _ in range(3):
+            torch.distributed.all_reduce(probe)
+        ce = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a_, b_ in ce:
+            barrier()
+            a_.record(stream); torch.distributed.all_reduce(probe); b_.record(stream)
+        torch.cuda.synchronize(device)
+        coll_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in ce]))
+        del probe
 
-    # e2e: camera blocks + dL/dpixel from pinned host memory every view, dL/dtau of the local views + the gradient
-    # norm (what an optimiser step would read first) back to the host, host blocks every step
-    tau_pin = torch.empty((max(len(win.views), 1), 6), dtype=torch.float32).pin_memory()
-    norm_pin = torch.empty(1, dtype=torch.float32).pin_memory()
+    # ---------------- e2e: the host-driven mapping iteration (slam_ops.MappingWindow) ----------------
+    # Per step from pinned HOST memory: the camera blocks of all keyframes (the poses are optimisation variables).  The loss
+    # of every unit is evaluated in its forward's epilogue against device-resident ground truth (uploaded once per keyframe,
+    # like the reference keeps viewpoint.original_image on the GPU), so dL/dpixel never crosses PCIe.  Back to the host:
+    # per-unit {loss, dL/da, dL/db}, every view's dL/dtau and the gradient norm; the host blocks every step.
+    e2e_s, h2d, d2h = 0.0, 0, 0
+    if reduce:
+        g = torch.Generator().manual_seed(7)
+        gt_c = torch.rand((V, 3, H, W), generator=g).to(device)
+        gt_d = (torch.rand((V, 1, H, W), generator=g) * 3.0).to(device)
+        expo = torch.zeros((V, 2), dtype=torch.float32, device=device)
+        mw = SO.MappingWindow(win, gt_c, gt_d, expo, alpha=0.95)
+        n_loc = max(len(win.units), 1)
+        sums_pin = torch.empty((n_loc, 4), dtype=torch.float32).pin_memory()
+        tau_pin = torch.empty((V, 6), dtype=torch.float32).pin_memory()
+        norm_pin = torch.empty(1, dtype=torch.float32).pin_memory()
+        body = eng.grad_flat[:eng.grad_flat.numel() - 8 * eng.tau_slots]
 
-    def up_host(v, e=None):
-        e = eng if e is None else e
-        e.dL_dcolor.copy_(dc_pin, non_blocking=True)
-        e.dL_ddepth.copy_(dd_pin, non_blocking=True)
-        return e.dL_dcolor, e.dL_ddepth
+        def e2e_step():
+            cams_dev.copy_(cams_pin, non_blocking=True)
+            flat, sums, _ = mw.iteration(reduce=True)
+            sums_pin.copy_(sums, non_blocking=True)
+            tau_pin.copy_(win.tau_all, non_blocking=True)
+            norm_pin.copy_(body.norm().reshape(1), non_blocking=True)
+            stream.synchronize()
 
-    def e2e_step():
-        cams_dev.copy_(cams_pin, non_blocking=True)
-        win.iteration(up_host, reduce=reduce)
-        tau_pin[:len(win.views)].copy_(win.tau, non_blocking=True)
-        norm_pin.copy_(eng.grad_flat.norm().reshape(1), non_blocking=True)
-        stream.synchronize()
+        h2d, d2h = cams.nbytes, n_loc * 16 + V * 24 + 4
+    else:      # candidate-pose batch: pinned poses in, dL/dtau of the local poses out
+        tau_pin = torch.empty((V, 6), dtype=torch.float32).pin_memory()
 
+        def e2e_step():
+            cams_dev.copy_(cams_pin, non_blocking=True)
+            win.iteration(up, reduce=False, upstream_precomputed=True)
+            tau_pin.copy_(win.tau_all, non_blocking=True)
+            stream.synchronize()
+
+        h2d, d2h = cams.nbytes, V * 24
     for _ in range(Wm):
         flush()
         torch.cuda.synchronize(device)
         e2e_step()
     barrier()
-    e2e_s = 0.0
     for _ in range(K):
         flush()
         barrier()
@@ -478,16 +586,21 @@ def run_window(args, rank, world, device):
         e2e_step()
         e2e_s += time.perf_counter() - t0
     barrier()
-    h2d = cams.nbytes + len(win.views) * (dc.nbytes + dd.nbytes)
-    d2h = len(win.views) * 24 + 4
+    loss_check = float(sums_pin[:, 0].sum()) if reduce else None
 
-    # per-stage timing on this rank's first view
+    # per-stage timing + consumed instances on this rank's first whole view
     names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
     stage = np.zeros(5)
-    if win.views:
+    R_view, R_cons = 0.0, 0.0
+    whole = [u for u in win.units if u[2] == 0]
+    if whole:
+        eng.set_camera(cams_dev[whole[0][0]]); eng.set_band(0, 0)
+        eng.dL_dcolor.copy_(gc_dev); eng.dL_ddepth.copy_(gd_dev)
+        R_view = float(eng.calibrate())
+        eng.launch_forward()
+        R_cons = float(consumed_instances(eng))
         L.gsr_stage_timing(1)
         out5 = (C.c_float * 5)()
-        eng.set_camera(cams_dev[win.views[0]])
         for i in range(3):
             flush()
             eng.step(use_graph=False)
@@ -496,51 +609,64 @@ def run_window(args, rank, world, device):
         stage /= 3
         L.gsr_stage_timing(0)
     tmax, emax = dev_ms, e2e_s
-    R_sum = float(sum(Rs))
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         tmax, emax = float(tt[0]), float(tt[1])
-        rr = torch.tensor([R_sum], dtype=torch.float64, device=device)
-        torch.distributed.all_reduce(rr)
-        R_sum = float(rr[0])
     if rank != 0:
         return None
     HW = W * H
-    R_view = R_sum / V
-    rb = roofline_bytes(cfg["P"], R_view, HW, fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], W, H)))
+    fs_on, fsc_on = fused_sort_active(eng), bool(L.gsr_forward_nosync_fuses_scatter(cfg["P"], W, H))
+    rb = roofline_bytes(cfg["P"], R_view, HW, fs_on, fsc_on, R_consumed=R_cons)
+    rb_full = roofline_bytes(cfg["P"], R_view, HW, fs_on, fsc_on)
     peak, peak_src = peaks()
     dom = int(np.argmax([stage[2], stage[3]])) + 2
     achieved = rb[names[dom]] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
     grad_bytes = int(eng.grad_flat.numel() * 4)
     line = {
-        "metric": "fwd+bwd raster window iters/s incl. pose dL/dtau", "value": K / (tmax * 1e-3), "unit": "window iters/s",
+        "metric": WINDOW_METRIC, "value": K / (tmax * 1e-3), "unit": WINDOW_UNIT,
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": tmax / K, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%d, P=%d Gaussians, SH deg %d, V=%d views/step sharded by view over %d GPU(s)"
-                   % (name, W, H, cfg["P"], cfg["sh_degree"], V, world),
-                   "views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view,
-                   "collective": ("all_reduce(sum) of %d B of packed per-Gaussian gradients per step" % grad_bytes) if reduce else "none",
-                   "l2": "flushed between steps (256 MiB fill, outside the per-step events)",
-                   "parallelism": "keyframe-parallel x%d, %d engine(s) / stream(s) per GPU" % (world, len(win.engines)),
-                   "path": "KeyframeWindow over RasterEngine(s), no host sync; per-tile lists ordered " + sort_path(eng)},
-        "e2e": {"value": K / emax, "unit": "window iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": emax / K * 1e3},
+        "config": workload_config(name, V),
+        "details": {"views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view, "num_consumed_per_view": R_cons,
+                    "units_per_rank": [["v%d" % u[0] if u[2] == 0 else "v%d[rows %d:%d]" % u for u in r] for r in win.plan],
+                    "collective": ("all_reduce(sum) of %d B (packed per-Gaussian gradients + every view's dL/dtau) per step, inside the timed region; "
+                                   "alone %.3f ms" % (grad_bytes, coll_ms)) if reduce else "none",
+                    "parallelism": "keyframe-parallel x%d (left-over views split into bands of tile rows), %d engine(s) / stream(s) per GPU"
+                                   % (world, len(win.engines)),
+                    "path": "KeyframeWindow over RasterEngine(s), no host sync; per-tile lists ordered " + sort_path(eng)},
+        "e2e": {"value": K / emax, "unit": WINDOW_UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": emax / K * 1e3,
+                "what": ("slam_ops.MappingWindow.iteration: pinned camera blocks H2D, mapping loss of every view fused into its forward "
+                         "(ground truth resident), backward, all-reduce, per-view loss + dL/dtau + gradient norm D2H; host sync every step")
+                        if reduce else "KeyframeWindow.iteration(reduce=False): pinned candidate poses H2D, dL/dtau of every pose D2H"},
         "gpu_launches": launches_per_step * K,
+        "launches_per_step": {"kernels": launches_per_step},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
+                     "byte_model": "gather terms on consumed instances (R_consumed = %.0f of R = %.0f per view)" % (R_cons, R_view),
+                     "frac_whole_list_model": round(rb_full[names[dom]] / (stage[dom] * 1e-3) / 1e9 / peak, 4) if stage[dom] > 0 else None,
                      "whole_step": {"alg_bytes": int(sum(rb.values()) * V),
                                     "frac": round(sum(rb.values()) * V / (tmax / K * 1e-3) / 1e9 / (peak * world), 4)},
-                     "stages_one_view": {n: round(float(ms), 4) for n, ms in zip(names, stage)}},
-        "clocks": clocks, "check": {"grad_norm": gnorm_check},
+                     "stages_one_view": {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]),
+                                             "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if (ms > 0 and rb[n] > 0) else None}
+                                         for n, ms in zip(names, stage)}},
+        "clocks": clocks, "check": {"grad_norm": gnorm_check, "dL_dtau_last": tau_last, "e2e_loss_sum_rank0": loss_check},
     }
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        line["roofline"]["traffic"] = json.load(open(tp)).get(name[:2] + "_" + names[dom])
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample = cpu_oracle_iters_per_s(S.with_camera(sc, S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], S.arc_poses(V, radius=0.5, seed=2)[0])),
+                                                  dc, dd, views_per_iter=V)
+        line["cpu_baseline"] = {"value": v, "unit": WINDOW_UNIT, "cores": cores, "kind": "port", "sample": sample}
     return line
 
 
 def _tracking_setup(device):
     """C1 scene, ground-truth images rendered at the base pose, start pose = Exp(noise) * base."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     cfg = S.CONFIGS["C1_tum_tracking"]
@@ -680,33 +806,27 @@ class _RawView:
 # ----------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world, device):
     """The reference arm (rank 0 only)."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     K, Wm = args.steps, args.warmup
     window = not args.workload.startswith(("C0", "C1"))
     if window:      # V views per step over one map, per-view gradients summed like autograd does (slam_backend.py:168-232)
-        cfg = S.CONFIGS[args.workload]
-        V = args.views or cfg["V"]
-        sc = S.make_scene(args.workload, seed=0)
-        poses = S.noisy_poses(V, seed=2) if args.workload.startswith("C3") else S.arc_poses(V, radius=0.5, seed=2)
-        cams = np.stack([np.concatenate([c["viewmatrix"].reshape(-1), c["projmatrix"].reshape(-1), c["projmatrix_raw"].reshape(-1),
-                                         c["campos"], [0.0]]).astype(np.float32)
-                         for c in (S.make_camera(cfg["W"], cfg["H"], cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], w2c) for w2c in poses)])
-        dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=1)
+        V = args.views or S.CONFIGS[args.workload]["V"]
+        cfg, sc, cams, dc, dd = window_inputs(args.workload, V)
     else:
         V = 1
         cfg, sc, cams, dc, dd = build_workload(args.workload, K + Wm, 0, device)
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libgsref.so")
-    base = {"metric": METRIC if not window else "fwd+bwd raster window iters/s incl. pose dL/dtau",
-            "unit": UNIT if not window else "window iters/s", "n_gpus": world, "steps": K, "warmup": Wm, "higher_is_better": True,
-            "scaling": "weak" if not window else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload + (": %dx%d, P=%d Gaussians, SH deg %d, " % (cfg["W"], cfg["H"], cfg["P"], cfg["sh_degree"]))
-                       + ("1 view/step, pose perturbed every step" if not window else "V=%d views/step on one GPU" % V)}}
+    unit = UNIT if not window else WINDOW_UNIT
+    base = {"metric": METRIC if not window else WINDOW_METRIC, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+            "higher_is_better": True, "scaling": "weak" if not window else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": workload_config(args.workload, V if window else None),
+            "details": {"where": "one GPU (rank 0): the reference has no multi-GPU path"}}
     if not (os.path.exists(ref_so) and torch.cuda.is_available()):
-        v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd)
+        v, cores, sample = cpu_oracle_iters_per_s(sc, dc, dd, views_per_iter=V)
         base.update(value=v, ms_per_step=1e3 / v,
-                    cpu_baseline={"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                    e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+                    cpu_baseline={"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         return base
     Lr = C.CDLL(ref_so)
     Lr.gsref_create.restype = C.c_void_p
@@ -776,12 +896,13 @@ def run_reference(args, rank, world, device):
     v = K / (ms * 1e-3)
     Lr.gsref_destroy(h)
     base.update(value=v, ms_per_step=ms / K, clocks=clocks,
-                cpu_baseline={"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "device": "cuda",
+                cpu_baseline={"value": v, "unit": unit, "cores": 1, "kind": "reference", "device": "cuda",
                               "sample": "all %d steps of the workload; the reference path has no CPU implementation, so its own "
                                         "CUDA kernels (unmodified sources, sm_100a) run on the B200, driven by one host thread" % K},
-                e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                e2e={"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 check={"dL_dtau_last": [float(x) for x in tau.cpu().numpy()]})
-    base["config"]["l2"] = "flushed between steps (256 MiB fill, outside the per-step events)"
+    if window:
+        base["check"]["grad_norm"] = float(torch.cat([acc[k].reshape(-1) for k in ("m3d", "sh", "opac", "rot", "sc")]).double().norm())
     return base
 
 
@@ -802,12 +923,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C1_tum_tracking")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--views", type=int, default=0, help="override the window size of C2/C3/C4")
     ap.add_argument("--engines", type=int, default=4,
                     help="window workloads: engines (streams) the local views are dealt to (device time is flat from 2 up, the "
                          "host-driven e2e gains from overlapping the per-view copies: C2 6.61 / 6.40 / 6.19 ms, C3 19.5 / 16.7 / 16.4 ms with 2 / 3 / 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="window workloads: whole views only (round robin), no bands of tile rows")
+    ap.add_argument("--no-also-c1", action="store_true", help="skip the nested C1 tracking record of the default run at N = 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -833,8 +956,16 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     if args.workload == "C1_tracking_loop":
         line = run_tracking_loop(args, rank, world, device)
+    elif args.workload.startswith(("C0", "C1")):
+        line = run_ours(args, rank, world, device)
     else:
-        line = run_ours(args, rank, world, device) if args.workload.startswith(("C0", "C1")) else run_window(args, rank, world, device)
+        line = run_window(args, rank, world, device)
+        if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_also_c1:
+            # last round's headline rides along: the C1 tracking step (same flags; its own value / e2e / roofline)
+            torch.cuda.empty_cache()
+            a1 = argparse.Namespace(**vars(args))
+            a1.workload, a1.no_cpu_baseline = "C1_tum_tracking", True
+            line["also_C1"] = run_ours(a1, rank, world, device)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

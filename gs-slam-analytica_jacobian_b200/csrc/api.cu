@@ -1,10 +1,14 @@
 // C-ABI of gsr_b200 (declared in include/gsr_b200.h).  Thin host layer: argument checks, workspace
-// carve-up, stream plumbing; no torch types, no global state beyond a thread-local error string.
+// carve-up, stream plumbing; no torch types.  Process-wide state: the thread-local error string, the launch counter, the
+// default on-demand threshold (gsr_sort_on_demand; per call: gsr_scene.sort_on_demand) and the opt-in stage timing, whose
+// events are kept per device.
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/gsr_b200.h"
 #include "gsr_params.h"
 
@@ -20,18 +24,52 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py: gpu_launches)
 // optional stage timing (bench.py roofline): CUDA events recorded on the launching stream between stages
-bool g_timing = false;
+std::atomic<bool> g_timing{false};
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
 const bool g_no_pdl = getenv("GSR_NO_PDL") != nullptr;                 // A/B switch: no programmatic dependent launches
-const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;         // A/B switch: forward not a programmatic dependent of the preprocess
+const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;
+// default of gsr_scene.exact_exp == 0 (GSR_EXACT_EXP=0 / 1 overrides the built-in default)
+const int g_exact_exp_default = getenv("GSR_EXACT_EXP") ? atoi(getenv("GSR_EXACT_EXP")) : GSR_EXACT_EXP_DEFAULT;         // A/B switch: forward not a programmatic dependent of the preprocess
 // lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
 // is sorted completely
 std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
-cudaEvent_t g_ev[7];
+// stage-timing events live per device and are created on first use there (a process may drive several GPUs: KeyframeWindow
+// with engines on different devices, one thread per GPU); the mutex covers creation and teardown only
+constexpr int kMaxDevices = 64;
+struct StageEvents {
+	cudaEvent_t ev[7];
+	bool made = false;
+};
+StageEvents g_stage[kMaxDevices];
+std::mutex g_stage_mutex;
+StageEvents* stage_events(bool create)
+{
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+	StageEvents& se = g_stage[dev];
+	if (!se.made) {
+		if (!create) return nullptr;
+		std::lock_guard<std::mutex> lock(g_stage_mutex);
+		if (!se.made) {
+			for (int i = 0; i < 7; i++)
+				if (cudaEventCreate(&se.ev[i]) != cudaSuccess) return nullptr;
+			se.made = true;
+		}
+	}
+	return &se;
+}
 void stage_mark(int i, cudaStream_t st)
 {
-	if (g_timing) cudaEventRecord(g_ev[i], st);
+	if (!g_timing.load(std::memory_order_relaxed)) return;
+	if (StageEvents* se = stage_events(true)) cudaEventRecord(se->ev[i], st);
 }
+
+// NVTX ranges around the stages of a call (host side: they bracket the launches; under a tracing tool the kernels carry
+// their own names).  No-ops unless a tool is attached.
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const char* fmt, const char* detail = "")
 {
@@ -95,6 +133,15 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
 	s.overlap_forward = a->overlap_forward;
 	s.upstream_ready = a->upstream_ready;
+	s.exact_exp = a->exact_exp > 0 ? 1 : (a->exact_exp < 0 ? 0 : (g_exact_exp_default ? 1 : 0));
+	s.band_y0 = s.band_y1 = 0;
+	if (a->tile_row_end != 0 || a->tile_row_begin != 0) {
+		if (a->tile_row_begin < 0 || a->tile_row_end <= a->tile_row_begin || a->tile_row_end > s.grid_y)
+			return fail(GSR_ERR_ARG, "tile_row_begin / tile_row_end: need 0 <= begin < end <= ceil(H / 16)");
+		if (a->densify_grad_accum || a->densify_denom || a->max_radii2D)
+			return fail(GSR_ERR_ARG, "densification statistics are per view: not available for a band of tile rows");
+		if (a->tile_row_begin != 0 || a->tile_row_end != s.grid_y) { s.band_y0 = a->tile_row_begin; s.band_y1 = a->tile_row_end; }
+	}
 	s.has_loss = a->fused_loss != nullptr;
 	if (s.has_loss) {
 		const gsr_fused_loss* l = a->fused_loss;
@@ -142,6 +189,7 @@ int gsr_forward_plan(const gsr_scene* a, void* geom, size_t geom_bytes, int* rad
 	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
 	cudaStream_t st = (cudaStream_t)stream;
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
+	NvtxRange nvtx_call("gsr_forward_plan: preprocess");
 	stage_mark(0, st);
 	gsr::launch_preprocess_forward(s, g, radii, n_touched, st);
 	stage_mark(1, st);
@@ -169,6 +217,8 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 {
 	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
 	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
+	// num_rendered unknown to the host: an empty workspace cannot even hold the lists' overflow bookkeeping
+	if (R_host < 0 && capacity == 0 && s.P > 0) return fail(GSR_ERR_WORKSPACE, "binning capacity must be positive when num_rendered is read on the device");
 	if (capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "more than 2^31 tile instances are not supported");
 	if (!geom || !image || image_bytes < gsr::image_bytes(s.W, s.H)) return fail(GSR_ERR_WORKSPACE, "image workspace too small");
 	if (!binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles_of(s.W, s.H))) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
@@ -180,15 +230,18 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	// lists known to fit one shared-memory chunk: sort them inside the compositing kernel (one launch less, overlap)
 	// or ANY list length when lists are ordered on demand
 	// (when the longest list expected does not reach the threshold, the plain fused kernel does: it still copes with longer ones)
-	int lazy_min = g_no_fused_sort ? 0 : g_lazy_min.load();
+	int lazy_min = g_no_fused_sort ? 0 : (a->sort_on_demand > 0 ? a->sort_on_demand : (a->sort_on_demand < 0 ? 0 : g_lazy_min.load()));
 	if (max_tile_hint > 0 && max_tile_hint <= lazy_min) lazy_min = 0;
 	const bool fuse_sort = !g_no_fused_sort && (lazy_min > 0 || (max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK));
+	nvtxRangePushA("gsr: binning");
 	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done);
 	stage_mark(2, st);
+	nvtxRangePop();
 	int rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
+	NvtxRange nvtx_render("gsr: render forward");
 	// directly behind the cooperative preprocess + scatter (no kernel in between): start inside its tail
-	const bool behind_preprocess = scatter_done && fuse_sort && !g_timing && !a->debug && !g_no_pdl && !g_no_pdl_fwd;
+	const bool behind_preprocess = scatter_done && fuse_sort && !g_timing.load() && !a->debug && !g_no_pdl && !g_no_pdl_fwd;
 	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st,
 	                           behind_preprocess);
 	stage_mark(3, st);
@@ -218,9 +271,11 @@ int gsr_forward_nosync(const gsr_scene* a, void* geom, size_t geom_bytes, void* 
 	if (!geom || geom_bytes < gsr::geom_bytes(s.P, tiles)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
 	if (s.P > 0 && !radii) return fail(GSR_ERR_ARG, "radii output is required");
 	if (capacity < 0 || !binning || binning_bytes < gsr::binning_bytes((size_t)capacity, tiles)) return fail(GSR_ERR_WORKSPACE, "binning workspace too small");
+	if (capacity == 0 && s.P > 0) return fail(GSR_ERR_WORKSPACE, "binning capacity must be positive when num_rendered is read on the device");
 	cudaStream_t st = (cudaStream_t)stream;
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
+	NvtxRange nvtx_call("gsr_forward_nosync");
 	stage_mark(0, st);
 	const bool scatter_done = gsr::launch_preprocess_forward(s, g, radii, n_touched, st, &b, (size_t)capacity);
 	stage_mark(1, st);
@@ -237,12 +292,27 @@ int gsr_forward_overflowed(void* geom, void* stream, int* overflowed, long long*
 {
 	if (!geom || !overflowed) return fail(GSR_ERR_ARG, "null argument");
 	gsr::GeomView g = gsr::geom_view(geom, 0, 0);
-	unsigned int h[2] = {0, 0};
-	cudaError_t e = cudaMemcpyAsync(h, g.hdr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	gsr::GeomHeader h;
+	cudaError_t e = cudaMemcpyAsync(&h, g.hdr, 32, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
 	if (e != cudaSuccess) return fail(GSR_ERR_CUDA, "reading overflow flag: %s", cudaGetErrorString(e));
-	*overflowed = h[1] != 0;
-	if (needed) *needed = h[0];
+	*overflowed = h.overflow != 0;
+	if (needed) *needed = h.num_rendered;
+	if (h.spin_timeout)
+		return fail(GSR_ERR_TIMEOUT, "the compositing backward gave up waiting for %s: gradients of this step are incomplete",
+		            h.spin_timeout == 2 ? "the upstream_ready word" : "a tile flag of the forward");
+	return GSR_OK;
+}
+
+int gsr_step_status(void* geom, void* stream, unsigned int* out4)
+{
+	if (!geom || !out4) return fail(GSR_ERR_ARG, "null argument");
+	gsr::GeomView g = gsr::geom_view(geom, 0, 0);
+	gsr::GeomHeader h;
+	cudaError_t e = cudaMemcpyAsync(&h, g.hdr, 32, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+	if (e != cudaSuccess) return fail(GSR_ERR_CUDA, "reading the step status: %s", cudaGetErrorString(e));
+	out4[0] = h.num_rendered; out4[1] = h.overflow; out4[2] = h.spin_timeout; out4[3] = h.max_tile_count;
 	return GSR_OK;
 }
 
@@ -291,15 +361,16 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 	gsr::GeomView g = gsr::geom_view(geom, s.P, tiles);
 	gsr::BinView b = gsr::bin_view(binning, (size_t)capacity, tiles);
 	gsr::ImageView im = gsr::image_view(image, s.W, s.H);
+	NvtxRange nvtx_call("gsr_rasterize_gaussians_backward");
 	stage_mark(4, st);
 	// (with stage timing the event record sits between the two kernels: plain ordering)
-	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, s.overlap_forward != 0 && !g_timing && !a->debug && !g_no_pdl, st);
+	gsr::launch_render_backward(s, g, b, im, dL_dout_color, dL_dout_depth, s.overlap_forward != 0 && !g_timing.load() && !a->debug && !g_no_pdl, st);
 	stage_mark(5, st);
 	g_launches += 2;
 	rc = debug_sync(a, st, "render backward");
 	if (rc) return rc;
 	gsr::launch_preprocess_backward(s, g, radii, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales,
-	                                dL_drotations, dL_dcov3D, dL_dtau, !g_timing && !a->debug && !g_no_pdl, st);
+	                                dL_drotations, dL_dcov3D, dL_dtau, !g_timing.load() && !a->debug && !g_no_pdl, st);
 	stage_mark(6, st);
 	return debug_sync(a, st, "preprocess backward");
 }
@@ -370,24 +441,23 @@ int gsr_sort_on_demand(int min_list_length)
 
 int gsr_stage_timing(int enable)
 {
-	if (enable && !g_timing) {
-		for (int i = 0; i < 7; i++)
-			if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GSR_ERR_CUDA, "cudaEventCreate failed");
-		g_timing = true;
-	} else if (!enable && g_timing) {
-		g_timing = false;
-		for (int i = 0; i < 7; i++) cudaEventDestroy(g_ev[i]);
+	if (enable) {
+		if (!stage_events(true)) return fail(GSR_ERR_CUDA, "cudaEventCreate failed");
+		g_timing.store(true);
+	} else {
+		g_timing.store(false);      // the events stay (per device, reused): another thread may still be recording into them
 	}
 	return GSR_OK;
 }
 
 int gsr_stage_times_ms(float* out5)
 {
-	if (!g_timing || !out5) return fail(GSR_ERR_ARG, "stage timing is not enabled");
-	if (cudaEventSynchronize(g_ev[6]) != cudaSuccess) return fail(GSR_ERR_CUDA, "event sync failed");
+	StageEvents* se = g_timing.load() ? stage_events(false) : nullptr;
+	if (!se || !out5) return fail(GSR_ERR_ARG, "stage timing is not enabled (or nothing was timed on the current device)");
+	if (cudaEventSynchronize(se->ev[6]) != cudaSuccess) return fail(GSR_ERR_CUDA, "event sync failed");
 	const int a[5] = {0, 1, 2, 4, 5}, b[5] = {1, 2, 3, 5, 6};
 	for (int i = 0; i < 5; i++)
-		if (cudaEventElapsedTime(&out5[i], g_ev[a[i]], g_ev[b[i]]) != cudaSuccess) return fail(GSR_ERR_CUDA, "elapsed time failed");
+		if (cudaEventElapsedTime(&out5[i], se->ev[a[i]], se->ev[b[i]]) != cudaSuccess) return fail(GSR_ERR_CUDA, "elapsed time failed");
 	return GSR_OK;
 }
 

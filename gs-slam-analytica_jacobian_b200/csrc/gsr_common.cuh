@@ -10,6 +10,7 @@
 #define GSR_SORT_CHUNK 2048    // longest tile list the 256-thread sort handles as one shared-memory chunk (8 keys per thread);
                                // lists above it are queued for the long-list kernel, lists up to it can be sorted by the
                                // forward compositing kernel itself
+#define GSR_EXACT_EXP_DEFAULT 1     // forward compositing: alpha from the reference's expf by default (gsr_scene.exact_exp)
 #define GSR_LAZY_MIN_DEFAULT 256    // per-tile lists longer than this are ordered on demand by the forward compositing kernel
 
 namespace gsr {
@@ -45,7 +46,8 @@ struct GeomHeader {
 	unsigned int bwd_blocks_done;
 	unsigned int max_tile_count; // longest per-tile list
 	unsigned int num_long_tiles; // tiles queued for the long-list sort kernel (> GSR_SORT_CHUNK entries)
-	unsigned int pad[64 - 7];
+	unsigned int spin_timeout;   // a compositing-backward CTA gave up waiting: 1 = tile flag of the forward, 2 = upstream_ready word
+	unsigned int pad[64 - 8];
 };
 static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");
 
@@ -291,8 +293,11 @@ __device__ __forceinline__ void deposit_rows3_warp(float* s, const Rows3Regs& r,
 // The mirror image: ROWS rows of a [P,3] fp32 array staged in shared memory (row r at s[3r..3r+2]) go out as 16-byte
 // stores (full sectors) instead of three scalar stores per thread at a 12-byte stride.  accumulate: dst += rows (the
 // group owns its rows; views of a window run in stream order).  The caller synchronises the group between filling s and this.
+// accumulate: 0 = overwrite, 1 = read-modify-write (the caller's views run in stream order), 2 = vector / scalar REDs
+// (views of a window running concurrently on several streams add into ONE buffer; red_add_v4 is defined below).
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v);
 template <int ROWS = 256>
-__device__ __forceinline__ void store_rows3(float* __restrict__ g, int row0, int P, const float* s, bool vec_ok, bool accumulate)
+__device__ __forceinline__ void store_rows3(float* __restrict__ g, int row0, int P, const float* s, bool vec_ok, int accumulate)
 {
 	const int t = threadIdx.x & (ROWS - 1);
 	const int n = max(0, min(ROWS, P - row0)) * 3;
@@ -301,13 +306,20 @@ __device__ __forceinline__ void store_rows3(float* __restrict__ g, int row0, int
 	float4* dst4 = reinterpret_cast<float4*>(dst);
 	for (int i = t; i < n4; i += ROWS) {
 		float4 v = reinterpret_cast<const float4*>(s)[i];
+		if (accumulate == 2) {
+			if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(dst4 + i, v);
+			continue;
+		}
 		if (accumulate) {
 			const float4 o = dst4[i];
 			v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
 		}
 		dst4[i] = v;
 	}
-	for (int i = (n4 << 2) + t; i < n; i += ROWS) dst[i] = accumulate ? dst[i] + s[i] : s[i];
+	for (int i = (n4 << 2) + t; i < n; i += ROWS) {
+		if (accumulate == 2) { if (s[i] != 0.f) atomicAdd(dst + i, s[i]); }
+		else dst[i] = accumulate ? dst[i] + s[i] : s[i];
+	}
 }
 
 // Optional phase probe (compile with -DGSR_PHASE_PROBE): thread 0 of every CTA records %globaltimer at phase

@@ -212,9 +212,13 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 				const int mr = (int)my_radius;
 				const unsigned gx = (unsigned)s.grid_x, gy = (unsigned)s.grid_y;
 				const unsigned rminx = min(gx, (unsigned)max((int)0, (int)((pix_x - mr) / GSR_TILE)));
-				const unsigned rminy = min(gy, (unsigned)max((int)0, (int)((pix_y - mr) / GSR_TILE)));
+				unsigned rminy = min(gy, (unsigned)max((int)0, (int)((pix_y - mr) / GSR_TILE)));
 				const unsigned rmaxx = min(gx, (unsigned)max((int)0, (int)((pix_x + mr + GSR_TILE - 1) / GSR_TILE)));
-				const unsigned rmaxy = min(gy, (unsigned)max((int)0, (int)((pix_y + mr + GSR_TILE - 1) / GSR_TILE)));
+				unsigned rmaxy = min(gy, (unsigned)max((int)0, (int)((pix_y + mr + GSR_TILE - 1) / GSR_TILE)));
+				if (s.band_y1 > 0) {      // a band of tile rows: Gaussians that do not reach it are culled for this call (radii 0)
+					rminy = min(max(rminy, (unsigned)s.band_y0), (unsigned)s.band_y1);
+					rmaxy = min(max(rmaxy, (unsigned)s.band_y0), (unsigned)s.band_y1);
+				}
 				const unsigned area = (rmaxx - rminx) * (rmaxy - rminy);
 				if (area != 0) {
 					float3 rgb;

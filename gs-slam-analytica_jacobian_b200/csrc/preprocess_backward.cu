@@ -28,7 +28,7 @@ __device__ const float bSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.
 // SH backward for one Gaussian (backward.cu:21-145).  dRGB already masked by the clamp flags.
 // Writes dL_dsh[0..M) (zeros above the active degree), returns dL/dmean through the view direction.
 __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __restrict__ sh, float3 pos, float3 campos,
-                                              const float dRGB[3], float* __restrict__ dL_dsh, bool accumulate)
+                                              const float dRGB[3], float* __restrict__ dL_dsh, int accumulate)
 {
 	const float3 dir_o = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
 	const float len = sqrtf(dir_o.x * dir_o.x + dir_o.y * dir_o.y + dir_o.z * dir_o.z);
@@ -57,7 +57,11 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float* __res
 	}
 	for (int i = 0; i < M; i++) {
 		const float wi = i < ncoef ? w[i] : 0.f;
-		if (accumulate) {
+		if (accumulate == 2) {
+			atomicAdd(&dL_dsh[3 * i + 0], wi * dRGB[0]);
+			atomicAdd(&dL_dsh[3 * i + 1], wi * dRGB[1]);
+			atomicAdd(&dL_dsh[3 * i + 2], wi * dRGB[2]);
+		} else if (accumulate) {
 			dL_dsh[3 * i + 0] += wi * dRGB[0];
 			dL_dsh[3 * i + 1] += wi * dRGB[1];
 			dL_dsh[3 * i + 2] += wi * dRGB[2];
@@ -340,7 +344,8 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				// degree 0: colour = C0 * sh + 0.5 does not depend on the view direction (backward.cu:21-145 with deg = 0)
 				if (dL_dcolors) {      // the colour gradient itself is wanted as well (rows[3] carries dL_dsh): direct stores
 					float* d = dL_dcolors + 3 * (size_t)idx;
-					if (s.accumulate_grads) { d[0] += dcol[0]; d[1] += dcol[1]; d[2] += dcol[2]; }
+					if (s.accumulate_grads == 2) { atomicAdd(d, dcol[0]); atomicAdd(d + 1, dcol[1]); atomicAdd(d + 2, dcol[2]); }
+					else if (s.accumulate_grads) { d[0] += dcol[0]; d[1] += dcol[1]; d[2] += dcol[2]; }
 					else { d[0] = dcol[0]; d[1] = dcol[1]; d[2] = dcol[2]; }
 				}
 				const unsigned cl = g.clamped[idx];
@@ -351,7 +356,7 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 				const float dRGB[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
 				const float3 campos = {s.campos[0], s.campos[1], s.campos[2]};
 				const float3 dm = sh_backward(s.D, s.M, s.shs + (size_t)idx * s.M * 3, make_float3(mx, my, mz), campos, dRGB,
-				                              dL_dsh + (size_t)idx * s.M * 3, s.accumulate_grads != 0);
+				                              dL_dsh + (size_t)idx * s.M * 3, s.accumulate_grads);
 				dmean[0] += dm.x; dmean[1] += dm.y; dmean[2] += dm.z;
 				tau[0] += -dm.x; tau[1] += -dm.y; tau[2] += -dm.z;
 			}
@@ -400,6 +405,14 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 #pragma unroll
 				for (int i = 0; i < 6; i++) dL_dcov3D_out[(size_t)idx * 6 + i] = dcov[i];
 			}
+		} else if (visible && s.accumulate_grads == 2) {
+			// window accumulation by views running concurrently on several streams: REDs
+			atomicAdd(&dL_dopacity[idx], dopac);
+			if (s.scales) red_add_v4(reinterpret_cast<float4*>(dL_drot) + idx, make_float4(drot[0], drot[1], drot[2], drot[3]));
+			if (dL_dcov3D_out) {
+#pragma unroll
+				for (int i = 0; i < 6; i++) atomicAdd(&dL_dcov3D_out[(size_t)idx * 6 + i], dcov[i]);
+			}
 		} else if (visible) {
 			// window accumulation: this thread owns row idx, plain read-modify-write (views run in stream order)
 			dL_dopacity[idx] += dopac;
@@ -427,8 +440,8 @@ preprocess_backward_kernel(Scene s, GeomView g, const int* __restrict__ radii, f
 	}
 	__syncwarp();
 	{
-		const bool accum = s.accumulate_grads != 0;
-		store_rows3<32>(dL_dmeans2D, row0, s.P, rows2, vec_mask & 4, false);
+		const int accum = s.accumulate_grads;
+		store_rows3<32>(dL_dmeans2D, row0, s.P, rows2, vec_mask & 4, 0);
 		store_rows3<32>(dL_dmeans3D, row0, s.P, rows0, vec_mask & 8, accum);
 		if (s.scales) store_rows3<32>(dL_dscales, row0, s.P, rows1, vec_mask & 16, accum);
 		if (sh_rows) store_rows3<32>(dL_dsh, row0, s.P, rows3, vec_mask & 32, accum);

@@ -36,7 +36,10 @@ struct FwdSmem {
 	uint32_t tmask[8][32];      // per warp and queue slot: ballot of "still above 0.5 after this blend"
 };
 
-template <bool COUNT_TOUCHED>
+// EXACT: alpha from the reference's own exp (expf without fast-math, forward.cu:496; same nvcc, same instruction sequence)
+// instead of one ex2.approx: with power and the conic bit-identical, alpha and hence T are then BIT-identical to the
+// reference's for every pair, so that every threshold decision -- and with them n_contrib and n_touched -- is the reference's.
+template <bool COUNT_TOUCHED, bool EXACT>
 __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int n, float pxf, float pyf, float& T, float& C0,
                                             float& C1, float& C2, float& D, int& last, uint32_t* __restrict__ tmask, int lane)
 {
@@ -49,7 +52,7 @@ __device__ __forceinline__ void blend_queue(const QueueRec* __restrict__ q, int 
 			const float4 w2 = r->w2;
 			const float dx = w0.x - pxf, dy = w0.y - pyf;
 			const float power = falloff_power(w0.z, w0.w, w1.x, dx, dy);
-			const float alpha = fminf(0.99f, w1.y * gsr_exp(power));
+			const float alpha = fminf(0.99f, w1.y * (EXACT ? expf(power) : gsr_exp(power)));
 			const float test_T = T * (1.0f - alpha);
 			// reference order (forward.cu:481-507): skip if power > 0, skip if alpha < 1/255, stop if test_T < 1e-4.
 			// A stopped pixel has T < 0, hence test_T < 0: it can only re-enter the "stop" arm, which is idempotent.
@@ -99,6 +102,7 @@ struct FusedSortArgs {
 	GeomHeader* hdr;
 	uint32_t* tile_done;
 	int lazy_min;        // lists longer than this are ordered on demand; <= 0: every list is sorted completely
+	int tile0;           // first tile of the band this launch renders (CTA b <-> tile tile0 + b); 0 for a whole view
 };
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
 constexpr int kFusedIdsCap = GSR_SORT_CHUNK;
@@ -362,7 +366,7 @@ __device__ __noinline__ void sort_whole_tile(int tile, FusedSortArgs fs, int ids
 #ifndef GSR_FWD_MINB
 #define GSR_FWD_MINB 4      // CTAs per SM the forward compositing kernel is compiled for (experiments: GSR_EXTRA_NVCC_FLAGS=-DGSR_FWD_MINB=3)
 #endif
-template <int MODE, bool LOSS>
+template <int MODE, bool LOSS, bool EXACT>
 __global__ void __launch_bounds__(256, GSR_FWD_MINB)
 render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_list,
                       const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
@@ -377,7 +381,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 	FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 	const uint32_t* s_ids = reinterpret_cast<const uint32_t*>(smem_raw + kFusedIdsOffset);
 	LazySmem* lz = reinterpret_cast<LazySmem*>(smem_raw + kLazyOffset);
-	const int tile = blockIdx.x;
+	const int tile = fs.tile0 + (int)blockIdx.x;
 
 	GSR_PROBE(3, 0);
 	// ---- the tile's list: complete, or ordered on demand (positions < lz->sorted_end are final) ----
@@ -502,7 +506,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 					}
 					__syncwarp();
 					if (warp_hi_T) {
-						blend_queue<true>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+						blend_queue<true, EXACT>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
 						__syncwarp();
 						if (keep) {
 							const unsigned m = wmask[pos];
@@ -510,7 +514,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 						}
 						warp_hi_T = __any_sync(kFull, T > 0.5f);
 					} else {
-						blend_queue<false>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
+						blend_queue<false, EXACT>(wq, nq, pxf, pyf, T, C0, C1, C2, D, last, wmask, lane);
 					}
 					__syncwarp();   // queue fully consumed before the next chunk overwrites it
 				}
@@ -591,7 +595,7 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* point_li
 			float v = 0.f;
 #pragma unroll
 			for (int w = 0; w < 8; w++) v += s_red[w * 4 + threadIdx.x];
-			lf.partials[tile * 4 + threadIdx.x] = v;
+			lf.partials[blockIdx.x * 4 + threadIdx.x] = v;
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) {
@@ -632,8 +636,9 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
                            float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
                            cudaStream_t stream, bool behind_preprocess)
 {
-	const int tiles = s.grid_x * s.grid_y;
-	if (tiles == 0) return;
+	const bool band = s.band_y1 > 0;
+	const int tiles = band ? s.grid_x * (s.band_y1 - s.band_y0) : s.grid_x * s.grid_y;
+	if (tiles <= 0) return;
 	// behind_preprocess: the cooperative preprocess + scatter kernel was launched just before on this stream and releases its
 	// dependents behind its grid barrier: the first forward CTAs are resident (and waiting) when it ends
 	cudaLaunchConfig_t cfg = {};
@@ -649,22 +654,28 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 	fs.id_bits = 1;
 	while (fs.id_bits < 32 && (1ll << fs.id_bits) < (long long)s.P) fs.id_bits++;
 	fs.lazy_min = lazy_min;
+	fs.tile0 = band ? s.band_y0 * s.grid_x : 0;
 	const size_t smem_plain = sizeof(FwdSmem);
 	static_assert(kLazyOffset == (4 * kSmallChunk + 8 * kMaxBins + kMaxBins + 64) * 4, "LazySmem sits right behind the sort scratch");
 	static_assert(kFusedIdsOffset + kFusedIdsCap * 4 <= kLazyOffset, "sorted ids end inside the sort scratch");
 	const size_t smem_fused = (kLazyOffset + sizeof(LazySmem) + 15) / 16 * 16;
 	const size_t smem_sort = sort_smem_bytes(kSmallChunk, 256);
-	static SmemAttrCache attr[6];
+	static SmemAttrCache attr[12];
 	const int mode = (fused_sort && s.P > 0 && R_capacity > 0) ? (lazy_min > 0 ? 2 : 1) : 0;
 	const size_t smem = mode == 2 ? smem_fused : (mode == 1 ? smem_sort : smem_plain);
 	FusedLoss lf = s.loss;
-#define GSR_FWD_LAUNCH(M, L)                                                                                                      \
+#define GSR_FWD_LAUNCH_E(M, L, E)                                                                                                 \
 	do {                                                                                                                          \
-		ensure_dynamic_smem(render_forward_kernel<M, L>, smem, attr[2 * M + (L ? 1 : 0)]);                                        \
+		ensure_dynamic_smem(render_forward_kernel<M, L, E>, smem, attr[4 * M + (L ? 2 : 0) + (E ? 1 : 0)]);                       \
 		cfg.dynamicSmemBytes = smem;                                                                                              \
-		cudaLaunchKernelEx(&cfg, render_forward_kernel<M, L>, (const uint2*)g.ranges, (const uint32_t*)b.point_list,              \
+		cudaLaunchKernelEx(&cfg, render_forward_kernel<M, L, E>, (const uint2*)g.ranges, (const uint32_t*)b.point_list,           \
 		                   (const GaussRec*)g.rec, s.W, s.H, s.grid_x, (const float*)s.background, im.final_T, im.n_contrib,      \
 		                   out_color, out_depth, out_opacity, n_touched, b.cull_masks, fs, lf);                                   \
+	} while (0)
+#define GSR_FWD_LAUNCH(M, L)                                                                                                      \
+	do {                                                                                                                          \
+		if (s.exact_exp) GSR_FWD_LAUNCH_E(M, L, true);                                                                            \
+		else GSR_FWD_LAUNCH_E(M, L, false);                                                                                       \
 	} while (0)
 	if (s.has_loss) {
 		if (mode == 2) GSR_FWD_LAUNCH(2, true);
@@ -676,6 +687,7 @@ void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, 
 		else GSR_FWD_LAUNCH(0, false);
 	}
 #undef GSR_FWD_LAUNCH
+#undef GSR_FWD_LAUNCH_E
 }
 
 GSR_PROBE_READER(probe_read_render)

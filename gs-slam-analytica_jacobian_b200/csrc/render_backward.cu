@@ -149,28 +149,34 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
                        GaussAcc* __restrict__ acc, const uint32_t* __restrict__ cull_masks, const uint32_t* __restrict__ tile_done,
-                       const uint32_t* __restrict__ upstream_ready, GeomHeader* __restrict__ hdr)
+                       const uint32_t* __restrict__ upstream_ready, GeomHeader* __restrict__ hdr, int tile0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
-	const int tile = blockIdx.x;
+	const int tile = tile0 + (int)blockIdx.x;      // tile0: first tile of the band this launch covers
 	pdl_launch_dependents();      // the per-Gaussian backward may move in (and fetch its inputs) during this kernel's tail
 	// Launched as a programmatic dependent of the forward compositing kernel (RasterEngine.step) this CTA may be running
 	// while forward CTAs of other tiles still are: wait for ITS tile (a flag the forward CTA releases behind its last
 	// write; always set in a normally ordered launch) and read what the forward wrote with L2-coherent loads only.
 	// upstream_ready (optional): a word that whoever delivers dL/dpixel sets behind the data (e.g. the last of the host-to-device
 	// copies of a step on another stream): the dependency on it then need not be a full edge in front of this kernel.
-	// The spins are bounded (~1 s): a flag that never comes is reported through the header, not by hanging the GPU.
+	// The spins are bounded (~1 s each, separate budgets): a flag that never comes is reported through the header's
+	// spin_timeout word (1 = tile flag, 2 = upstream word; gsr_step_status / GSR_ERR_TIMEOUT), not by hanging the GPU; the
+	// tile then contributes no gradients.
 	// The flag's value is the tile's deepest contributor + 1 (the forward CTA knows it): how far the list has to be walked
 	// (backward.cu:763) is known here, and the first gather is on its way before this CTA's own n_contrib loads are back.
 	if (threadIdx.x == 0) {
 		int spins = 0;
 		uint32_t v;
 		while ((v = ld_acquire_u32(tile_done + tile)) == 0 && ++spins < (1 << 22)) __nanosleep(200);
-		if (upstream_ready)
-			while (ld_acquire_u32(upstream_ready) == 0 && ++spins < (1 << 22)) __nanosleep(200);
-		if (spins >= (1 << 22)) hdr->overflow = 2;
+		if (v == 0) hdr->spin_timeout = 1;
+		if (upstream_ready) {
+			spins = 0;
+			uint32_t u;
+			while ((u = ld_acquire_u32(upstream_ready)) == 0 && ++spins < (1 << 22)) __nanosleep(200);
+			if (u == 0) { hdr->spin_timeout = 2; v = 0; }
+		}
 		sm.wmax[0] = v ? v - 1u : 0u;
 	}
 	__syncthreads();
@@ -294,8 +300,9 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
                             const float* dL_dpix, const float* dL_dpix_depth, bool overlap_forward, cudaStream_t stream)
 {
-	const int tiles = s.grid_x * s.grid_y;
-	if (tiles == 0) return;
+	const bool band = s.band_y1 > 0;
+	const int tiles = band ? s.grid_x * (s.band_y1 - s.band_y0) : s.grid_x * s.grid_y;
+	if (tiles <= 0) return;
 	const size_t smem = sizeof(BwdSmem);
 	static SmemAttrCache attr;
 	ensure_dynamic_smem(render_backward_kernel, smem, attr);
@@ -308,7 +315,8 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	cfg.numAttrs = overlap_forward ? 1 : 0;
 	cudaLaunchKernelEx(&cfg, render_backward_kernel, (const uint2*)g.ranges, (const uint32_t*)b.point_list, (const GaussRec*)g.rec, s.W, s.H,
 	                   s.grid_x, s.background, (const float*)im.final_T, (const uint32_t*)im.n_contrib, dL_dpix, dL_dpix_depth, g.acc,
-	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done, (const uint32_t*)s.upstream_ready, g.hdr);
+	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done, (const uint32_t*)s.upstream_ready, g.hdr,
+	                   band ? s.band_y0 * s.grid_x : 0);
 }
 
 }  // namespace gsr

@@ -98,6 +98,10 @@ __device__ void mat3_mul(const float* A, const float* B, float* C)      // row-m
 __global__ void tracking_step_kernel(TrackingStepArgs a)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	// The reference leaves its loop on the iteration that converged (`if converged: break`, slam_frontend.py:180,192-193): replays
+	// of a captured iteration behind it must leave pose, exposure, Adam state and the iteration counter exactly as they are
+	// (the camera block already holds the converged pose).
+	if (a.status[2] != 0) return;
 	// ---- Adam (torch defaults: betas 0.9 / 0.999, eps 1e-8), parameters start from 0 for the pose deltas ----
 	// parameter order: rot delta (3), trans delta (3), exposure_a, exposure_b   (slam_frontend.py:132-160)
 	float grad[8];

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgsr_b200.so")
 
 GSR_OK = 0
-GSR_ERR_ARG, GSR_ERR_CUDA, GSR_ERR_WORKSPACE, GSR_ERR_OVERFLOW = -1, -2, -3, -4
+GSR_ERR_ARG, GSR_ERR_CUDA, GSR_ERR_WORKSPACE, GSR_ERR_OVERFLOW, GSR_ERR_TIMEOUT = -1, -2, -3, -4, -5
 
 # every symbol include/gsr_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
@@ -20,6 +20,7 @@ EXPORTS = (
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
     "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand", "gsr_fused_loss_scratch_bytes",
+    "gsr_step_status",
 )
 
 
@@ -41,6 +42,7 @@ class GsrScene(C.Structure):
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
         ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
         ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p), ("fused_loss", C.POINTER(GsrFusedLoss)),
+        ("sort_on_demand", C.c_int), ("exact_exp", C.c_int), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
     ]
 
 
@@ -85,6 +87,7 @@ def load():
     lib.gsr_forward_nosync.argtypes = [sp, vp, sz, vp, sz, ll, ll, vp, sz, vp, vp, vp, vp, vp, vp]
     lib.gsr_forward_nosync_fuses_scatter.argtypes = [ip, ip, ip]
     lib.gsr_forward_overflowed.argtypes = [vp, vp, C.POINTER(ip), C.POINTER(ll)]
+    lib.gsr_step_status.argtypes = [vp, vp, C.POINTER(C.c_uint)]
     lib.gsr_rasterize_gaussians.argtypes = [sp, vp, sz, vp, sz, ALLOC_FN, vp, C.POINTER(vp), C.POINTER(ll),
                                             vp, vp, vp, vp, vp, vp]
     lib.gsr_rasterize_gaussians_backward.argtypes = [sp, vp, vp, vp, ll, vp, vp, vp] + [vp] * 9 + [vp]

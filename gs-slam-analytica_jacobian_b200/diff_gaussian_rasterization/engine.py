@@ -36,9 +36,13 @@ class _RawDeviceBytes:
 
 class RasterEngine:
     def __init__(self, gaussians, image_width, image_height, tanfovx, tanfovy, bg, sh_degree=0, scale_modifier=1.0,
-                 device="cuda", headroom=1.25):
+                 device="cuda", headroom=1.25, tau_slots=64, grad_flat=None):
         """gaussians: dict with means3D[P,3], opacities[P,1], shs[P,M,3] or colors_precomp[P,3],
-        scales[P,3]+rotations[P,4] or cov3D_precomp[P,6] (fp32 tensors; moved to `device`)."""
+        scales[P,3]+rotations[P,4] or cov3D_precomp[P,6] (fp32 tensors; moved to `device`).
+        tau_slots: rows of the [tau_slots, 8] pose-gradient block kept at the tail of grad_flat (a keyframe window reduces
+        the per-view dL/dtau of views split over ranks together with the per-Gaussian gradients).
+        grad_flat: share the flat gradient buffer of another engine over the SAME Gaussians (views of a window running on
+        several streams then add into one buffer: launch_backward(accumulate="atomic"))."""
         self.dev = torch.device(device)
         f = lambda k: (gaussians[k].to(self.dev, torch.float32).contiguous() if gaussians.get(k) is not None else None)
         self.g = {k: f(k) for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp")}
@@ -67,7 +71,12 @@ class RasterEngine:
         # flat per-Gaussian gradient buffer: [means3D 3P | colour part | opacity P | covariance part]
         ncol = 3 * M if self.g["shs"] is not None else 3
         ncov = 7 if self.g["scales"] is not None else 6
-        self.grad_flat = torch.zeros(P * (3 + ncol + 1 + ncov) + 32, **f32)   # +32: keeps every segment 16-B aligned
+        self.tau_slots = int(tau_slots)
+        n_flat = P * (3 + ncol + 1 + ncov) + 32 + 8 * self.tau_slots            # +32: keeps every segment 16-B aligned
+        if grad_flat is not None:
+            assert grad_flat.numel() == n_flat and grad_flat.device == self.dev and grad_flat.dtype == torch.float32
+        self.grad_flat = torch.zeros(n_flat, **f32) if grad_flat is None else grad_flat
+        self.tau_block = self.grad_flat[n_flat - 8 * self.tau_slots:].view(self.tau_slots, 8)   # row v: [rho, theta, 0, 0] of view v
         o = 0
 
         def take(n, shape):
@@ -126,6 +135,14 @@ class RasterEngine:
     def set_camera(self, packed, non_blocking=True):
         self.cam.copy_(packed, non_blocking=non_blocking)
 
+    def set_band(self, tile_row_begin=0, tile_row_end=0):
+        """Render only the tile rows [begin, end) of the view from now on (gsr_scene.tile_row_begin / tile_row_end; 0, 0 =
+        the whole image): Gaussians outside the band are culled (radii 0), pixels outside are not written, gradients and
+        n_touched are the band's share.  The captured graphs belong to the previous band."""
+        if (int(tile_row_begin), int(tile_row_end)) != (self.scene.tile_row_begin, self.scene.tile_row_end):
+            self.scene.tile_row_begin, self.scene.tile_row_end = int(tile_row_begin), int(tile_row_end)
+            self.graph_fwd = self.graph_bwd = self.graph_all = None
+
     # ---- capacity -------------------------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -180,22 +197,26 @@ class RasterEngine:
         self._densify_refs = (xyz_gradient_accum, denom, max_radii2D)      # keep the tensors alive
         self.graph_fwd = self.graph_bwd = self.graph_all = None
 
-    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False, upstream_ready=None):
+    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False, upstream_ready=None,
+                        tau_out=None):
         """dL_dcolor / dL_ddepth default to the engine's own buffers; accumulate=True adds this view's
-        per-Gaussian gradients into grad_flat (mapping window) instead of overwriting.
+        per-Gaussian gradients into grad_flat (mapping window) instead of overwriting; accumulate="atomic" does so with
+        REDs (several engines on different streams sharing one pre-zeroed grad_flat).  tau_out: a 6-float device tensor
+        that receives dL/dtau instead of g_tau (e.g. a row of tau_block).
         overlap_forward=True: ONLY directly behind launch_forward() on the same stream, with upstream gradients that were
         complete before it -- the compositing backward then starts tile by tile behind the compositing forward
         (programmatic dependent launch + per-tile flags, gsr_scene.overlap_forward) instead of waiting for its tail."""
         gc = self.dL_dcolor if dL_dcolor is None else dL_dcolor
         gd = self.dL_ddepth if dL_ddepth is None else dL_ddepth
-        self.scene.accumulate_grads = 1 if accumulate else 0
+        self.scene.accumulate_grads = 2 if accumulate == "atomic" else (1 if accumulate else 0)
         self.scene.overlap_forward = 1 if (overlap_forward and self.overlap) else 0
         self.scene.upstream_ready = None if upstream_ready is None else upstream_ready.data_ptr()
         try:
             _cabi.check(_L.gsr_rasterize_gaussians_backward(
                 C.byref(self.scene), _p(self.radii), _p(self.geom), _p(self.binning), self.capacity, _p(self.img),
                 _p(gc), _p(gd), _p(self.g_means3D), _p(self.g_means2D), _p(self.g_sh), _p(self.g_colors),
-                _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov), _p(self.g_tau), self._stream()), "backward")
+                _p(self.g_opacity), _p(self.g_scales), _p(self.g_rot), _p(self.g_cov),
+                _p(self.g_tau if tau_out is None else tau_out), self._stream()), "backward")
         finally:
             self.scene.accumulate_grads = 0
             self.scene.overlap_forward = 0
@@ -298,8 +319,16 @@ class RasterEngine:
                 self.launch_forward()
                 self.launch_backward(overlap_forward=True)
 
+    def status(self):
+        """Raw header words of the last step -- synchronises: dict(num_rendered, overflow, spin_timeout, max_tile)."""
+        out = (C.c_uint * 4)()
+        with torch.cuda.device(self.dev):
+            _cabi.check(_L.gsr_step_status(_p(self.geom), self._stream(), out), "step_status")
+        return dict(num_rendered=int(out[0]), overflow=int(out[1]), spin_timeout=int(out[2]), max_tile=int(out[3]))
+
     def header(self):
-        """(num_rendered, overflow) of the last forward -- synchronises."""
+        """(num_rendered, overflow) of the last forward -- synchronises.  Raises RuntimeError (GSR_ERR_TIMEOUT) when a
+        compositing backward gave up waiting for a tile flag / the upstream_ready word: that step's gradients are incomplete."""
         ov, need = C.c_int(0), C.c_longlong(0)
         with torch.cuda.device(self.dev):
             _cabi.check(_L.gsr_forward_overflowed(_p(self.geom), self._stream(), C.byref(ov), C.byref(need)), "overflowed")

@@ -101,6 +101,7 @@ def camera_block_from_pose(pose, camera_block):
     """Fill the engine's camera block from the current R, T without moving the pose (zero gradients, fresh Adam state)."""
     z6 = torch.zeros(6, dtype=torch.float32, device=pose.dev)
     adam, status, expo = pose.adam.clone(), pose.status.clone(), pose.exposure.clone()
+    pose.status.zero_()      # (a frame that has converged ignores further steps)
     tracking_step(pose, z6, None, camera_block, 0.0, 0.0, 0.0, -1.0)
     pose.adam.copy_(adam); pose.status.copy_(status); pose.exposure.copy_(expo)
 
@@ -188,42 +189,48 @@ class MappingWindow:
     def __init__(self, window, gt_colors, gt_depths=None, exposures=None, rgb_boundary_threshold=0.01, alpha=0.95, initialization=False,
                  fused=None):
         """gt_colors [V,3,H,W], gt_depths [V,1,H,W] or None (monocular), exposures [V,2] device tensor or None.
-        fused (default: single-engine windows): the loss of every view is evaluated in its forward's epilogue."""
+        fused (default): the loss of every unit is evaluated in its forward's epilogue; a unit that is a band of tile rows
+        yields the band's share of the view's loss / dL/dexposure (the shares of a view add up)."""
         self.win, self.eng = window, window.engine
         self.gt_colors, self.gt_depths, self.exposures = gt_colors, gt_depths, exposures
         self.kw = dict(rgb_boundary_threshold=rgb_boundary_threshold, alpha=alpha)
         self.initialization = initialization
         self.ws = LossWorkspace(self.eng.W, self.eng.H, self.eng.dev)
         n = max(len(window.views), 1)
-        self.view_sums = torch.zeros((n, 4), dtype=torch.float32, device=self.eng.dev)    # per local view: loss, dL/da, dL/db, 0
+        self.view_sums = torch.zeros((n, 4), dtype=torch.float32, device=self.eng.dev)    # per local unit: loss, dL/da, dL/db, 0
         self.fused = None
         if fused is None:
-            fused = len(window.engines) == 1
+            fused = True
         if fused:
-            assert len(window.engines) == 1, "the fused loss writes into the one engine's upstream buffers"
-            self.fused = {}
+            self.fused = []
             for i, v in enumerate(window.views):
                 expo = None if (initialization or exposures is None) else exposures[v]
+                e = window.engine_of(i)
 
-                class _Slot:      # a LossWorkspace whose sums are this view's row and whose gradients are the engine's buffers
+                class _Slot:      # a LossWorkspace whose sums are this unit's row and whose gradients are its engine's buffers
                     pass
                 slot = _Slot()
-                slot.W, slot.H, slot.dev, slot.sums = self.eng.W, self.eng.H, self.eng.dev, self.view_sums[i]
-                slot.dL_dcolor, slot.dL_ddepth = self.eng.dL_dcolor, self.eng.dL_ddepth
-                self.fused[v] = FusedLoss(slot, gt_colors[v], None if gt_depths is None else gt_depths[v], None, expo, tracking=False,
-                                          **self.kw)
+                slot.W, slot.H, slot.dev, slot.sums = e.W, e.H, e.dev, self.view_sums[i]
+                slot.dL_dcolor, slot.dL_ddepth = e.dL_dcolor, e.dL_ddepth
+                self.fused.append(FusedLoss(slot, gt_colors[v], None if gt_depths is None else gt_depths[v], None, expo, tracking=False,
+                                            **self.kw))
 
     def iteration(self, reduce=True, on_view=None):
         """Returns (grad_flat summed over all views of all ranks, per-local-view sums [n,4], per-local-view dL/dtau [n,6])."""
         eng, local = self.eng, {v: i for i, v in enumerate(self.win.views)}
 
-        def upstream(v):
+        def upstream(v, e=None):
+            # (stand-alone loss kernel: whole views only -- it reads every pixel of the rendered images)
+            e = eng if e is None else e
             expo = None if (self.initialization or self.exposures is None) else self.exposures[v]
-            slam_loss(self.ws, eng.color, eng.depth, eng.opacity, self.gt_colors[v], None if self.gt_depths is None else self.gt_depths[v],
-                      None, expo, tracking=False, dL_dcolor=eng.dL_dcolor, dL_ddepth=eng.dL_ddepth, **self.kw)
+            slam_loss(self.ws, e.color, e.depth, e.opacity, self.gt_colors[v], None if self.gt_depths is None else self.gt_depths[v],
+                      None, expo, tracking=False, dL_dcolor=e.dL_dcolor, dL_ddepth=e.dL_ddepth, **self.kw)
             self.view_sums[local[v]].copy_(self.ws.sums, non_blocking=True)
-            return eng.dL_dcolor, eng.dL_ddepth
+            return e.dL_dcolor, e.dL_ddepth
 
+        if self.fused is None:
+            assert all(y1 == 0 for (_, _, y1) in self.win.units) and len(self.win.engines) == 1, \
+                "the stand-alone loss kernel needs whole views on one engine; use fused=True"
         flat = self.win.iteration(upstream, reduce=reduce, on_view=on_view,
-                                  fused_loss=None if self.fused is None else (lambda v: self.fused[v].struct))
+                                  fused_loss=None if self.fused is None else (lambda i, v: self.fused[i].struct))
         return flat, self.view_sums, self.win.tau

@@ -5,27 +5,83 @@ window through the same Gaussians, sums the losses and back-propagates once: aut
 gradients of every Gaussian parameter.  The views are independent given the (replicated) map, so the path
 shards by view:
 
-  * rank r owns views r, r + world, r + 2 world, ...   (round robin; V=10 on 8 GPUs -> 2/2/1/1/1/1/1/1)
-  * each rank runs forward + backward for its views on its own RasterEngine; the first local view
-    overwrites the flat per-Gaussian gradient buffer, the following ones accumulate into it in the
-    backward kernel itself (gsr_scene.accumulate_grads), so no extra add / memset passes;
-  * ONE all-reduce(sum) of that flat fp32 buffer per iteration (NCCL over NVLink / NVSwitch when the
-    process group is NCCL; gloo works for CPU tests of the host logic) gives every rank the window gradient;
-  * per-view results (dL/dtau = pose gradient, radii, n_touched, dL/dmeans2D, images) stay on the owning
-    rank -- each pose lives on one GPU, exactly like the reference keeps them per viewpoint
-    (utils/slam_backend.py:195-198,236-240,277-284).
-Candidate-pose batches for tracking (C3) use the same sharding with reduce=False: no collective at all.
+  * the work is cut into UNITS (view, tile_row_begin, tile_row_end).  floor(V / world) whole views go to every
+    rank round robin (rank r owns views r, r + world, ...); the V mod world views left over are not handed to a
+    few ranks whole (10 keyframes on 8 GPUs: two ranks with two views -> 5x at best) but split into bands of tile
+    rows (gsr_scene.tile_row_begin / tile_row_end), one band per rank (10 on 8: every rank renders one whole view
+    plus a quarter of a ninth / tenth view).  The bands of a view sum to the view: per-Gaussian gradients, dL/dtau
+    and n_touched are linear in the pixels;
+  * each rank runs forward + backward of its units on its RasterEngine(s); every unit ADDS its per-Gaussian
+    gradients into ONE flat buffer in the backward kernel itself (gsr_scene.accumulate_grads) -- read-modify-write
+    on one stream, REDs when several engines on as many streams share the buffer -- and writes its dL/dtau into
+    row `view` of the [V, 8] block at the tail of that buffer;
+  * ONE all-reduce(sum) of the flat buffer per iteration (NCCL over NVLink / NVSwitch when the process group is
+    NCCL; gloo works for CPU tests of the host logic) gives every rank the window gradient and every view's
+    dL/dtau;
+  * per-unit results (radii, n_touched, dL/dmeans2D, images) stay on the owning rank -- like the reference keeps
+    them per viewpoint (utils/slam_backend.py:195-198,236-240,277-284).
+Candidate-pose batches for tracking (C3) use the same sharding with reduce=False and no bands: no collective at all.
 """
+import math
+
 import torch
 
 
 def shard_views(num_views, world_size, rank):
-    """Round-robin owner map: the views rank `rank` renders."""
+    """Round-robin owner map of WHOLE views: the views rank `rank` renders when nothing is split."""
     return list(range(rank, num_views, world_size))
 
 
 def owner_of(view, world_size):
     return view % world_size
+
+
+def band_rows(grid_y, parts, weights=None):
+    """Cut grid_y tile rows into `parts` consecutive bands [(begin, end), ...]: equal row counts, or -- weights = work per
+    tile row (e.g. instances per row from a calibration pass) -- equal work.  Every band holds at least one row while
+    grid_y >= parts; bands may be empty (begin == end) beyond that."""
+    parts = int(parts)
+    if weights is None:
+        cuts = [(grid_y * k) // parts for k in range(parts + 1)]
+    else:
+        w = [max(float(x), 0.0) for x in weights]
+        assert len(w) == grid_y
+        total = sum(w) or 1.0
+        cuts, acc, k = [0], 0.0, 1
+        for y in range(grid_y):
+            acc += w[y]
+            while k < parts and acc >= total * k / parts and len(cuts) <= k:
+                cuts.append(y + 1)
+                k += 1
+        while len(cuts) < parts:
+            cuts.append(grid_y)
+        cuts.append(grid_y)
+        if grid_y >= parts:        # no empty band: push cuts apart
+            for k in range(1, parts):
+                cuts[k] = min(max(cuts[k], cuts[k - 1] + 1), grid_y - (parts - k))
+    return [(cuts[k], cuts[k + 1]) for k in range(parts)]
+
+
+def plan_units(num_views, world_size, grid_y, split=True, row_weights=None):
+    """The units (view, tile_row_begin, tile_row_end) of every rank: list (per rank) of lists.  (view, 0, 0) = whole view.
+    split=False reproduces shard_views.  row_weights: optional {view: work per tile row} for equal-work bands."""
+    V, N = int(num_views), int(world_size)
+    units = [[] for _ in range(N)]
+    whole = V if not split else (V // N) * N
+    for v in range(whole):
+        units[v % N].append((v, 0, 0))
+    rem = V - whole
+    if rem:
+        b = N // math.gcd(rem, N)                 # bands per left-over view: rem * b units, rem / gcd per rank
+        b = min(b, max(int(grid_y), 1))
+        j = 0
+        for v in range(whole, V):
+            bands = band_rows(grid_y, b, None if row_weights is None else row_weights.get(v))
+            for (y0, y1) in bands:
+                if y1 > y0:
+                    units[j % N].append((v, y0, y1) if b > 1 else (v, 0, 0))
+                j += 1
+    return units
 
 
 def allreduce_window_gradients(grad_flat, group=None):
@@ -39,91 +95,115 @@ def allreduce_window_gradients(grad_flat, group=None):
 
 
 class KeyframeWindow:
-    """Runs the views a rank owns through a RasterEngine and reduces the window gradient.
+    """Runs the units a rank owns through its RasterEngine(s) and reduces the window gradient.
 
     cameras: [V, 52] packed camera blocks (RasterEngine.pack_camera) resident on the engine's device.
     upstream(v) -> (dL_dcolor[3,H,W], dL_ddepth[1,H,W]) device tensors for view v, called AFTER view v's
     forward so it may depend on engine.color / engine.depth (the loss gradient); or a pair of
-    [V,3,H,W] / [V,1,H,W] tensors.
+    [V,3,H,W] / [V,1,H,W] tensors.  For a band unit only the band's pixel rows of the engine's images are valid and
+    only the band's rows of the upstream gradients are read.
 
-    extra_engines: further RasterEngines over the SAME Gaussians (own workspaces and output buffers).  The local views
-    are then dealt round robin to the engines, each on its own CUDA stream, so that the latency-bound stages of one view
-    (per-Gaussian kernels, scatter, sort) overlap the issue-bound compositing of another; every engine accumulates into
-    its own flat gradient buffer and the buffers are summed into the first engine's before the all-reduce.  With several
-    engines `upstream` is called as upstream(v, engine).
+    extra_engines: further RasterEngines over the SAME Gaussians, constructed with grad_flat=engine.grad_flat (own
+    workspaces and output buffers, ONE gradient buffer).  The local units are then dealt round robin to the engines, each
+    on its own CUDA stream, so that the latency-bound stages of one view (per-Gaussian kernels, scatter) overlap the
+    issue-bound compositing of another; all of them add into the shared buffer with REDs.  With several engines
+    `upstream` is called as upstream(v, engine).
+
+    split=True (default): views left over after every rank has floor(V / world) whole ones are split into bands of tile
+    rows over the ranks (plan_units).  `self.views` lists the views of this rank's units, `self.units` the units.
     """
 
-    def __init__(self, engine, cameras, rank=0, world_size=1, group=None, extra_engines=()):
+    def __init__(self, engine, cameras, rank=0, world_size=1, group=None, extra_engines=(), split=True, row_weights=None):
         self.engine, self.cameras = engine, cameras
         self.engines = [engine] + list(extra_engines)
+        for e in self.engines[1:]:
+            assert e.grad_flat.data_ptr() == engine.grad_flat.data_ptr(), "extra engines must share the first engine's grad_flat"
         self.rank, self.world, self.group = rank, world_size, group
-        self.views = shard_views(int(cameras.shape[0]), world_size, rank)
-        V = len(self.views)
-        dev = engine.dev
-        self.tau = torch.zeros((V, 6), dtype=torch.float32, device=dev)             # per local view [rho, theta]
-        self.num_rendered = [0] * V
-        self.streams = [torch.cuda.Stream(dev) for _ in self.engines] if len(self.engines) > 1 else None
+        self.num_views = int(cameras.shape[0])
+        assert self.num_views <= engine.tau_slots, "more views than tau_slots of the engine"
+        grid_y = (engine.H + 15) // 16
+        self.plan = plan_units(self.num_views, world_size, grid_y, split=split, row_weights=row_weights)
+        self.units = self.plan[rank]
+        self.views = [u[0] for u in self.units]
+        n = len(self.units)
+        self.num_rendered = [0] * n
+        self.streams = [torch.cuda.Stream(engine.dev) for _ in self.engines] if len(self.engines) > 1 else None
+        # dL/dtau of EVERY view of the window (complete after the all-reduce; rows of other ranks' whole views are theirs)
+        self.tau_all = engine.tau_block[:self.num_views, :6]
+
+    def engine_of(self, local_unit):
+        """The engine that runs local unit i (units are dealt round robin to the engines)."""
+        return self.engines[local_unit % len(self.engines)]
+
+    @property
+    def tau(self):
+        """[local units, 6]: dL/dtau = [rho, theta] of the views of this rank's units (a view split into bands holds the
+        sum over its bands once the iteration has been reduced)."""
+        return self.tau_all[self.views] if self.views else self.tau_all[:0]
 
     def calibrate(self):
-        """Size the binning workspace for the largest local view (one exact plan per view)."""
+        """Size the binning workspaces for the largest local unit (one exact plan per unit and engine)."""
         for e in self.engines:
-            for v in self.views:
+            for (v, y0, y1) in self.units:
                 e.set_camera(self.cameras[v])
+                e.set_band(y0, y1)
                 e.calibrate()
 
     def iteration(self, upstream, reduce=True, on_view=None, upstream_precomputed=False, fused_loss=None):
-        """One window iteration.  Returns engine.grad_flat (summed over all views of all ranks when
-        reduce=True).  on_view(local_index, view) can read the engine's per-view outputs.
+        """One window iteration.  Returns engine.grad_flat (summed over all units of all ranks when reduce=True; its tail
+        holds every view's dL/dtau, self.tau_all).  on_view(local_index, view) can read the engine's per-unit outputs.
         upstream_precomputed=True: the upstream gradients do not depend on this iteration's renders and upstream() launches
-        nothing -- every view's compositing backward then starts tile by tile behind its forward
+        nothing -- every unit's compositing backward then starts tile by tile behind its forward
         (RasterEngine.launch_backward(overlap_forward=True)).
-        fused_loss: callable view -> _cabi.GsrFusedLoss writing into the engine's upstream buffers (slam_ops.FusedLoss): the
-        loss of every view is evaluated inside its forward, `upstream` is not called, the backward overlaps the forward
-        (single-engine windows)."""
+        fused_loss: callable (local unit index, view) -> _cabi.GsrFusedLoss writing into the upstream buffers of the engine
+        that runs the unit (self.engine_of(i); slam_ops.FusedLoss): the loss of every unit is evaluated inside its forward,
+        `upstream` is not called, the backward overlaps the forward."""
         eng = self.engine
-        if not self.views:
-            eng.grad_flat.zero_()        # a rank without views still takes part in the collective
         if self.streams is None:
-            for i, v in enumerate(self.views):
+            if not self.units:
+                eng.grad_flat.zero_()        # a rank without units still takes part in the collective
+            else:
+                eng.tau_block.zero_()
+            for i, (v, y0, y1) in enumerate(self.units):
                 eng.set_camera(self.cameras[v])
+                eng.set_band(y0, y1)
                 if fused_loss is not None:
-                    eng.launch_forward(fused_loss=fused_loss(v))
-                    eng.launch_backward(accumulate=(i > 0), overlap_forward=True)
+                    eng.launch_forward(fused_loss=fused_loss(i, v))
+                    eng.launch_backward(accumulate=(i > 0), overlap_forward=True, tau_out=eng.tau_block[v])
                 else:
                     eng.launch_forward()
                     if callable(upstream):
                         gc, gd = upstream(v)
                     else:
                         gc, gd = upstream[0][v], upstream[1][v]
-                    eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed)
-                self.tau[i].copy_(eng.g_tau, non_blocking=True)
+                    eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed, tau_out=eng.tau_block[v])
                 if on_view is not None:
                     on_view(i, v)
         else:
             main = torch.cuda.current_stream(eng.dev)
-            used = [False] * len(self.engines)
+            eng.grad_flat.zero_()            # every unit ADDS (REDs): the engines run concurrently into one buffer
             for st in self.streams:
                 st.wait_stream(main)
-            for i, v in enumerate(self.views):
+            for i, (v, y0, y1) in enumerate(self.units):
                 k = i % len(self.engines)
                 e = self.engines[k]
                 with torch.cuda.stream(self.streams[k]):
                     e.set_camera(self.cameras[v])
-                    e.launch_forward()
-                    if callable(upstream):
-                        gc, gd = upstream(v, e)
+                    e.set_band(y0, y1)
+                    if fused_loss is not None:
+                        e.launch_forward(fused_loss=fused_loss(i, v))
+                        e.launch_backward(accumulate="atomic", overlap_forward=True, tau_out=eng.tau_block[v])
                     else:
-                        gc, gd = upstream[0][v], upstream[1][v]
-                    e.launch_backward(gc, gd, accumulate=used[k], overlap_forward=upstream_precomputed)
-                    used[k] = True
-                    self.tau[i].copy_(e.g_tau, non_blocking=True)
+                        e.launch_forward()
+                        if callable(upstream):
+                            gc, gd = upstream(v, e)
+                        else:
+                            gc, gd = upstream[0][v], upstream[1][v]
+                        e.launch_backward(gc, gd, accumulate="atomic", overlap_forward=upstream_precomputed, tau_out=eng.tau_block[v])
                     if on_view is not None:
                         on_view(i, v)
             for st in self.streams:
                 main.wait_stream(st)
-            for k in range(1, len(self.engines)):
-                if used[k]:
-                    eng.grad_flat.add_(self.engines[k].grad_flat)
         if reduce:
             allreduce_window_gradients(eng.grad_flat, self.group)
         return eng.grad_flat

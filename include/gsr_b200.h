@@ -25,7 +25,10 @@
  * alternative path exactly like the reference's empty tensors (forward.cu:207,382).
  * All work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream).  Functions return
  * GSR_OK or a negative error code and never throw; gsr_error_string() explains the last failure
- * of the calling thread.  The library holds no global mutable state besides that string.
+ * of the calling thread.
+ * Process-wide state, all of it optional and off the data path: the default threshold of gsr_sort_on_demand (per call:
+ * gsr_scene.sort_on_demand), the launch counter, and the opt-in stage timing (events kept per device).  Everything a call
+ * computes lives in the caller's workspaces, so calls on different workspaces may run concurrently from different threads.
  */
 #ifndef GSR_B200_H
 #define GSR_B200_H
@@ -40,6 +43,7 @@ extern "C" {
 #define GSR_ERR_CUDA -2       /* a CUDA call failed */
 #define GSR_ERR_WORKSPACE -3  /* a caller-provided workspace is too small */
 #define GSR_ERR_OVERFLOW -4   /* num_rendered exceeded the binning capacity (no-sync mode) */
+#define GSR_ERR_TIMEOUT -5    /* a compositing-backward CTA gave up waiting for a tile flag / the upstream_ready word */
 
 /* Optional: the SLAM loss of the view evaluated in the epilogue of the forward compositing kernel (the pixel values are
  * still in registers), see gsr_slam_loss below for the arithmetic (utils/slam_utils.py:56-128).  The forward then also
@@ -83,7 +87,10 @@ typedef struct gsr_scene {
 	                                dL_drotations/dL_dcov3D instead of overwriting them (what autograd's AccumulateGrad
 	                                does across the views of a mapping window, utils/slam_backend.py:168-232);
 	                                rows of culled Gaussians are then left untouched.  dL_dmeans2D and dL_dtau are
-	                                per-view quantities and are always overwritten. */
+	                                per-view quantities and are always overwritten.
+	                                1: read-modify-write -- the views adding into one buffer run in stream order;
+	                                2: atomic REDs -- views on DIFFERENT streams may add into one (pre-zeroed) buffer
+	                                   concurrently (the summation order, hence the last bits, then varies run to run) */
 	/* backward only, optional (null = off): densification statistics of the view, updated for the Gaussians with
 	 * radii > 0 in the backward's per-Gaussian epilogue instead of by masked torch ops afterwards
 	 * (gaussian_splatting/scene/gaussian_model.py:767-771, utils/slam_backend.py:115-121) */
@@ -103,10 +110,24 @@ typedef struct gsr_scene {
 	                                waits for it on the device, so that this dependency need not be a full edge in front of
 	                                the kernel (which would undo overlap_forward).  The caller clears the word before the
 	                                forward of the step and joins the other stream behind the backward.  If the word (or a
-	                                tile flag) does not arrive within about a second the kernel gives up and sets the
-	                                header's overflow word to 2 (gsr_forward_overflowed). */
+	                                tile flag) does not arrive within about a second the kernel gives up, the tile contributes
+	                                no gradients and the header's spin_timeout word is set: gsr_forward_overflowed() then
+	                                returns GSR_ERR_TIMEOUT, gsr_step_status() reports the raw word. */
 	const gsr_fused_loss* fused_loss; /* forward (gsr_forward_render / gsr_forward_nosync) only, optional (null = off):
 	                                host pointer, read during the call */
+	int sort_on_demand;          /* forward only: per-call form of gsr_sort_on_demand().  0 = the process default; > 0: lists
+	                                longer than this are ordered on demand; < 0: every list of this call is sorted completely */
+	int exact_exp;               /* forward only: 0 = the library default (exact; environment GSR_EXACT_EXP=0/1), > 0: alpha =
+	                                min(0.99, o * expf(power)) with the reference's own expf (forward.cu:496) -- T, hence every
+	                                threshold decision, n_contrib and n_touched are then bit-identical to the reference's;
+	                                < 0: one ex2.approx per pair (6 instructions less per pair; alpha within ~1e-6 relative,
+	                                n_contrib / n_touched then differ from the reference's on a ~1e-5 fraction of entries) */
+	int tile_row_begin, tile_row_end; /* forward + backward: render only the band of tile rows [begin, end) of the view
+	                                (rows of 16 pixels; 0, 0 = the whole image).  Gaussians whose tile rectangle does not
+	                                reach the band are culled for this call (radii 0, zero gradient rows); pixels outside the
+	                                band are not written; n_touched, every per-Gaussian gradient and dL_dtau are the band's
+	                                share -- the bands of a view sum to the whole view (a view of a mapping window split over
+	                                several GPUs, window.py).  Pass the same values to the backward of the same workspaces. */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
@@ -135,8 +156,12 @@ int gsr_forward_render(const gsr_scene* s, void* geom, void* binning, size_t bin
                        float* out_color /*[3,H,W]*/, float* out_depth /*[1,H,W]*/, float* out_opacity /*[1,H,W]*/,
                        int* n_touched /*[P]*/, void* stream);
 /* Synchronises and reports whether the last no-sync forward ran out of binning capacity
- * (*needed_host receives the required capacity). */
+ * (*needed_host receives the required capacity).  Returns GSR_ERR_TIMEOUT (outputs still filled in) when a compositing
+ * backward of these workspaces gave up waiting since the last forward (see gsr_scene.upstream_ready). */
 int gsr_forward_overflowed(void* geom, void* stream, int* overflowed_host, long long* needed_host);
+/* Synchronises and returns the raw header words of the last step: out4 = {num_rendered, overflow (binning capacity),
+ * spin_timeout (0 = none, 1 = a tile flag of the forward, 2 = the upstream_ready word never arrived), longest tile list}. */
+int gsr_step_status(void* geom, void* stream, unsigned int* out4_host);
 
 /* One-call forward with the reference's semantics: allocates the binning workspace through
  * `binning_alloc` once num_rendered is known, returns it in *num_rendered_host and the buffer in
@@ -217,15 +242,17 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
  * a threshold only as far as they are read, depth slab by depth slab: point_list then holds the reference's list exactly
  * up to (at least) each tile's deepest contributor and is unspecified behind it; all outputs and gradients are unchanged.
  * min_list_length > 0: lists longer than this are ordered on demand; 0: every list is sorted completely (what the
- * bit-exact list tests compare); < 0: query only.  Process-wide; returns the previous value.  Default 256
- * (environment: GSR_LAZY_MIN). */
+ * bit-exact list tests compare); < 0: query only.  Sets the process-wide DEFAULT (used by calls whose
+ * gsr_scene.sort_on_demand is 0); returns the previous value.  Default 256 (environment: GSR_LAZY_MIN). */
 int gsr_sort_on_demand(int min_list_length);
 
 /* ---- measurement hooks (bench.py) ---- */
 /* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
 unsigned long long gsr_kernel_launch_count(void);
-/* enable/disable CUDA-event stage timing; gsr_stage_times_ms returns the durations of the last
- * forward+backward: {preprocess, binning, render_forward, render_backward, preprocess_backward} */
+/* enable/disable CUDA-event stage timing (process-wide switch; the events are kept per device and created on first use
+ * there); gsr_stage_times_ms returns the durations of the last forward+backward timed on the CURRENT device:
+ * {preprocess, binning, render_forward, render_backward, preprocess_backward}.  While it is on, calls are launched without
+ * programmatic dependent launches (the event records sit between the kernels). */
 int gsr_stage_timing(int enable);
 int gsr_stage_times_ms(float* out5);
 /* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3 or 4][4096][8] %globaltimer table

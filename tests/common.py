@@ -44,24 +44,20 @@ def settings_from_scene(sc_t):
         prefiltered=False, debug=bool(sc_t.get("debug", False)))
 
 
-def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, on_demand=0):
+def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, on_demand=0, exact_exp=0, lean=False):
     """Run the product path through its C-ABI on `device`; returns outputs, internals and gradients
-    as numpy arrays.  sc: numpy scene dict (diff_gaussian_rasterization.scenes).
-    on_demand: gsr_sort_on_demand threshold for this call -- 0 (default here): every per-tile list is sorted completely,
-    so that the WHOLE point_list can be compared; > 0: lists longer than this are ordered only as far as they are read
-    (the library default is 1024)."""
+    as numpy arrays.  sc: numpy scene dict (tests/scenes.py).
+    on_demand: per-call threshold (gsr_scene.sort_on_demand) -- 0 (default here): every per-tile list is sorted completely,
+    so that the WHOLE point_list can be compared; > 0: lists longer than this are ordered only as far as they are read;
+    None: the library default (on demand, 256).
+    exact_exp: gsr_scene.exact_exp (0 = library default = exact, -1 = ex2.approx).
+    lean: skip the host copies of the per-Gaussian records (large scenes)."""
+    return _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand, exact_exp, lean)
+
+
+def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand=0, exact_exp=0, lean=False):
     import diff_gaussian_rasterization as dgr
-
-    prev = dgr._L.gsr_sort_on_demand(int(on_demand))
-    try:
-        return _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity)
-    finally:
-        dgr._L.gsr_sort_on_demand(prev)
-
-
-def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity):
-    import diff_gaussian_rasterization as dgr
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     t = S.to_torch(sc, device)
     rs = settings_from_scene(t)
@@ -71,6 +67,8 @@ def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity):
                      t.get("scales", e) if t.get("cov3D_precomp") is None else e,
                      t.get("rotations", e) if t.get("cov3D_precomp") is None else e,
                      t.get("cov3D_precomp", e) if t.get("cov3D_precomp") is not None else e)
+    call.scene.sort_on_demand = 0 if on_demand is None else (-1 if int(on_demand) == 0 else int(on_demand))
+    call.scene.exact_exp = int(exact_exp)
     R, cap, color, radii, geom, binning, img, depth, opacity, n_touched = dgr._forward_impl(call, capacity)
     torch.cuda.synchronize()
     P, W, H = call.P, call.W, call.H
@@ -82,12 +80,15 @@ def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity):
     R_dev = int(hdr[0])
     out["num_rendered"] = R_dev
     out["overflow"] = int(hdr[1])
-    rec = dev_view(ptrs[0], P * 48, torch.float32, device).view(P, 12).cpu().numpy()
+    rec = dev_view(ptrs[0], P * 48, torch.float32, device).view(P, 12)
     vis = radii.cpu().numpy() > 0
-    out["means2D"] = rec[:, 0:2].copy()
-    out["conic_opacity"] = np.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1)
-    out["depths"] = rec[:, 6].copy()
-    out["rgb"] = np.stack([rec[:, 7], rec[:, 8], rec[:, 9]], 1)
+    out["rec_dev"] = rec
+    if not lean:
+        rec = rec.cpu().numpy()
+        out["means2D"] = rec[:, 0:2].copy()
+        out["conic_opacity"] = np.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1)
+        out["depths"] = rec[:, 6].copy()
+        out["rgb"] = np.stack([rec[:, 7], rec[:, 8], rec[:, 9]], 1)
     out["tiles_touched"] = dev_view(ptrs[1], P * 4, torch.int32, device).cpu().numpy().astype(np.uint32)
     out["clamped_bits"] = dev_view(ptrs[2], P, torch.uint8, device).cpu().numpy()
     n_list = min(R_dev, cap)
@@ -131,7 +132,7 @@ class RefLib:
         return None if t is None else C.c_void_p(t.data_ptr())
 
     def forward(self, sc, device="cuda"):
-        from diff_gaussian_rasterization import scenes as S
+        import scenes as S
 
         t = S.to_torch(sc, device)
         P = int(t["means3D"].shape[0])

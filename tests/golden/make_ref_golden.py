@@ -4,7 +4,7 @@
     gpurun -- 'python tests/golden/make_ref_golden.py gpurun_out'      # then copy the .npz into tests/golden/
 
 Each fixture stores the seeded scene parameters (not the arrays: they are regenerated from the seed by
-diff_gaussian_rasterization.scenes), the upstream gradients' seed, and every reference output:
+tests/scenes.py), the upstream gradients' seed, and every reference output:
 radii, tiles_touched, depth keys, means2D, conic/opacity, rgb, per-tile ranges, the sorted point list,
 colour/depth/opacity images, final_T, n_contrib, n_touched and all gradients incl. dL/dtau.
 The CPU tests pin the oracle against these files; the GPU tests pin the CUDA product against them.
@@ -27,7 +27,7 @@ CASES = {
 
 
 def build_case(c):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = S.make_scene(c["cfg"], seed=c["seed"])
     sc["scales"] = sc["scales"] * np.float32(c["scale_mul"])

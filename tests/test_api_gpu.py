@@ -14,7 +14,7 @@ TOL = 1e-4
 
 
 def _scene(P=2500, sh_degree=0, seed=4):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg = dict(W=176, H=144, fx=160.0, fy=158.0, cx=88.0, cy=72.0, P=P, sh_degree=sh_degree)
     sc = S.make_scene(cfg, seed=seed)
@@ -34,7 +34,7 @@ def _oracle_grads(sc, dc, dd):
 @pytest.mark.parametrize("sh_degree", [0, 2])
 def test_autograd_end_to_end(sh_degree):
     from diff_gaussian_rasterization import GaussianRasterizer
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = _scene(sh_degree=sh_degree)
     t = S.to_torch(sc, "cuda")
@@ -72,7 +72,7 @@ def test_autograd_end_to_end(sh_degree):
 
 def test_backward_twice_and_determinism_of_integer_outputs():
     from diff_gaussian_rasterization import GaussianRasterizer
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = _scene(P=1500)
     t = S.to_torch(sc, "cuda")
@@ -98,7 +98,7 @@ def test_backward_twice_and_determinism_of_integer_outputs():
 
 def test_mark_visible_and_empty_input():
     from diff_gaussian_rasterization import GaussianRasterizer
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from oracle.gs_oracle import Oracle
 
     sc = _scene(P=4000)
@@ -116,7 +116,7 @@ def test_mark_visible_and_empty_input():
 
 def test_error_behaviour():
     from diff_gaussian_rasterization import GaussianRasterizer
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = _scene(P=100)
     t = S.to_torch(sc, "cuda")
@@ -135,7 +135,7 @@ def test_cabi_one_call_with_allocator_callback():
     data-dependent binning buffer, returns num_rendered)."""
     import diff_gaussian_rasterization as dgr
     from diff_gaussian_rasterization import _cabi
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = _scene(P=3000)
     t = S.to_torch(sc, "cuda")

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _scene(P, sh_degree=0, seed=11):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg = dict(W=176, H=144, fx=160.0, fy=158.0, cx=88.0, cy=72.0, P=P, sh_degree=sh_degree)
     sc = S.make_scene(cfg, seed=seed)
@@ -24,7 +24,7 @@ def _scene(P, sh_degree=0, seed=11):
 
 def _forward(sc):
     import diff_gaussian_rasterization as dgr
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     t = S.to_torch(sc, "cuda")
     e = torch.empty(0)
@@ -71,7 +71,7 @@ def _alloc(P, M, offset_floats=0, fill=None, colors=False):
 
 @pytest.mark.parametrize("P", [2501, 2560, 31])      # partial last slice (197 rows: 591 floats, 3-float tail), full slices, one warp
 def test_misaligned_outputs_equal_aligned_outputs(P):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     sc = _scene(P)
     dc, dd = S.make_pixel_grads(176, 144)
@@ -95,7 +95,7 @@ def test_misaligned_outputs_equal_aligned_outputs(P):
 
 
 def test_accumulation_adds_rows_and_leaves_culled_rows_alone():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     P = 2501
     sc = _scene(P)
@@ -116,7 +116,7 @@ def test_accumulation_adds_rows_and_leaves_culled_rows_alone():
 
 
 def test_colour_gradient_together_with_sh_gradient():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     P = 1800
     sc = _scene(P)

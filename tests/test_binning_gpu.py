@@ -24,7 +24,7 @@ def ref():
 
 def _identity_scene(W, H, P, seed, f=150.0):
     """Camera at the identity pose: camera-space depth == world z exactly, so depth bits can be planted."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cam = S.make_camera(W, H, f, f, W / 2 - 0.5, H / 2 - 0.5, np.eye(4))
     g = S.make_gaussians(P, cam, seed=seed)

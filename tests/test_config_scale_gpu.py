@@ -1,0 +1,161 @@
+"""Parity at the shapes BASELINE.json names: one view each of C1 (100 k Gaussians, 640x480), C1 at SH
+degree 3, C2 (500 k, 1200x680), C3 (300 k, 640x480) and C4 (3 M, 1920x1080) against the UNMODIFIED reference kernels
+(oracle/_ref/libgsref.so; rasterizer_impl.cu:198-516), through the public operator path AND through RasterEngine.step()
+(no-sync forward, CUDA graph, programmatic dependent launches; cooperative preprocess + scatter at C1, the two-kernel path
+above ~151 k Gaussians).  These sizes run every compiled kernel variant: preprocess_backward_kernel<4> (P > 113 664), the
+non-cooperative preprocess + scatter, id_bits = 22, lists ordered on demand at 2 k - 12 k entries per tile.
+
+Bars: radii / tiles_touched / depth bits / mean2D bits / conic bits / ranges bit-exact; point_list bit-exact (complete lists
+at C1 / C2, the consumed prefix of every tile in the default on-demand mode everywhere); n_contrib / n_touched / final_T
+bit-exact (gsr_scene.exact_exp default); images and every gradient incl. dL/dtau within 1e-4 in the max norm AND the L2
+norm (north_star: rel <= 1e-4).  The flip rate of n_contrib / n_touched with ex2.approx (exact_exp = -1) is printed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import REF_LIB, RefLib, l2_err, rel_err, run_ours
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+CASES = {
+    # name: (config, SH degree override, complete-list comparison too)
+    "C1": ("C1_tum_tracking", None, True),
+    "C1_sh3": ("C1_tum_tracking", 3, False),
+    "C2": ("C2_replica_mapping", None, True),
+    "C3": ("C3_batched_tracking", None, False),
+    "C4": ("C4_large", None, False),
+}
+GRADS = ("dL_dmeans3D", "dL_dmean2D", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dsh", "dL_dtau")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libgsref.so not built")
+    r = RefLib()
+    yield r
+    r.close()
+
+
+def _scene(case):
+    import scenes as S
+
+    name, deg, _ = CASES[case]
+    cfg = dict(S.CONFIGS[name])
+    if deg is not None:
+        cfg["sh_degree"] = deg
+    return cfg, S.make_scene(cfg, seed=0)
+
+
+def _tile_top(n_contrib, W, H):
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    nc = np.zeros((gy * 16, gx * 16), np.int64)
+    nc[:H, :W] = n_contrib
+    return nc.reshape(gy, 16, gx, 16).max(axis=(1, 3)).ravel()
+
+
+def _consumed_mask(ranges, top):
+    """bool[R]: positions of every tile's list up to its deepest contributor."""
+    start = ranges[:, 0].astype(np.int64)
+    n = ranges[:, 1].astype(np.int64) - start
+    assert (top <= n).all()
+    R = int(ranges[:, 1].max())
+    mark = np.zeros(R + 1, np.int32)
+    nz = top > 0
+    np.add.at(mark, start[nz], 1)
+    np.add.at(mark, (start + top)[nz], -1)
+    return np.cumsum(mark[:-1]) > 0
+
+
+def _close(a, b, what, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b).reshape(np.asarray(a).shape)
+    e_inf, e_2 = rel_err(a, b), l2_err(a, b)
+    assert e_inf <= tol and e_2 <= tol, "%s: max-norm %.3e, L2 %.3e" % (what, e_inf, e_2)
+    return e_inf, e_2
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_config_scale_parity(ref, case):
+    import scenes as S
+    from diff_gaussian_rasterization.engine import RasterEngine
+
+    cfg, sc = _scene(case)
+    W, H, P = cfg["W"], cfg["H"], cfg["P"]
+    dc, dd = S.make_pixel_grads(W, H, seed=1)
+    r = ref.forward(sc)
+    rb = ref.backward(sc, dc, dd)
+    vis = r["visible"]
+
+    # ---- public operator path, library defaults (lists ordered on demand, exact exp) ----
+    o = run_ours(sc, dc, dd, on_demand=None)
+    assert o["overflow"] == 0 and o["num_rendered"] == r["num_rendered"]
+    np.testing.assert_array_equal(o["radii"], r["radii"])
+    np.testing.assert_array_equal(o["tiles_touched"], r["tiles_touched"])
+    np.testing.assert_array_equal(o["depths"][vis].view(np.uint32), r["depths"][vis].view(np.uint32))
+    np.testing.assert_array_equal(o["means2D"][vis].view(np.uint32), r["means2D"][vis].view(np.uint32))
+    np.testing.assert_array_equal(o["conic_opacity"][vis].view(np.uint32), r["conic_opacity"][vis].view(np.uint32))
+    np.testing.assert_array_equal(o["ranges"], r["ranges"])
+    top = _tile_top(o["n_contrib"], W, H)
+    used = _consumed_mask(r["ranges"], top)
+    np.testing.assert_array_equal(o["point_list"][used], r["point_list"][used])
+    consumed = float(used.sum()) / max(r["num_rendered"], 1)
+    # integer outputs and the transmittance: the reference's, bit for bit
+    np.testing.assert_array_equal(o["n_contrib"], r["n_contrib"])
+    np.testing.assert_array_equal(o["n_touched"], r["n_touched"])
+    np.testing.assert_array_equal(o["final_T"].view(np.uint32), r["final_T"].view(np.uint32))
+    errs = {}
+    for k in ("color", "depth", "opacity"):
+        errs[k] = _close(o[k], r[k], k)
+    for k in GRADS:
+        if rb.get(k) is not None and o.get(k) is not None:
+            errs[k] = _close(o[k], rb[k], k)
+
+    # ---- complete lists (C1, C2): the whole point_list ----
+    if CASES[case][2]:
+        oc = run_ours(sc, None, None, on_demand=0, lean=True)
+        np.testing.assert_array_equal(oc["point_list"], r["point_list"])
+        np.testing.assert_array_equal(oc["n_contrib"], r["n_contrib"])
+        np.testing.assert_array_equal(oc["color"], o["color"])
+
+    # ---- flip rate of the integer outputs with one ex2.approx per pair instead of the reference's expf ----
+    of = run_ours(sc, None, None, on_demand=None, exact_exp=-1, lean=True)
+    flips_c = float(np.mean(of["n_contrib"] != r["n_contrib"]))
+    flips_t = float(np.mean(of["n_touched"][vis] != r["n_touched"][vis]))
+    assert flips_c <= 1e-3 and flips_t <= 1e-3
+    for k in ("color", "depth", "opacity"):
+        _close(of[k], r[k], k + " (ex2.approx)")
+
+    # ---- RasterEngine.step(): no host sync, CUDA graph, overlapped backward ----
+    t = S.to_torch(sc, "cuda")
+    eng = RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
+                       W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"])
+    eng.set_camera(RasterEngine.pack_camera(*(torch.from_numpy(sc[k]) for k in ("viewmatrix", "projmatrix", "projmatrix_raw", "campos"))).cuda())
+    eng.dL_dcolor.copy_(torch.from_numpy(dc)); eng.dL_ddepth.copy_(torch.from_numpy(dd))
+    assert eng.calibrate() == r["num_rendered"]
+    for use_graph in (False, True):
+        eng.step(use_graph=use_graph)
+        torch.cuda.synchronize()
+        R, ov = eng.header()
+        assert R == r["num_rendered"] and not ov
+        np.testing.assert_array_equal(eng.radii.cpu().numpy(), r["radii"])
+        np.testing.assert_array_equal(eng.n_touched.cpu().numpy(), r["n_touched"])
+        np.testing.assert_array_equal(eng.color.cpu().numpy(), o["color"])
+        np.testing.assert_array_equal(eng.depth.cpu().numpy(), o["depth"])
+        _close(eng.g_tau.cpu().numpy(), rb["dL_dtau"], "engine dL_dtau")
+        _close(eng.g_means3D.cpu().numpy(), rb["dL_dmeans3D"], "engine dL_dmeans3D")
+        _close(eng.g_means2D.cpu().numpy(), rb["dL_dmean2D"], "engine dL_dmean2D")
+        _close(eng.g_opacity.cpu().numpy(), rb["dL_dopacity"], "engine dL_dopacity")
+        _close(eng.g_scales.cpu().numpy(), rb["dL_dscales"], "engine dL_dscales")
+        _close(eng.g_rot.cpu().numpy(), rb["dL_drotations"], "engine dL_drotations")
+        _close(eng.g_sh.cpu().numpy(), rb["dL_dsh"], "engine dL_dsh")
+    from diff_gaussian_rasterization import _cabi
+    coop = bool(_cabi.load().gsr_forward_nosync_fuses_scatter(P, W, H))
+    print("\n[config-scale %s] P=%d %dx%d SH%d R=%d longest list %d consumed %.1f%% | cooperative preprocess+scatter: %s | "
+          "ex2.approx flip rate n_contrib %.2e n_touched %.2e | max-norm / L2 errors: %s"
+          % (case, P, W, H, cfg["sh_degree"], r["num_rendered"], int((r["ranges"][:, 1] - r["ranges"][:, 0]).max()), 100 * consumed,
+             coop, flips_c, flips_t, ", ".join("%s %.1e/%.1e" % (k, a, b) for k, (a, b) in errs.items())))
+    del eng
+    torch.cuda.empty_cache()

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _scene_and_cams(P=6000, V=4):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg = dict(W=208, H=160, fx=190.0, fy=188.0, cx=104.0, cy=80.0, P=P, sh_degree=0)
     sc = S.make_scene(cfg, seed=8)
@@ -20,14 +20,14 @@ def _scene_and_cams(P=6000, V=4):
     return cfg, sc, cams
 
 
-def _engine(sc, cfg):
-    from diff_gaussian_rasterization import scenes as S
+def _engine(sc, cfg, **kw):
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     t = S.to_torch(sc, "cuda")
     return RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"],
                              rotations=t["rotations"]), cfg["W"], cfg["H"], sc["tanfovx"], sc["tanfovy"], sc["bg"],
-                        sh_degree=cfg["sh_degree"])
+                        sh_degree=cfg["sh_degree"], **kw)
 
 
 def _pack(cam):
@@ -37,7 +37,7 @@ def _pack(cam):
 
 
 def test_engine_graph_matches_per_call_path():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg, sc, cams = _scene_and_cams(V=3)
     dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=2)
@@ -63,7 +63,7 @@ def test_engine_graph_matches_per_call_path():
 
 
 def test_engine_overflow_is_detected_and_recovered():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg, sc, cams = _scene_and_cams(V=1)
     eng = _engine(sc, cfg)
@@ -80,7 +80,7 @@ def test_engine_overflow_is_detected_and_recovered():
 
 
 def test_window_accumulates_views():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.window import KeyframeWindow
 
     V = 4
@@ -110,7 +110,7 @@ def test_window_accumulates_views():
 def test_densification_statistics_in_backward_epilogue():
     """xyz_gradient_accum / denom / max_radii2D updated by the backward kernel == the reference's masked torch ops after
     each view (gaussian_splatting/scene/gaussian_model.py:767-771, utils/slam_backend.py:115-121)."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.window import KeyframeWindow
 
     V = 3
@@ -150,7 +150,7 @@ def test_densification_statistics_in_backward_epilogue():
 def test_host_driven_step_graph_matches_resident_step():
     """RasterEngine.capture_host_step / step_host (pinned camera block + upstream gradients copied inside the graph,
     results copied back) == the device-resident step at the same pose."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg, sc, cams = _scene_and_cams(V=3)
     dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=4)
@@ -175,7 +175,7 @@ def test_fused_sort_survives_lists_longer_than_the_hint():
     """The engine decides from its calibrated longest-list hint whether the forward kernel sorts its own tiles (lists up to one
     shared-memory chunk).  If a later pose produces longer lists than the hint promised, the fused kernel must still sort them
     (general path) -- slower, never wrong."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfg = dict(W=160, H=128, fx=120.0, fy=120.0, cx=79.5, cy=63.5, P=15000, sh_degree=0)
     sc = S.make_scene(cfg, seed=6)
@@ -199,7 +199,7 @@ def test_fused_sort_survives_lists_longer_than_the_hint():
 
 
 def test_window_with_two_engines_on_two_streams_matches_one_engine():
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.window import KeyframeWindow
 
     V = 5
@@ -213,7 +213,8 @@ def test_window_with_two_engines_on_two_streams_matches_one_engine():
     w1.calibrate()
     flat1 = w1.iteration((gc, gd)).clone()
     tau1 = w1.tau.clone()
-    ea, eb = _engine(sc, cfg), _engine(sc, cfg)
+    ea = _engine(sc, cfg)
+    eb = _engine(sc, cfg, grad_flat=ea.grad_flat)      # one gradient buffer, REDs from both streams
     w2 = KeyframeWindow(ea, packed, extra_engines=[eb])
     w2.calibrate()
     for _ in range(2):      # twice: the second iteration must not see leftovers of the first
@@ -221,3 +222,84 @@ def test_window_with_two_engines_on_two_streams_matches_one_engine():
         torch.cuda.synchronize()
         assert rel_err(flat2.cpu().numpy(), flat1.cpu().numpy()) <= 1e-5
         assert rel_err(w2.tau.cpu().numpy(), tau1.cpu().numpy()) <= 1e-5
+
+
+def test_bands_of_a_view_sum_to_the_view():
+    """gsr_scene.tile_row_begin / tile_row_end: the bands of a view partition its pixels, and per-Gaussian gradients, dL/dtau
+    and n_touched are linear in the pixels (window.py splits left-over keyframes over the ranks this way)."""
+    import scenes as S
+    from diff_gaussian_rasterization.window import band_rows
+
+    cfg, sc, cams = _scene_and_cams(V=1)
+    dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"], seed=41)
+    eng = _engine(sc, cfg)
+    eng.set_camera(_pack(cams[0]).cuda())
+    eng.dL_dcolor.copy_(torch.from_numpy(dc)); eng.dL_ddepth.copy_(torch.from_numpy(dd))
+    eng.calibrate()
+    eng.step(use_graph=False)
+    torch.cuda.synchronize()
+    full = dict(color=eng.color.clone(), depth=eng.depth.clone(), opacity=eng.opacity.clone(), n_touched=eng.n_touched.clone(),
+                radii=eng.radii.clone(), flat=eng.grad_flat.clone(), tau=eng.g_tau.clone(), m2d=eng.g_means2D.clone())
+    grid_y = (cfg["H"] + 15) // 16
+    for parts in (2, 3):
+        color, depth, opacity = torch.zeros_like(eng.color), torch.zeros_like(eng.depth), torch.zeros_like(eng.opacity)
+        n_touched, radii = torch.zeros_like(eng.n_touched), torch.zeros_like(eng.radii)
+        tau, m2d = torch.zeros_like(eng.g_tau), torch.zeros_like(eng.g_means2D)
+        for k, (y0, y1) in enumerate(band_rows(grid_y, parts)):
+            eng.set_band(y0, y1)
+            eng.calibrate()
+            eng.launch_forward()
+            eng.launch_backward(accumulate=(k > 0))
+            torch.cuda.synchronize()
+            R, ov = eng.header()
+            assert not ov
+            r0, r1 = 16 * y0, min(16 * y1, cfg["H"])
+            color[:, r0:r1] = eng.color[:, r0:r1]; depth[:, r0:r1] = eng.depth[:, r0:r1]; opacity[:, r0:r1] = eng.opacity[:, r0:r1]
+            n_touched += eng.n_touched
+            radii = torch.maximum(radii, eng.radii)
+            tau += eng.g_tau
+            m2d += eng.g_means2D
+        flat = eng.grad_flat.clone()
+        # the last band once more as a captured graph (forward + overlapped backward): same per-band results
+        tau_band, nt_band = eng.g_tau.clone(), eng.n_touched.clone()
+        eng.step(use_graph=True)
+        torch.cuda.synchronize()
+        assert rel_err(eng.g_tau.cpu().numpy(), tau_band.cpu().numpy()) <= 2e-5 and torch.equal(eng.n_touched, nt_band)
+        assert torch.equal(color, full["color"]) and torch.equal(depth, full["depth"]) and torch.equal(opacity, full["opacity"])
+        assert torch.equal(n_touched, full["n_touched"])
+        # a Gaussian's radius is reported by every band its rectangle reaches; one that no band renders has no tiles at all
+        assert torch.equal(radii, full["radii"])
+        assert rel_err(flat.cpu().numpy(), full["flat"].cpu().numpy()) <= 2e-5
+        assert rel_err(tau.cpu().numpy(), full["tau"].cpu().numpy()) <= 2e-5
+        assert rel_err(m2d.cpu().numpy(), full["m2d"].cpu().numpy()) <= 2e-5
+    eng.set_band(0, 0)
+
+
+def test_window_plan_splits_leftover_views_and_matches_unsplit_window():
+    """10 views on 8 ranks (simulated one rank at a time on this GPU): every rank holds one whole view + one band; the sum of
+    the ranks' buffers is the unsplit window's gradient and every view's dL/dtau."""
+    import scenes as S
+    from diff_gaussian_rasterization.window import KeyframeWindow, plan_units
+
+    V, world = 5, 4
+    cfg, sc, cams = _scene_and_cams(V=V)
+    packed = torch.stack([_pack(c) for c in cams]).cuda()
+    grads = [S.make_pixel_grads(cfg["W"], cfg["H"], seed=60 + v) for v in range(V)]
+    gc = torch.stack([torch.from_numpy(g[0]) for g in grads]).cuda()
+    gd = torch.stack([torch.from_numpy(g[1]) for g in grads]).cuda()
+    e = _engine(sc, cfg)
+    w = KeyframeWindow(e, packed)
+    w.calibrate()
+    ref = w.iteration((gc, gd)).clone()
+    grid_y = (cfg["H"] + 15) // 16
+    plan = plan_units(V, world, grid_y)
+    assert [len(u) for u in plan] == [2, 2, 2, 2] and all(u[1][2] > u[1][1] for u in plan)      # whole view + band of view 4
+    total = torch.zeros_like(ref)
+    for r in range(world):
+        er = _engine(sc, cfg)
+        wr = KeyframeWindow(er, packed, rank=r, world_size=world)
+        wr.calibrate()
+        total += wr.iteration((gc, gd), reduce=False)
+        torch.cuda.synchronize()
+    assert rel_err(total.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
+    assert rel_err(total[-8 * e.tau_slots:].cpu().numpy(), ref[-8 * e.tau_slots:].cpu().numpy()) <= 2e-5     # every view's dL/dtau

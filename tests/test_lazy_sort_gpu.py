@@ -31,7 +31,7 @@ def _tile_top(o, W, H):
 
 
 def _check_on_demand(sc, ref, threshold, grads=True, expect_partial=True):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     W, H = int(sc["image_width"]), int(sc["image_height"])
     dc, dd = S.make_pixel_grads(W, H, seed=11)
@@ -119,7 +119,7 @@ def test_engine_default_is_on_demand_and_matches():
     """The engine path (no host sync, CUDA graph) with the library default threshold on a scene of long lists."""
     import torch
     import diff_gaussian_rasterization as dgr
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     assert dgr._L.gsr_sort_on_demand(-1) > 0

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from autograd_ref import render_autograd
-from diff_gaussian_rasterization import scenes as S
+import scenes as S
 from oracle.gs_oracle import Oracle
 
 

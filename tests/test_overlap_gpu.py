@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _engine(P=60000, W=320, H=240, seed=0, overlap=True):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
     cfg = dict(S.CONFIGS["C1_tum_tracking"], W=W, H=H, P=P, fx=260.0, fy=260.0, cx=W / 2 - 0.5, cy=H / 2 - 0.5)

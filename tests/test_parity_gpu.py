@@ -16,7 +16,7 @@ TOL = 1e-4   # stated fp32 tolerance (north_star): rel <= 1e-4
 
 
 def _scene(name, **kw):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     cfgs = {
         "small": dict(W=160, H=128, fx=150.0, fy=150.0, cx=80.0, cy=64.0, P=3000, sh_degree=0),
@@ -33,7 +33,7 @@ def _scene(name, **kw):
 
 
 def _grads(sc, seed=1):
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     return S.make_pixel_grads(sc["image_width"], sc["image_height"], seed=seed)
 
@@ -203,7 +203,7 @@ def test_randomised_shapes_vs_reference_kernels(ref, seed):
     """Seeded sweep over image sizes (ragged and tile-aligned), Gaussian counts, footprint scales, backgrounds and SH
     degrees: list lengths around every internal boundary (32-entry cull groups, 128/256-entry batches, 16-entry role
     switches, 2048-entry sort chunks) occur somewhere in the sweep.  Same bars as the fixed cases."""
-    from diff_gaussian_rasterization import scenes as S
+    import scenes as S
 
     rng = np.random.default_rng(1000 + seed)
     W, H = int(rng.integers(17, 260)), int(rng.integers(17, 200))

@@ -62,7 +62,7 @@ def test_loss_and_gradients_match_autograd(mode):
 
 
 def test_tracking_step_matches_adam_and_update_pose():
-    from diff_gaussian_rasterization import scenes as SC
+    import scenes as SC
     from diff_gaussian_rasterization import slam_ops as S
 
     cam = SC.make_camera(640, 480, 517.3, 516.5, 318.6, 255.3, SC.base_pose())
@@ -107,7 +107,7 @@ def test_tracking_step_matches_adam_and_update_pose():
 
 
 def test_tracking_loop_graph_converges_towards_the_target_pose():
-    from diff_gaussian_rasterization import scenes as SC
+    import scenes as SC
     from diff_gaussian_rasterization import slam_ops as S
     from diff_gaussian_rasterization.engine import RasterEngine
 
@@ -153,7 +153,7 @@ def test_mapping_window_with_fused_loss_matches_per_view_autograd(fused):
     """MappingWindow (render -> fused mapping loss -> backward, accumulated over the window) == per-view rasterizer calls fed
     with the autograd gradients of the restated get_loss_mapping (utils/slam_utils.py:92-128), summed like autograd does."""
     from common import run_ours
-    from diff_gaussian_rasterization import scenes as SC
+    import scenes as SC
     from diff_gaussian_rasterization import slam_ops as S
     from diff_gaussian_rasterization.engine import RasterEngine
     from diff_gaussian_rasterization.window import KeyframeWindow
@@ -199,7 +199,7 @@ def test_mapping_window_with_fused_loss_matches_per_view_autograd(fused):
 def test_loss_fused_into_the_forward_epilogue_matches_the_loss_kernel(mode):
     """gsr_fused_loss: dL/dcolor, dL/ddepth and {loss, dL/da, dL/db} written by the forward compositing kernel's epilogue ==
     the stand-alone loss kernel run on the images that forward produced; with and without lists ordered on demand."""
-    from diff_gaussian_rasterization import scenes as SC
+    import scenes as SC
     from diff_gaussian_rasterization import slam_ops as S
     from diff_gaussian_rasterization.engine import RasterEngine
     import diff_gaussian_rasterization as dgr
@@ -240,7 +240,7 @@ def test_loss_fused_into_the_forward_epilogue_matches_the_loss_kernel(mode):
 
 
 def test_tracking_loop_with_fused_loss_follows_the_unfused_loop():
-    from diff_gaussian_rasterization import scenes as SC
+    import scenes as SC
     from diff_gaussian_rasterization import slam_ops as S
     from diff_gaussian_rasterization.engine import RasterEngine
 

@@ -28,43 +28,67 @@ def _view_grad(v, n):
     return torch.randn(n, generator=g, dtype=torch.float32)
 
 
+GRID_Y = 43      # tile rows of the 1200x680 mapping shape
+
+
 def _worker(rank, world, port, V, n, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
-    from diff_gaussian_rasterization.window import allreduce_window_gradients, shard_views
+    from diff_gaussian_rasterization.window import allreduce_window_gradients, plan_units
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    views = shard_views(V, world, rank)
-    flat = torch.zeros(n)
-    for i, v in enumerate(views):            # first view overwrites, the rest accumulate (engine protocol)
-        flat = _view_grad(v, n) if i == 0 else flat + _view_grad(v, n)
+    units = plan_units(V, world, GRID_Y)[rank]
+    # engine protocol: every unit adds into ONE flat buffer whose tail holds a row of dL/dtau per view; a unit that is a band
+    # of tile rows contributes the band's share of its view (here: in proportion to its rows)
+    flat = torch.zeros(n + 8 * V)
+    for (v, y0, y1) in units:
+        share = 1.0 if y1 == 0 else (y1 - y0) / GRID_Y
+        flat[:n] += share * _view_grad(v, n)
+        flat[n + 8 * v:n + 8 * v + 6] += share * _view_grad(100 + v, 6)
     allreduce_window_gradients(flat)
     np.save(os.path.join(out_dir, "r%d.npy" % rank), flat.numpy())
-    np.save(os.path.join(out_dir, "v%d.npy" % rank), np.asarray(views, np.int64))
+    np.save(os.path.join(out_dir, "u%d.npy" % rank), np.asarray(units, np.int64).reshape(-1, 3))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,V", [(2, 10), (3, 2)])
+@pytest.mark.parametrize("world,V", [(2, 10), (3, 2), (4, 10)])
 def test_window_allreduce_gloo(tmp_path, world, V):
     n = 4099
     mp.spawn(_worker, args=(world, _free_port(), V, n, str(tmp_path)), nprocs=world, join=True)
-    expect = sum(_view_grad(v, n) for v in range(V)).numpy()
-    seen = []
+    expect = torch.zeros(n + 8 * V)
+    expect[:n] = sum(_view_grad(v, n) for v in range(V))
+    for v in range(V):
+        expect[n + 8 * v:n + 8 * v + 6] = _view_grad(100 + v, 6)
+    rows = np.zeros((V, GRID_Y), np.int64)      # how often every tile row of every view is rendered
     for r in range(world):
         got = np.load(tmp_path / ("r%d.npy" % r))
-        np.testing.assert_allclose(got, expect, rtol=1e-5, atol=1e-5)
-        seen += list(np.load(tmp_path / ("v%d.npy" % r)))
-    assert sorted(seen) == list(range(V))          # every view rendered exactly once
+        np.testing.assert_allclose(got, expect.numpy(), rtol=1e-5, atol=1e-5)
+        for v, y0, y1 in np.load(tmp_path / ("u%d.npy" % r)):
+            rows[v, (y0 if y1 else 0):(y1 if y1 else GRID_Y)] += 1
+    assert (rows == 1).all()                    # every tile row of every view rendered exactly once
 
 
 def test_shard_map():
     sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
-    from diff_gaussian_rasterization.window import owner_of, shard_views
+    from diff_gaussian_rasterization.window import band_rows, owner_of, plan_units, shard_views
 
-    assert [len(shard_views(10, 8, r)) for r in range(8)] == [2, 2, 1, 1, 1, 1, 1, 1]
+    assert [len(shard_views(10, 8, r)) for r in range(8)] == [2, 2, 1, 1, 1, 1, 1, 1]     # whole views only
     assert [len(shard_views(32, 8, r)) for r in range(8)] == [4] * 8
     assert shard_views(3, 4, 3) == []
     for v in range(10):
         assert v in shard_views(10, 8, owner_of(v, 8))
+    # split plan: 10 keyframes on 8 ranks -> one whole view + a quarter of view 8 or 9 each
+    plan = plan_units(10, 8, 43)
+    assert all(len(u) == 2 and u[0] == (r, 0, 0) for r, u in enumerate(plan))
+    assert [u[1][0] for u in plan] == [8, 8, 8, 8, 9, 9, 9, 9]
+    assert [(u[1][1], u[1][2]) for u in plan[:4]] == band_rows(43, 4) and band_rows(43, 4)[0][0] == 0 and band_rows(43, 4)[-1][1] == 43
+    assert plan_units(32, 8, 68) == [[(v, 0, 0) for v in range(r, 32, 8)] for r in range(8)]      # C4: nothing to split
+    assert plan_units(10, 8, 43, split=False) == [[(v, 0, 0) for v in shard_views(10, 8, r)] for r in range(8)]
+    assert plan_units(10, 1, 43) == [[(v, 0, 0) for v in range(10)]]
+    # equal-work bands follow the weights
+    assert band_rows(8, 2, [1, 1, 1, 1, 1, 1, 1, 9]) == [(0, 7), (7, 8)]
+    for parts in (2, 3, 5):
+        b = band_rows(43, parts, list(range(43)))
+        assert b[0][0] == 0 and b[-1][1] == 43 and all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(y1 > y0 for y0, y1 in b)

@@ -7,13 +7,13 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200")):
+for p in (ROOT, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np
 import torch
 
 from diff_gaussian_rasterization import _cabi
-from diff_gaussian_rasterization import scenes as S
+import scenes as S
 from diff_gaussian_rasterization.engine import RasterEngine
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C1_tum_tracking"

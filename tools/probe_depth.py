@@ -11,7 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"), os.path.j
     sys.path.insert(0, p)
 import numpy as np
 
-from diff_gaussian_rasterization import scenes as S
+import scenes as S
 from common import run_ours
 
 for name in sys.argv[1:]:

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from common import run_ours
-from diff_gaussian_rasterization import scenes as S
+import scenes as S
 from diff_gaussian_rasterization import slam_ops as SO
 from diff_gaussian_rasterization.engine import RasterEngine
 
