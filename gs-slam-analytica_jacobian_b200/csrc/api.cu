@@ -28,8 +28,10 @@ std::atomic<bool> g_timing{false};
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
 const bool g_no_pdl = getenv("GSR_NO_PDL") != nullptr;                 // A/B switch: no programmatic dependent launches
 const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;
-// default of gsr_scene.exact_exp == 0 (GSR_EXACT_EXP=0 / 1 overrides the built-in default)
-const int g_exact_exp_default = getenv("GSR_EXACT_EXP") ? atoi(getenv("GSR_EXACT_EXP")) : GSR_EXACT_EXP_DEFAULT;         // A/B switch: forward not a programmatic dependent of the preprocess
+// what gsr_scene.exact_exp == 0 means: 2 = exact forward + backward (built-in), 1 = exact forward only, <= 0 = ex2.approx
+// (environment GSR_EXACT_EXP overrides the built-in default: A/B switch for measurements)
+const int g_exact_exp_default = getenv("GSR_EXACT_EXP") ? (atoi(getenv("GSR_EXACT_EXP")) > 0 ? atoi(getenv("GSR_EXACT_EXP")) : -1)
+                                                        : GSR_EXACT_EXP_DEFAULT;         // A/B switch: forward not a programmatic dependent of the preprocess
 // lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
 // is sorted completely
 std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
@@ -133,7 +135,9 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.densify_grad_accum = a->densify_grad_accum; s.densify_denom = a->densify_denom; s.max_radii2D = a->max_radii2D;
 	s.overlap_forward = a->overlap_forward;
 	s.upstream_ready = a->upstream_ready;
-	s.exact_exp = a->exact_exp > 0 ? 1 : (a->exact_exp < 0 ? 0 : (g_exact_exp_default ? 1 : 0));
+	const int exact = a->exact_exp != 0 ? a->exact_exp : g_exact_exp_default;
+	s.exact_exp = exact > 0 ? 1 : 0;
+	s.exact_exp_bwd = exact > 1 ? 1 : 0;
 	s.band_y0 = s.band_y1 = 0;
 	if (a->tile_row_end != 0 || a->tile_row_begin != 0) {
 		if (a->tile_row_begin < 0 || a->tile_row_end <= a->tile_row_begin || a->tile_row_end > s.grid_y)

@@ -10,7 +10,7 @@
 #define GSR_SORT_CHUNK 2048    // longest tile list the 256-thread sort handles as one shared-memory chunk (8 keys per thread);
                                // lists above it are queued for the long-list kernel, lists up to it can be sorted by the
                                // forward compositing kernel itself
-#define GSR_EXACT_EXP_DEFAULT 1     // forward compositing: alpha from the reference's expf by default (gsr_scene.exact_exp)
+#define GSR_EXACT_EXP_DEFAULT 2     // compositing kernels: alpha from the reference's expf in forward and backward (gsr_scene.exact_exp)
 #define GSR_LAZY_MIN_DEFAULT 256    // per-tile lists longer than this are ordered on demand by the forward compositing kernel
 
 namespace gsr {

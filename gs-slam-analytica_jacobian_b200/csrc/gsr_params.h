@@ -41,6 +41,7 @@ struct Scene {
 	bool has_loss;
 	FusedLoss loss;
 	int overlap_forward;          // backward: launch the compositing backward as programmatic dependent of the forward before it
+	int exact_exp_bwd;            // backward: the reference's expf and an exact division in the compositing backward as well
 	int exact_exp;                // forward: alpha from the reference's expf instead of ex2.approx (bit-identical T, n_contrib, n_touched)
 	int band_y0, band_y1;         // tile rows [band_y0, band_y1) this call renders (a band of the view); band_y1 == 0: the whole image
 	float* densify_grad_accum;    // [P] or null

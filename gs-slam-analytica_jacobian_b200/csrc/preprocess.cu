@@ -165,9 +165,20 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 				const float4 q = __ldg(reinterpret_cast<const float4*>(s.rotations) + idx);
 				const float r = q.x, x = q.y, y = q.z, z = q.w;
 				M3 R;
-				R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
-				R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-				R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+				// Which product of a sum  a*b +- c*d  is rounded and which is fused is the compiler's choice and depends on the
+				// surrounding code; the reference build (forward.cu:131-140 under nvcc 12.9 for sm_100a, read off its SASS with
+				// tools/sass_symbolic.py) rounds r*z, r*x, x*z, y*y, z*z and fuses the other factor pair.  Pinned with intrinsics so
+				// that cov3D -- and through it the conic, alpha and T -- is bit-identical in every instantiation of this kernel.
+				const float rz = __fmul_rn(r, z), rx = __fmul_rn(r, x), xz = __fmul_rn(x, z), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+				R.m[0][0] = 1.f - 2.f * __fadd_rn(yy, zz);
+				R.m[0][1] = 2.f * __fmaf_rn(x, y, -rz);
+				R.m[0][2] = 2.f * __fmaf_rn(r, y, xz);
+				R.m[1][0] = 2.f * __fmaf_rn(x, y, rz);
+				R.m[1][1] = 1.f - 2.f * __fmaf_rn(x, x, zz);
+				R.m[1][2] = 2.f * __fmaf_rn(y, z, -rx);
+				R.m[2][0] = 2.f * __fmaf_rn(-r, y, xz);
+				R.m[2][1] = 2.f * __fmaf_rn(y, z, rx);
+				R.m[2][2] = 1.f - 2.f * __fmaf_rn(x, x, yy);
 				const M3 Mm = m3_mul(S, R);
 				const M3 Sigma = m3_mul(m3_transpose(Mm), Mm);
 				cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];

@@ -53,6 +53,13 @@ struct PixelState {
 };
 
 // One thread per pixel: entries grp[0 .. cnt) (cnt even, a padding record with opacity 0 at the end if needed)
+// EXACT: G from the reference's expf (backward.cu:779), so that alpha -- and with it every skip decision -- is bit-identical to
+// the (exact) forward's and T = T / (1 - alpha) retraces the forward's transmittances to an ulp or two per step (the quotient
+// itself as T * rcp.approx(1 - alpha): a correctly rounded division, -DGSR_BWD_DIV=1, was measured -- gradients 4e-7 instead
+// of 7e-7 from the reference at 300 k Gaussians, compositing backward 126 -> 157 us at C1 -- and is not worth it).
+// Otherwise ex2.approx (6 instructions less per pair, alpha within ~5e-7 relative, which the chain of divisions amplifies:
+// gradients 1e-4 .. 2e-4 from the reference at 300 k Gaussians instead of 1e-6, tools/grad_noise.py).
+template <bool EXACT>
 __device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int cnt, float2* __restrict__ panel, PixelState& s)
 {
 	for (int k = 0; k < cnt; k += 2) {
@@ -64,14 +71,17 @@ __device__ __forceinline__ void eval_group(const QueueRec* __restrict__ grp, int
 			const float4 w2 = r->w2;
 			const float dx = w0.x - s.pxf, dy = w0.y - s.pyf;
 			const float power = falloff_power(w0.z, w0.w, w1.x, dx, dy);
-			const float G = gsr_exp(power);
+			const float G = EXACT ? expf(power) : gsr_exp(power);
 			const float alpha = fminf(0.99f, w1.y * G);
 			// backward.cu:763-783: only entries in front of the pixel's last contributor, same skips as the forward
 			const bool valid = (__float_as_int(w2.z) < s.last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
 			float ga = 0.f, w = 0.f;
 			if (valid) {
-				const float rcp = rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
-				s.T = s.T * rcp;
+#ifndef GSR_BWD_DIV
+#define GSR_BWD_DIV 0
+#endif
+				const float rcp = (EXACT && GSR_BWD_DIV) ? __frcp_rn(1.f - alpha) : rcp_approx(1.f - alpha);   // 1 - alpha >= 0.01
+				s.T = (EXACT && GSR_BWD_DIV) ? __fdiv_rn(s.T, 1.f - alpha) : s.T * rcp;
 				w = alpha * s.T;     // d(channel)/d(colour)
 				const float sdot = w1.z * s.dp0 + w1.w * s.dp1 + w2.x * s.dp2 + w2.y * s.dpd;
 				// beta = <accum_rec, dL/dpixel> of the entries behind this one.  The reference updates accum_rec when it
@@ -143,6 +153,7 @@ __device__ __forceinline__ void flush_panel(const float2* __restrict__ panel, co
 	}
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(256, 3)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const GaussRec* __restrict__ rec, int W, int H, int grid_x, const float* __restrict__ bg,
@@ -272,7 +283,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 			qn += __popc(mask);
 			__syncwarp();
 			while (qn >= kSlots) {
-				eval_group(wq + head, kSlots, panel + lane, s);
+				eval_group<EXACT>(wq + head, kSlots, panel + lane, s);
 				__syncwarp();
 				flush_panel(panel, sm.dpix[warp], kSlots, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
 				__syncwarp();   // panel and queue group consumed
@@ -288,7 +299,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 			wq[head + qn].w2 = make_float4(0.f, 0.f, 0.f, 0.f);
 		}
 		__syncwarp();
-		eval_group(wq + head, (qn + 1) & ~1, panel + lane, s);
+		eval_group<EXACT>(wq + head, (qn + 1) & ~1, panel + lane, s);
 		__syncwarp();
 		flush_panel(panel, sm.dpix[warp], qn, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
 	}
@@ -304,8 +315,9 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	const int tiles = band ? s.grid_x * (s.band_y1 - s.band_y0) : s.grid_x * s.grid_y;
 	if (tiles <= 0) return;
 	const size_t smem = sizeof(BwdSmem);
-	static SmemAttrCache attr;
-	ensure_dynamic_smem(render_backward_kernel, smem, attr);
+	static SmemAttrCache attr[2];
+	ensure_dynamic_smem(render_backward_kernel<false>, smem, attr[0]);
+	ensure_dynamic_smem(render_backward_kernel<true>, smem, attr[1]);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(tiles); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
 	cudaLaunchAttribute at[1];
@@ -313,7 +325,8 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
 	cfg.numAttrs = overlap_forward ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, render_backward_kernel, (const uint2*)g.ranges, (const uint32_t*)b.point_list, (const GaussRec*)g.rec, s.W, s.H,
+	auto kernel = s.exact_exp_bwd ? render_backward_kernel<true> : render_backward_kernel<false>;
+	cudaLaunchKernelEx(&cfg, kernel, (const uint2*)g.ranges, (const uint32_t*)b.point_list, (const GaussRec*)g.rec, s.W, s.H,
 	                   s.grid_x, s.background, (const float*)im.final_T, (const uint32_t*)im.n_contrib, dL_dpix, dL_dpix_depth, g.acc,
 	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done, (const uint32_t*)s.upstream_ready, g.hdr,
 	                   band ? s.band_y0 * s.grid_x : 0);

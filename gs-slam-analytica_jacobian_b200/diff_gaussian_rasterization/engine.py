@@ -44,6 +44,8 @@ class RasterEngine:
         grad_flat: share the flat gradient buffer of another engine over the SAME Gaussians (views of a window running on
         several streams then add into one buffer: launch_backward(accumulate="atomic"))."""
         self.dev = torch.device(device)
+        if self.dev.type == "cuda" and self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         f = lambda k: (gaussians[k].to(self.dev, torch.float32).contiguous() if gaussians.get(k) is not None else None)
         self.g = {k: f(k) for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp")}
         if self.g["colors_precomp"] is not None:

@@ -117,11 +117,16 @@ typedef struct gsr_scene {
 	                                host pointer, read during the call */
 	int sort_on_demand;          /* forward only: per-call form of gsr_sort_on_demand().  0 = the process default; > 0: lists
 	                                longer than this are ordered on demand; < 0: every list of this call is sorted completely */
-	int exact_exp;               /* forward only: 0 = the library default (exact; environment GSR_EXACT_EXP=0/1), > 0: alpha =
-	                                min(0.99, o * expf(power)) with the reference's own expf (forward.cu:496) -- T, hence every
-	                                threshold decision, n_contrib and n_touched are then bit-identical to the reference's;
-	                                < 0: one ex2.approx per pair (6 instructions less per pair; alpha within ~1e-6 relative,
-	                                n_contrib / n_touched then differ from the reference's on a ~1e-5 fraction of entries) */
+	int exact_exp;               /* forward + backward: how alpha = min(0.99, o * exp(power)) is evaluated by the compositing kernels.
+	                                0 = the library default (2; environment GSR_EXACT_EXP overrides);
+	                                2: the reference's own expf (forward.cu:496, backward.cu:779) in forward and backward -- T, every
+	                                   threshold decision, n_contrib, n_touched and final_T are bit-identical to the reference's and
+	                                   the gradients agree with it to ~1e-6 (its own run-to-run spread is ~1e-7);
+	                                1: exact in the forward only (bit-identical integer outputs; gradients to ~1e-4);
+	                                < 0: one ex2.approx per pair in both (6 instructions less per pair, 6 % of a tracking step at
+	                                   640x480 / 100 k Gaussians; n_contrib / n_touched differ from the reference's on a ~1e-5
+	                                   fraction of entries, gradients to 1e-4 .. 2e-4 in the max norm).
+	                                Pass the same value to the forward and the backward of a step. */
 	int tile_row_begin, tile_row_end; /* forward + backward: render only the band of tile rows [begin, end) of the view
 	                                (rows of 16 pixels; 0, 0 = the whole image).  Gaussians whose tile rectangle does not
 	                                reach the band are culled for this call (radii 0, zero gradient rows); pixels outside the

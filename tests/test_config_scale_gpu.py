@@ -70,10 +70,10 @@ def _consumed_mask(ranges, top):
     return np.cumsum(mark[:-1]) > 0
 
 
-def _close(a, b, what, tol=TOL):
+def _close(a, b, what, tol=TOL, tol_inf=None):
     a, b = np.asarray(a), np.asarray(b).reshape(np.asarray(a).shape)
     e_inf, e_2 = rel_err(a, b), l2_err(a, b)
-    assert e_inf <= tol and e_2 <= tol, "%s: max-norm %.3e, L2 %.3e" % (what, e_inf, e_2)
+    assert e_inf <= (tol if tol_inf is None else tol_inf) and e_2 <= tol, "%s: max-norm %.3e, L2 %.3e" % (what, e_inf, e_2)
     return e_inf, e_2
 
 
@@ -125,8 +125,8 @@ def test_config_scale_parity(ref, case):
     flips_c = float(np.mean(of["n_contrib"] != r["n_contrib"]))
     flips_t = float(np.mean(of["n_touched"][vis] != r["n_touched"][vis]))
     assert flips_c <= 1e-3 and flips_t <= 1e-3
-    for k in ("color", "depth", "opacity"):
-        _close(of[k], r[k], k + " (ex2.approx)")
+    for k in ("color", "depth", "opacity"):      # a flipped threshold decision moves ONE pixel by up to alpha = 1/255 ...
+        _close(of[k], r[k], k + " (ex2.approx)", tol_inf=5e-3)      # ... of the image's range; the L2 bar stays 1e-4
 
     # ---- RasterEngine.step(): no host sync, CUDA graph, overlapped backward ----
     t = S.to_torch(sc, "cuda")
