@@ -1,18 +1,32 @@
 #!/bin/bash
-# Standard GPU evidence pass (run under gpurun): parity tests, bench, ncu launch list, ncu full capture.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag>'
-TAG=${1:-r1}
+# Standard GPU evidence pass (run under gpurun): parity tests, bench (both arms), ncu launch lists, ncu full captures.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag>'      (SKIP_TESTS=1 / SKIP_BENCH=1 / SKIP_NCU=1 to drop parts)
+TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
-if [ -z "$ONLY_NCU" ]; then
+if [ -z "$SKIP_TESTS" ]; then
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_$TAG.log; tail -3 $O/pytest_$TAG.log
-python bench.py --impl reference --steps 30 --warmup 5 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err; echo "bench ref rc=$?"
-python bench.py --steps 200 --warmup 5 > $O/bench_ours_$TAG.json 2> $O/bench_ours_$TAG.err; echo "bench ours rc=$?"
-cat $O/bench_ours_$TAG.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['stages'], d.get('cpu_baseline'))"
 fi
-python tools/profile_step.py C1_tum_tracking 3 > $O/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 5 -c 8 --csv --log-file $O/launches_$TAG.csv python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_launch_$TAG.log 2>&1
-echo "launch list rc=$?"
-python tools/profile_step.py C1_tum_tracking 3 > $O/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 9 -c 4 -f -o $O/prof_$TAG python tools/profile_step.py C1_tum_tracking 3 > $O/ncu_full_$TAG.log 2>&1
-echo "full capture rc=$?"
+if [ -z "$SKIP_BENCH" ]; then
+python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_ref_$TAG.json 2> $O/bench_ref_$TAG.err; echo "bench ref rc=$?"
+python bench.py --steps ${STEPS:-100} --warmup 5 > $O/bench_ours_$TAG.json 2> $O/bench_ours_$TAG.err; echo "bench ours rc=$?"
+python - <<PY
+import json
+d = json.load(open('$O/bench_ours_$TAG.json')); r = json.load(open('$O/bench_ref_$TAG.json'))
+print('C2 window: ours %.3f ms (e2e %.3f ms)  ref %.3f ms' % (d['ms_per_step'], d['e2e']['ms_per_step'], r['ms_per_step']))
+print(' roofline', d['roofline']['kernel'], d['roofline']['frac'], {k: v['ms'] for k, v in d['roofline']['stages_one_view'].items()})
+c = d.get('also_C1')
+if c: print('C1 step: %.4f ms (e2e %.4f ms)' % (c['ms_per_step'], c['e2e']['ms_per_step']), c['roofline']['frac'], {k: v['ms'] for k, v in c['roofline']['stages'].items()})
+print(' cpu', d.get('cpu_baseline'))
+PY
+fi
+if [ -z "$SKIP_NCU" ]; then
+for WL in C1_tum_tracking C2_replica_mapping; do
+S=${WL:0:2}
+python tools/profile_step.py $WL 3 > $O/plain_${S}_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 5 -c 10 --csv --log-file $O/launches_${S}_$TAG.csv python tools/profile_step.py $WL 3 > $O/ncu_launch_${S}_$TAG.log 2>&1
+echo "$S launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 10 -c 5 -f -o $O/prof_${S}_$TAG python tools/profile_step.py $WL 3 > $O/ncu_full_${S}_$TAG.log 2>&1
+echo "$S full capture rc=$?"
+done
+fi
