@@ -302,6 +302,12 @@ int FN(gso_bin)(int P, int W, int H, const int* radii, const real* means2D, cons
 	return 0;
 }
 
+/* "Math mode" (tests only): compositing without the rasterizer's cut-offs -- alpha = min(1, o G), no power > 0 skip, no
+ * alpha < 1/255 skip, no T < 1e-4 stop -- i.e. the dense formulation of the reference's analytic-Jacobian scripts
+ * (Loss_Derivative_script_compare.py:1173-1351), so that their chain can be compared term by term. */
+static int g_math_mode = 0; /* one per working precision (this file is compiled twice) */
+void FN(gso_set_math_mode)(int on) { g_math_mode = on; }
+
 /* ------------------------------------------------------------------------------------------
  * Stage 3: forward compositing.  CR/forward.cu:406-535.  features = colors_precomp or rgb.
  * ------------------------------------------------------------------------------------------ */
@@ -325,11 +331,11 @@ void FN(gso_render)(int W, int H, const uint32_t* ranges, const uint32_t* point_
 					real dx = means2D[2 * id] - (real)px, dy = means2D[2 * id + 1] - (real)py;
 					const real* co = conic_opacity + 4 * id;
 					real power = (real)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-					if (power > 0) continue;
-					real alpha = rmin((real)0.99f, co[3] * (real)exp((double)power));
-					if (alpha < (real)(1.0f / 255.0f)) continue;
+					if (power > 0 && !g_math_mode) continue;
+					real alpha = rmin(g_math_mode ? (real)1 : (real)0.99f, co[3] * (real)exp((double)power));
+					if (alpha < (real)(1.0f / 255.0f) && !g_math_mode) continue;
 					real test_T = T * (1 - alpha);
-					if (test_T < (real)0.0001f) break; /* done = true */
+					if (test_T < (real)0.0001f && !g_math_mode) break; /* done = true */
 					for (int ch = 0; ch < 3; ch++) C[ch] += features[3 * id + ch] * alpha * T;
 					Dp += depths[id] * alpha * T;
 					if (test_T > (real)0.5f) {
@@ -383,10 +389,10 @@ void FN(gso_render_bwd)(int W, int H, const uint32_t* ranges, const uint32_t* po
 					real dx = means2D[2 * id] - (real)px, dy = means2D[2 * id + 1] - (real)py;
 					const real* co = conic_opacity + 4 * id;
 					real power = (real)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-					if (power > 0) continue;
+					if (power > 0 && !g_math_mode) continue;
 					real G = (real)exp((double)power);
-					real alpha = rmin((real)0.99f, co[3] * G);
-					if (alpha < (real)(1.0f / 255.0f)) continue;
+					real alpha = rmin(g_math_mode ? (real)1 : (real)0.99f, co[3] * G);
+					if (alpha < (real)(1.0f / 255.0f) && !g_math_mode) continue;
 					T = T / (1 - alpha);
 					real dchannel_dcolor = alpha * T;
 					real dL_dalpha = 0;
