@@ -464,27 +464,38 @@ def run_window(args, rank, world, device):
     import scenes as S
     from diff_gaussian_rasterization import slam_ops as SO
     from diff_gaussian_rasterization.engine import RasterEngine
-    from diff_gaussian_rasterization.window import KeyframeWindow
+    from diff_gaussian_rasterization.window import KeyframeWindow, SwitchReducer
 
     L = _cabi.load()
     K, Wm = args.steps, args.warmup
     name = args.workload
     V = args.views or S.CONFIGS[name]["V"]
     reduce = not name.startswith("C3")
+    plan_rank, plan_world = rank, world
+    if args.as_rank_of and world == 1:      # tuning aid: rank 0's share of an N-rank window on ONE GPU, no collective
+        plan_rank, plan_world, reduce = 0, int(args.as_rank_of), False
     cfg, sc, cams, dc, dd = window_inputs(name, V)
     W, H = cfg["W"], cfg["H"]
     t = S.to_torch(sc, device)
     mk = lambda **kw: RasterEngine(dict(means3D=t["means3D"], opacities=t["opacities"], shs=t["shs"], scales=t["scales"], rotations=t["rotations"]),
                                    W, H, sc["tanfovx"], sc["tanfovy"], sc["bg"], sh_degree=cfg["sh_degree"], device=device,
                                    tau_slots=max(64, V), **kw)
-    eng = mk()
+    # the window gradient lives in a symmetric allocation and is summed over the ranks by the library's own NVSwitch kernel
+    # (multimem.ld_reduce / multimem.st, csrc/window_reduce.cu); --nccl-reduce (or no multicast memory): dist.all_reduce
+    reducer = None
+    if reduce and world > 1 and not args.nccl_reduce:
+        reducer = SwitchReducer.create(RasterEngine.flat_size(cfg["P"], 1, tau_slots=max(64, V)), device)
+        if reducer is None:
+            log("switch reducer unavailable (%s): NCCL all-reduce" % SwitchReducer.last_error)
+    eng = mk(grad_flat=reducer.buffer) if reducer is not None else mk()
     cams_dev = torch.from_numpy(cams).to(device)
     cams_pin = torch.from_numpy(cams).pin_memory()
     gc_dev, gd_dev = torch.from_numpy(dc).to(device), torch.from_numpy(dd).to(device)      # ONE resident copy, read by every view
     # further engines over the same Gaussians: units overlap on separate streams, all add into ONE gradient buffer (REDs)
-    n_units_max = -(-V // world) + 1
+    n_units_max = -(-V // plan_world) + 1
     extra = [mk(grad_flat=eng.grad_flat) for _ in range(min(max(args.engines, 1), n_units_max) - 1)]
-    win = KeyframeWindow(eng, cams_dev, rank=rank, world_size=world, extra_engines=extra, split=not args.no_split)
+    win = KeyframeWindow(eng, cams_dev, rank=plan_rank, world_size=plan_world, extra_engines=extra, split=not args.no_split,
+                         reducer=reducer)
     win.calibrate()
     Rs = []
     for (v, y0, y1) in win.units:
@@ -524,18 +535,29 @@ def run_window(args, rank, world, device):
     gnorm_check = float(eng.grad_flat[:eng.grad_flat.numel() - 8 * eng.tau_slots].double().norm())
     tau_last = [float(x) for x in win.tau_all[V - 1].cpu().numpy()] if reduce or world == 1 else None
     # the collective alone (same buffer, device-timed): what part of the step it is
-    coll_ms = 0.0
+    coll_ms, nccl_ms = 0.0, 0.0
     if reduce and world > 1:
+        def time_collective(fn):
+            for _ in range(3):
+                fn()
+            ce = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(7)]
+            for a_, b_ in ce:
+                barrier()
+                a_.record(stream); fn(); b_.record(stream)
+            torch.cuda.synchronize(device)
+            tt = torch.tensor(float(np.median([a_.elapsed_time(b_) for a_, b_ in ce])), device=device)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            return float(tt)
         probe = torch.zeros_like(eng.grad_flat)
-        for _ in range(3):
-            torch.distributed.all_reduce(probe)
-        ce = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for a_, b_ in ce:
-            barrier()
-            a_.record(stream); torch.distributed.all_reduce(probe); b_.record(stream)
-        torch.cuda.synchronize(device)
-        coll_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in ce]))
+        nccl_ms = time_collective(lambda: torch.distributed.all_reduce(probe))
         del probe
+        coll_ms = nccl_ms
+        if reducer is not None:
+            keep = eng.grad_flat.clone()
+            coll_ms = time_collective(reducer.all_reduce)
+            eng.grad_flat.copy_(keep)
+            assert not reducer.timed_out(), "a rank did not arrive in the switch reduction"
+            del keep
 
     # ---------------- e2e: the host-driven mapping iteration (slam_ops.MappingWindow) ----------------
     # Per step from pinned HOST memory: the camera blocks of all keyframes (the poses are optimisation variables).  The loss
@@ -630,8 +652,10 @@ def run_window(args, rank, world, device):
         "config": workload_config(name, V),
         "details": {"views_per_s": V * K / (tmax * 1e-3), "num_rendered_per_view": R_view, "num_consumed_per_view": R_cons,
                     "units_per_rank": [["v%d" % u[0] if u[2] == 0 else "v%d[rows %d:%d]" % u for u in r] for r in win.plan],
-                    "collective": ("all_reduce(sum) of %d B (packed per-Gaussian gradients + every view's dL/dtau) per step, inside the timed region; "
-                                   "alone %.3f ms" % (grad_bytes, coll_ms)) if reduce else "none",
+                    "collective": ("all_reduce(sum) of %d B (packed per-Gaussian gradients + every view's dL/dtau) per step, inside the timed region, by %s; "
+                                   "alone %.3f ms (dist.all_reduce / NCCL on the same buffer: %.3f ms)"
+                                   % (grad_bytes, "the library's NVSwitch kernel (gsr_window_allreduce: multimem.ld_reduce + multimem.st over symmetric memory)"
+                                      if reducer is not None else "dist.all_reduce (NCCL)", coll_ms, nccl_ms)) if reduce else "none",
                     "parallelism": "keyframe-parallel x%d (left-over views split into bands of tile rows), %d engine(s) / stream(s) per GPU"
                                    % (world, len(win.engines)),
                     "path": "KeyframeWindow over RasterEngine(s), no host sync; per-tile lists ordered " + sort_path(eng)},
@@ -931,6 +955,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-split", action="store_true", help="window workloads: whole views only (round robin), no bands of tile rows")
     ap.add_argument("--no-also-c1", action="store_true", help="skip the nested C1 tracking record of the default run at N = 1")
+    ap.add_argument("--nccl-reduce", action="store_true", help="window workloads at N > 1: sum the gradients with dist.all_reduce instead of the library's NVSwitch kernel")
+    ap.add_argument("--as-rank-of", type=int, default=0, help="tuning aid (N = 1 only): time rank 0's share of a window sharded over this many ranks, without the collective")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "diff_gaussian_rasterization", "libgsr_b200.so")
-SOURCES = ["preprocess.cu", "binning.cu", "render.cu", "render_backward.cu", "preprocess_backward.cu", "slam_ops.cu", "api.cu"]
+SOURCES = ["preprocess.cu", "binning.cu", "render.cu", "render_backward.cu", "preprocess_backward.cu", "slam_ops.cu", "window_reduce.cu", "api.cu"]
 HEADERS = ["gsr_common.cuh", "gsr_params.h", "render_common.cuh", "tile_sort.cuh", os.path.join("..", "..", "include", "gsr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

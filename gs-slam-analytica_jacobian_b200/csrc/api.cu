@@ -434,6 +434,23 @@ int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* ex
 	return check_cuda("tracking_step");
 }
 
+int gsr_window_allreduce(float* multicast, const void* signal_pads, int rank, int world_size, size_t n_floats, int ctas,
+                         size_t signal_pad_bytes, int* status, void* stream)
+{
+	if (!multicast || !signal_pads || !status) return fail(GSR_ERR_ARG, "null argument");
+	if (world_size < 2 || world_size > 32 || rank < 0 || rank >= world_size) return fail(GSR_ERR_ARG, "bad rank / world size");
+	if ((reinterpret_cast<uintptr_t>(multicast) & 15) != 0 || (n_floats & 3) != 0)
+		return fail(GSR_ERR_ARG, "the multicast buffer must be 16-byte aligned and hold a multiple of 4 floats");
+	if (ctas <= 0) ctas = 64;
+	const size_t fit = signal_pad_bytes / (sizeof(uint32_t) * (size_t)world_size);      // one flag per (CTA, peer)
+	if (fit < 1) return fail(GSR_ERR_WORKSPACE, "signal pad too small");
+	if ((size_t)ctas > fit) ctas = (int)fit;
+	if (ctas > 148) ctas = 148;       // every CTA must be resident: the CTAs of all ranks meet pairwise
+	gsr::launch_window_allreduce(multicast, signal_pads, rank, world_size, n_floats / 4, ctas, status, (cudaStream_t)stream);
+	g_launches += 1;
+	return check_cuda("window_allreduce");
+}
+
 unsigned long long gsr_kernel_launch_count(void) { return g_launches.load(); }
 
 int gsr_sort_on_demand(int min_list_length)

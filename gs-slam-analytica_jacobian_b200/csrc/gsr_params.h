@@ -80,6 +80,8 @@ struct TrackingStepArgs {
 size_t slam_loss_scratch_bytes(int W, int H);
 void launch_slam_loss(const SlamLossArgs& a, void* scratch, cudaStream_t stream);
 void launch_tracking_step(const TrackingStepArgs& a, cudaStream_t stream);
+void launch_window_allreduce(float* multicast, const void* signal_pads, int rank, int world, size_t n_float4, int ctas, int* status,
+                             cudaStream_t stream);
 
 // launchers (defined in the .cu files, all asynchronous on `stream`)
 bool fused_scatter_fits(int P, int tiles);

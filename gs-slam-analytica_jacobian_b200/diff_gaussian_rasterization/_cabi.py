@@ -20,7 +20,7 @@ EXPORTS = (
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
     "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand", "gsr_fused_loss_scratch_bytes",
-    "gsr_step_status",
+    "gsr_step_status", "gsr_window_allreduce",
 )
 
 
@@ -106,6 +106,7 @@ def load():
     fl = C.c_float
     lib.gsr_slam_loss.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, vp, fl, fl, ip, ip, vp, vp, vp, vp, vp]
     lib.gsr_tracking_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, fl, fl, fl, fl, vp]
+    lib.gsr_window_allreduce.argtypes = [vp, vp, ip, ip, sz, ip, sz, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

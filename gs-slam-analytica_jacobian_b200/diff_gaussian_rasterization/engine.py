@@ -122,6 +122,14 @@ class RasterEngine:
         # step(): the compositing backward overlaps the tail of the compositing forward (GSR_NO_OVERLAP=1: plain order)
         self.overlap = not os.environ.get("GSR_NO_OVERLAP")
 
+    @staticmethod
+    def flat_size(P, M=1, colors_precomp=False, cov3D_precomp=False, tau_slots=64):
+        """Length (floats) of grad_flat for a model of P Gaussians with M SH coefficients: what a caller-provided buffer
+        (e.g. a symmetric allocation, window.SwitchReducer) must hold."""
+        ncol = 3 if colors_precomp else 3 * int(M)
+        ncov = 6 if cov3D_precomp else 7
+        return int(P) * (3 + ncol + 1 + ncov) + 32 + 8 * int(tau_slots)
+
     # ---- camera ---------------------------------------------------------------------------------------
     @staticmethod
     def pack_camera(viewmatrix, projmatrix, projmatrix_raw, campos, out=None):

@@ -15,9 +15,10 @@ shards by view:
     gradients into ONE flat buffer in the backward kernel itself (gsr_scene.accumulate_grads) -- read-modify-write
     on one stream, REDs when several engines on as many streams share the buffer -- and writes its dL/dtau into
     row `view` of the [V, 8] block at the tail of that buffer;
-  * ONE all-reduce(sum) of the flat buffer per iteration (NCCL over NVLink / NVSwitch when the process group is
-    NCCL; gloo works for CPU tests of the host logic) gives every rank the window gradient and every view's
-    dL/dtau;
+  * ONE all-reduce(sum) of the flat buffer per iteration gives every rank the window gradient and every view's dL/dtau:
+    the library's own kernel over NVSwitch multicast memory when the buffer lives in a symmetric allocation
+    (SwitchReducer: multimem.ld_reduce + multimem.st, csrc/window_reduce.cu), else dist.all_reduce (NCCL; gloo for the
+    CPU tests of the host logic);
   * per-unit results (radii, n_touched, dL/dmeans2D, images) stay on the owning rank -- like the reference keeps
     them per viewpoint (utils/slam_backend.py:195-198,236-240,277-284).
 Candidate-pose batches for tracking (C3) use the same sharding with reduce=False and no bands: no collective at all.
@@ -94,6 +95,72 @@ def allreduce_window_gradients(grad_flat, group=None):
     return grad_flat
 
 
+class SwitchReducer:
+    """The window's gradient buffer in a symmetric allocation + its sum over the ranks by ONE kernel over NVSwitch multicast
+    memory (gsr_window_allreduce: multimem.ld_reduce / multimem.st, no NCCL on the data path).
+
+        red = SwitchReducer.create(n_floats, device, group)      # collective; None when multicast memory is unavailable
+        eng = RasterEngine(..., grad_flat=red.buffer)            # the engine accumulates straight into the symmetric buffer
+        win = KeyframeWindow(eng, cams, rank, world, reducer=red)
+
+    torch.distributed._symmetric_memory is used for the plumbing only (allocation, handle exchange, multicast mapping,
+    signal pads); the reduction itself is the library's kernel."""
+    last_error = None
+
+    def __init__(self, buffer, padded, handle, ctas):
+        import ctypes as C
+
+        from . import _cabi
+
+        self._C, self._cabi, self._L = C, _cabi, _cabi.load()
+        self.buffer, self.padded, self.handle, self.ctas = buffer, padded, handle, int(ctas)
+        self.rank, self.world = int(handle.rank), int(handle.world_size)
+        self.dev = buffer.device
+        self.mc = int(handle.multicast_ptr) + (padded.data_ptr() - int(handle.buffer_ptrs[self.rank]))
+        self.pads = int(handle.signal_pad_ptrs_dev)
+        self.pad_bytes = int(handle.signal_pad_size)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    @staticmethod
+    def create(n_floats, device, group=None, ctas=64):
+        """Collective over `group`.  Returns None (on every rank) when symmetric / multicast memory cannot be set up."""
+        import torch.distributed as dist
+
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            group = dist.group.WORLD if group is None else group
+            n_pad = (int(n_floats) + 3) // 4 * 4
+            padded = symm.empty(n_pad, dtype=torch.float32, device=torch.device(device))
+            handle = symm.rendezvous(padded, group)
+            ok = bool(handle.multicast_ptr) and handle.world_size > 1
+        except Exception as ex:      # no symmetric-memory support in this torch build / on this box: the caller falls back to NCCL
+            ok, padded, handle = False, None, None
+            SwitchReducer.last_error = "%s: %s" % (type(ex).__name__, ex)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device(device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # all ranks or none
+        if int(flag.item()) == 0:
+            return None
+        padded.zero_()
+        return SwitchReducer(padded[:int(n_floats)], padded, handle, ctas)
+
+    def all_reduce(self):
+        """In-place sum of the buffer over the ranks on the current stream (a collective: every rank calls it)."""
+        C = self._C
+        with torch.cuda.device(self.dev):
+            st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            self._cabi.check(self._L.gsr_window_allreduce(C.c_void_p(self.mc), C.c_void_p(self.pads), self.rank, self.world,
+                                                          self.padded.numel(), self.ctas, self.pad_bytes,
+                                                          C.c_void_p(self.status.data_ptr()), st), "window_allreduce")
+        return self.buffer
+
+    def timed_out(self):
+        """True when a peer did not arrive in some all_reduce since the last call (synchronises)."""
+        bad = bool(self.status.item())
+        self.status.zero_()
+        return bad
+
+
 class KeyframeWindow:
     """Runs the units a rank owns through its RasterEngine(s) and reduces the window gradient.
 
@@ -113,8 +180,13 @@ class KeyframeWindow:
     rows over the ranks (plan_units).  `self.views` lists the views of this rank's units, `self.units` the units.
     """
 
-    def __init__(self, engine, cameras, rank=0, world_size=1, group=None, extra_engines=(), split=True, row_weights=None):
+    def __init__(self, engine, cameras, rank=0, world_size=1, group=None, extra_engines=(), split=True, row_weights=None,
+                 reducer=None):
+        """reducer: a SwitchReducer whose buffer IS engine.grad_flat -- the window gradient is then summed by the library's
+        NVSwitch kernel instead of dist.all_reduce."""
         self.engine, self.cameras = engine, cameras
+        assert reducer is None or reducer.buffer.data_ptr() == engine.grad_flat.data_ptr(), "the reducer's buffer must be the engine's grad_flat"
+        self.reducer = reducer
         self.engines = [engine] + list(extra_engines)
         for e in self.engines[1:]:
             assert e.grad_flat.data_ptr() == engine.grad_flat.data_ptr(), "extra engines must share the first engine's grad_flat"
@@ -205,5 +277,8 @@ class KeyframeWindow:
             for st in self.streams:
                 main.wait_stream(st)
         if reduce:
-            allreduce_window_gradients(eng.grad_flat, self.group)
+            if self.reducer is not None:
+                self.reducer.all_reduce()
+            else:
+                allreduce_window_gradients(eng.grad_flat, self.group)
         return eng.grad_flat

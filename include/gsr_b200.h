@@ -251,6 +251,22 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
  * gsr_scene.sort_on_demand is 0); returns the previous value.  Default 256 (environment: GSR_LAZY_MIN). */
 int gsr_sort_on_demand(int min_list_length);
 
+/* ---- keyframe-window gradient reduction over the GPUs of one NVSwitch domain ----
+ * Sums, in place, the packed per-Gaussian gradient buffer every rank accumulated for its share of the window (the sum
+ * autograd forms over the views of utils/slam_backend.py:160-232) with ONE kernel over peer memory: rank r reduces slice r
+ * in the switch (multimem.ld_reduce) and broadcasts it (multimem.st); barriers over the ranks in front and behind.
+ *   multicast        the MULTICAST address of the buffer (same offset on every rank; e.g. torch symmetric memory:
+ *                    handle.multicast_ptr + offset of the tensor); 16-byte aligned
+ *   signal_pads      DEVICE array of world_size pointers: pad[p] = signal pad of rank p as mapped on this GPU; zero-filled
+ *                    once, signal_pad_bytes each (one 32-bit flag per (CTA, peer); the kernel leaves them zero)
+ *   n_floats         buffer length, a multiple of 4 (pad the allocation)
+ *   ctas             CTAs per rank (<= 0: 64); clamped to what the signal pad holds and to one CTA per SM.  EVERY rank must
+ *                    pass the same value and call in the same order (it is a collective)
+ *   status           device int, set to 1 when a peer did not arrive within 2 s (the buffer is then incomplete)
+ * The caller's stream order makes the local accumulation complete before the kernel starts.  Graph-capturable. */
+int gsr_window_allreduce(float* multicast, const void* signal_pads, int rank, int world_size, size_t n_floats, int ctas,
+                         size_t signal_pad_bytes, int* status, void* stream);
+
 /* ---- measurement hooks (bench.py) ---- */
 /* number of CUDA kernels this library has launched since it was loaded (bench.py: gpu_launches) */
 unsigned long long gsr_kernel_launch_count(void);

@@ -89,7 +89,7 @@ def test_loss_kernel_against_the_reference_module(mode):
     mono, tracking, init = mode.endswith("mono"), mode.startswith("track"), mode == "map_init"
     ws = S.LossWorkspace(W, H)
     cu = lambda t: t.cuda().contiguous()
-    sums = S.slam_loss(ws, cu(color), cu(depth), cu(opacity), cu(gt), None if (mono or init) else cu(gtd),
+    sums = S.slam_loss(ws, cu(color), cu(depth), cu(opacity), cu(gt), None if mono else cu(gtd),      # initialization only drops the exposure (:92-99)
                        cu(gmask.to(torch.uint8)) if tracking else None, None if init else torch.tensor([a0, b0]).cuda(), thr, alpha,
                        tracking=tracking).cpu().numpy()
     ref = float(G[mode + "_loss"])
