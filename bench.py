@@ -500,7 +500,7 @@ def run_window(args, rank, world, device):
     Rs = []
     for (v, y0, y1) in win.units:
         eng.set_camera(cams_dev[v]); eng.set_band(y0, y1)
-        Rs.append(eng.calibrate())
+        Rs.append(eng.calibrate(build_order=False))
     up = (lambda v, e: (gc_dev, gd_dev)) if extra else (lambda v: (gc_dev, gd_dev))
     flush = l2_flusher(device)
     stream = torch.cuda.current_stream(device)
@@ -614,11 +614,12 @@ def run_window(args, rank, world, device):
     names = ["preprocess", "binning", "render_forward", "render_backward", "preprocess_backward"]
     stage = np.zeros(5)
     R_view, R_cons = 0.0, 0.0
-    whole = [u for u in win.units if u[2] == 0]
+    whole = [i for i, u in enumerate(win.units) if u[2] == 0 and win.engine_of(i) is eng]
     if whole:
-        eng.set_camera(cams_dev[whole[0][0]]); eng.set_band(0, 0)
+        eng.set_camera(cams_dev[win.units[whole[0]][0]]); eng.set_band(0, 0)
+        eng.use_order(whole[0])      # the spatial order built for this unit on this engine
         eng.dL_dcolor.copy_(gc_dev); eng.dL_ddepth.copy_(gd_dev)
-        R_view = float(eng.calibrate())
+        R_view = float(eng.calibrate(build_order=False))
         eng.launch_forward()
         R_cons = float(consumed_instances(eng))
         L.gsr_stage_timing(1)

@@ -138,6 +138,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	const int exact = a->exact_exp != 0 ? a->exact_exp : g_exact_exp_default;
 	s.exact_exp = exact > 0 ? 1 : 0;
 	s.exact_exp_bwd = exact > 1 ? 1 : 0;
+	s.spatial_order = a->spatial_order;
 	s.band_y0 = s.band_y1 = 0;
 	if (a->tile_row_end != 0 || a->tile_row_begin != 0) {
 		if (a->tile_row_begin < 0 || a->tile_row_end <= a->tile_row_begin || a->tile_row_end > s.grid_y)
@@ -432,6 +433,20 @@ int gsr_tracking_step(const float* dL_dtau, const float* dL_dexposure, float* ex
 	gsr::launch_tracking_step(a, (cudaStream_t)stream);
 	g_launches += 1;
 	return check_cuda("tracking_step");
+}
+
+int gsr_spatial_order(const gsr_scene* a, void* geom, size_t geom_bytes, unsigned int* order_out, void* stream)
+{
+	gsr::Scene s;
+	int rc = make_scene(a, s);
+	if (rc) return rc;
+	const size_t tiles = (size_t)s.grid_x * s.grid_y;
+	if (!geom || geom_bytes < gsr::geom_bytes(s.P, tiles)) return fail(GSR_ERR_WORKSPACE, "geometry workspace too small");
+	if (s.P > 0 && !order_out) return fail(GSR_ERR_ARG, "order_out is required");
+	if (s.P == 0) return GSR_OK;
+	gsr::launch_spatial_order(s, gsr::geom_view(geom, s.P, tiles), order_out, (cudaStream_t)stream);
+	g_launches += 3;
+	return check_cuda("spatial_order");
 }
 
 int gsr_window_allreduce(float* multicast, const void* signal_pads, int rank, int world_size, size_t n_floats, int ctas,

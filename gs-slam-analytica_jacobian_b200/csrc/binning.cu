@@ -58,14 +58,24 @@ __device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint
 	for_each_tile((n > kSoloTiles && sub == 0) ? n : 0u, lo, hi, grid_x, key, id, f);
 }
 
+// ORDERED (gsr_scene.spatial_order): the CTA takes 256 consecutive entries of a screen-coherent permutation instead of 256
+// consecutive Gaussians.  Their rectangles then cover a small BOX of tiles with dozens of instances per tile, so the CTA
+// histograms in box-local shared memory (no sweep over every tile of the image), claims ONE slice per box tile (C2: ~100
+// global atomics per CTA instead of ~2000) and its pairs land in runs of dozens instead of isolated 8-byte stores.  A box
+// above kBoxMax tiles (an oversized Gaussian among the 256) sends the CTA down the per-instance path.
+constexpr int kBoxMax = 2048;
+
+template <bool ORDERED>
 __global__ void __launch_bounds__(kScatterThreads, 4)
 scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
                uint32_t* __restrict__ cursor, uint2* __restrict__ pairs, unsigned capacity, GeomHeader* hdr,
-               int n_tiles, int use_smem)
+               int n_tiles, int use_smem, const uint32_t* __restrict__ order)
 {
 	GSR_PROBE(1, 0);
 	const int sub = threadIdx.x & (kScatterLanes - 1);
-	const int idx = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
+	const int slot = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
+	int idx = slot;
+	if (ORDERED) idx = slot < P ? (int)__ldg(&order[slot]) : P;
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
 		// one round trip: the rectangle (all zero for a culled Gaussian) gives the tile count itself
@@ -75,21 +85,65 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 		hi = __float_as_uint(q2.w);
 		n = ((hi & 0xffff) - (lo & 0xffff)) * ((hi >> 16) - (lo >> 16));
 	}
-	extern __shared__ uint32_t s_tile[];          // [2][tiles]: CTA-local counts, then claimed bases (use_smem != 0)
+	extern __shared__ uint32_t s_tile[];          // [2][tiles or kBoxMax]: CTA-local counts, then claimed bases (use_smem != 0)
+	int span = n_tiles, gx = grid_x;              // the tile index space of the two passes: the image, or the CTA's box
+	uint32_t bx0 = 0, by0 = 0;
+	if (ORDERED) {
+		__shared__ uint32_t s_box[4][kScatterThreads / 32];
+		__shared__ uint32_t s_boxf[4];
+		const unsigned kAll = 0xffffffffu;
+		const uint32_t m0 = __reduce_min_sync(kAll, n ? (lo & 0xffff) : 0xffffu), m1 = __reduce_min_sync(kAll, n ? (lo >> 16) : 0xffffu);
+		const uint32_t m2 = __reduce_max_sync(kAll, n ? (hi & 0xffff) : 0u), m3 = __reduce_max_sync(kAll, n ? (hi >> 16) : 0u);
+		if ((threadIdx.x & 31) == 0) {
+			const int w = threadIdx.x >> 5;
+			s_box[0][w] = m0; s_box[1][w] = m1; s_box[2][w] = m2; s_box[3][w] = m3;
+		}
+		__syncthreads();
+		if (threadIdx.x < 4) {
+			uint32_t v = s_box[threadIdx.x][0];
+			for (int w = 1; w < kScatterThreads / 32; w++) v = threadIdx.x < 2 ? min(v, s_box[threadIdx.x][w]) : max(v, s_box[threadIdx.x][w]);
+			s_boxf[threadIdx.x] = v;
+		}
+		__syncthreads();
+		bx0 = s_boxf[0]; by0 = s_boxf[1];
+		const uint32_t bx1 = s_boxf[2], by1 = s_boxf[3];
+		if (bx1 <= bx0 || by1 <= by0) return;      // nothing visible among the CTA's Gaussians
+		const uint32_t bw = bx1 - bx0, bh = by1 - by0;
+		if (bw * bh <= (uint32_t)kBoxMax) {
+			// rectangles relative to the box: the walks below then yield box-local tile indices
+			if (n) {
+				lo = ((lo & 0xffff) - bx0) | (((lo >> 16) - by0) << 16);
+				hi = ((hi & 0xffff) - bx0) | (((hi >> 16) - by0) << 16);
+			}
+			span = (int)(bw * bh);
+			gx = (int)bw;
+			use_smem = 1;
+		} else {
+			use_smem = 0;
+			bx0 = by0 = 0;
+		}
+	}
 	uint32_t* s_cnt = s_tile;
-	uint32_t* s_base = s_tile + n_tiles;
+	uint32_t* s_base = s_tile + (ORDERED ? kBoxMax : n_tiles);
 	if (use_smem) {
 		// pass 1: CTA-local tile histogram; then ONE global atomic per (CTA, touched tile) claims a contiguous
 		// slice of the tile's segment (coalesced over consecutive tiles) instead of one atomic per instance
-		for (int t = threadIdx.x; t < n_tiles; t += kScatterThreads) s_cnt[t] = 0;
+		for (int t = threadIdx.x; t < span; t += kScatterThreads) s_cnt[t] = 0;
 		__syncthreads();
 		GSR_PROBE(1, 1);
-		for_each_tile_quad(n, lo, hi, grid_x, 0u, 0u, sub, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
+		for_each_tile_quad(n, lo, hi, gx, 0u, 0u, sub, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
 		__syncthreads();
 		GSR_PROBE(1, 2);
-		for (int t = threadIdx.x; t < n_tiles; t += kScatterThreads) {
+		for (int t = threadIdx.x; t < span; t += kScatterThreads) {
 			const uint32_t c = s_cnt[t];
-			if (c) s_base[t] = atomicAdd(&cursor[t], c);
+			if (c) {
+				uint32_t gt = (uint32_t)t;
+				if (ORDERED) {
+					const uint32_t ty = (uint32_t)t / (uint32_t)gx;
+					gt = (by0 + ty) * (uint32_t)grid_x + bx0 + ((uint32_t)t - ty * (uint32_t)gx);
+				}
+				s_base[t] = atomicAdd(&cursor[gt], c);
+			}
 			s_cnt[t] = 0;
 		}
 		__syncthreads();
@@ -97,13 +151,57 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 	GSR_PROBE(1, 3);
 	bool overflow = false;
 	// pass 2: claim a slot per (Gaussian, tile) inside the CTA's slice and store the pair
-	for_each_tile_quad(n, lo, hi, grid_x, key, (uint32_t)idx, sub, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
+	for_each_tile_quad(n, lo, hi, gx, key, (uint32_t)idx, sub, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
 		const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
 		if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
 		else overflow = true;
 	});
 	if (overflow) hdr->overflow = 1;
 	GSR_PROBE(1, 4);
+}
+
+// ---- screen-coherent permutation of the Gaussians (gsr_spatial_order): counting sort by home tile ----
+__device__ __forceinline__ uint32_t home_bucket(const GaussRec* __restrict__ rec, int idx, int grid_x)
+{
+	const float4 q2 = __ldg(&rec[idx].q2);
+	const uint32_t lo = __float_as_uint(q2.z), hi = __float_as_uint(q2.w);
+	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
+	if (x1 <= x0 || y1 <= y0) return 0u;      // culled: first bucket
+	return ((y0 + y1 - 1) >> 1) * (uint32_t)grid_x + ((x0 + x1 - 1) >> 1);      // the tile at the centre of the rectangle
+}
+__global__ void __launch_bounds__(256) home_count_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, uint32_t* __restrict__ count)
+{
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	if (idx < P) atomicAdd(&count[home_bucket(rec, idx, grid_x)], 1u);
+}
+__global__ void __launch_bounds__(256) bucket_scan_kernel(uint32_t* __restrict__ count, int tiles)      // one CTA: exclusive scan in place
+{
+	__shared__ unsigned s_red[8];
+	const int per = (tiles + 255) / 256;
+	const int t0 = min(tiles, (int)threadIdx.x * per), t1 = min(tiles, t0 + per);
+	unsigned sum = 0;
+	for (int t = t0; t < t1; t++) sum += count[t];
+	unsigned inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+		if ((threadIdx.x & 31) >= o) inc += v;
+	}
+	if ((threadIdx.x & 31) == 31) s_red[threadIdx.x >> 5] = inc;
+	__syncthreads();
+	unsigned run = inc - sum;
+	for (int w = 0; w < (int)(threadIdx.x >> 5); w++) run += s_red[w];
+	for (int t = t0; t < t1; t++) {
+		const unsigned c = count[t];
+		count[t] = run;
+		run += c;
+	}
+}
+__global__ void __launch_bounds__(256) home_order_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, uint32_t* __restrict__ cursor,
+                                                         uint32_t* __restrict__ order)
+{
+	const int idx = blockIdx.x * 256 + threadIdx.x;
+	if (idx < P) order[atomicAdd(&cursor[home_bucket(rec, idx, grid_x)], 1u)] = (uint32_t)idx;
 }
 
 // one CTA per tile; lists queued for the long-list kernel (use_long) are skipped here
@@ -151,10 +249,16 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	const int use_smem = tiles <= 16384 ? 1 : 0;     // 2 x tiles x 4 B of shared memory (1920x1080: 64 KB)
 	const size_t scatter_smem = use_smem ? 2 * (size_t)tiles * sizeof(uint32_t) : 0;
 	static SmemAttrCache scatter_attr;
-	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel, scatter_smem, scatter_attr);
-	if (!scatter_done)
-		scatter_kernel<<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
-		s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem);
+	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel<false>, scatter_smem, scatter_attr);
+	static const bool no_order = getenv("GSR_NO_SPATIAL_ORDER") != nullptr;      // A/B switch for measurements
+	if (!scatter_done) {
+		if (s.spatial_order && !no_order)
+			scatter_kernel<true><<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, 2 * kBoxMax * sizeof(uint32_t), stream>>>(
+			s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, 1, s.spatial_order);
+		else
+			scatter_kernel<false><<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
+			s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem, nullptr);
+	}
 	if (fuse_sort) return scatter_done ? 0 : 1;      // the forward compositing kernel sorts its own tile
 	int id_bits = 1;
 	while (id_bits < 32 && (1ll << id_bits) < (long long)s.P) id_bits++;
@@ -170,6 +274,15 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	tile_sort_long_kernel<<<min(tiles, 2 * 148), kLongThreads, lsmem, stream>>>(g.ranges, b.pairs, b.pairs_alt, b.point_list,
 	                                                                         (unsigned)R_capacity, id_bits, g.hdr, g.long_tiles);
 	return 3;
+}
+
+void launch_spatial_order(const Scene& s, const GeomView& g, uint32_t* order_out, cudaStream_t stream)
+{
+	const int tiles = s.grid_x * s.grid_y, grid = (s.P + 255) / 256;
+	cudaMemsetAsync(g.tile_cursor, 0, (size_t)tiles * sizeof(uint32_t), stream);
+	home_count_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, g.tile_cursor);
+	bucket_scan_kernel<<<1, 256, 0, stream>>>(g.tile_cursor, tiles);
+	home_order_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, g.tile_cursor, order_out);
 }
 
 GSR_PROBE_READER(probe_read_scatter)

@@ -44,6 +44,7 @@ struct Scene {
 	int exact_exp_bwd;            // backward: the reference's expf and an exact division in the compositing backward as well
 	int exact_exp;                // forward: alpha from the reference's expf instead of ex2.approx (bit-identical T, n_contrib, n_touched)
 	int band_y0, band_y1;         // tile rows [band_y0, band_y1) this call renders (a band of the view); band_y1 == 0: the whole image
+	const uint32_t* spatial_order; // optional permutation of [0, P): screen-coherent processing order of the scatter kernel
 	float* densify_grad_accum;    // [P] or null
 	float* densify_denom;         // [P] or null
 	float* max_radii2D;           // [P] or null
@@ -94,6 +95,8 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
                    bool fuse_sort, cudaStream_t stream, bool scatter_done = false);
 size_t tile_sort_smem_bytes(int cap_smem);
+// permutation of [0, P) by home tile from the records of the last forward plan (clobbers g.tile_count / g.tile_cursor)
+void launch_spatial_order(const Scene& s, const GeomView& g, uint32_t* order_out, cudaStream_t stream);
 // fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true);
 // lazy_min > 0: lists longer than lazy_min are ordered on demand, slab by slab, as far as the compositing gets (render.cu)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,

@@ -20,7 +20,7 @@ EXPORTS = (
     "gsr_mark_visible", "gsr_debug_pointers", "gsr_error_string", "gsr_version", "gsr_kernel_launch_count",
     "gsr_stage_timing", "gsr_stage_times_ms", "gsr_debug_probe", "gsr_slam_loss_scratch_bytes", "gsr_slam_loss",
     "gsr_tracking_step", "gsr_forward_nosync", "gsr_forward_nosync_fuses_scatter", "gsr_sort_on_demand", "gsr_fused_loss_scratch_bytes",
-    "gsr_step_status", "gsr_window_allreduce",
+    "gsr_step_status", "gsr_window_allreduce", "gsr_spatial_order",
 )
 
 
@@ -42,7 +42,7 @@ class GsrScene(C.Structure):
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
         ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
         ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p), ("fused_loss", C.POINTER(GsrFusedLoss)),
-        ("sort_on_demand", C.c_int), ("exact_exp", C.c_int), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int),
+        ("sort_on_demand", C.c_int), ("exact_exp", C.c_int), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int), ("spatial_order", C.c_void_p),
     ]
 
 
@@ -106,6 +106,7 @@ def load():
     fl = C.c_float
     lib.gsr_slam_loss.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, vp, fl, fl, ip, ip, vp, vp, vp, vp, vp]
     lib.gsr_tracking_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, fl, fl, fl, fl, vp]
+    lib.gsr_spatial_order.argtypes = [sp, vp, sz, vp, vp]
     lib.gsr_window_allreduce.argtypes = [vp, vp, ip, ip, sz, ip, sz, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)

@@ -115,10 +115,16 @@ class RasterEngine:
         s.scale_modifier, s.tan_fovx, s.tan_fovy = float(scale_modifier), float(tanfovx), float(tanfovy)
         s.prefiltered, s.debug, s.accumulate_grads, s.overlap_forward = 0, 0, 0, 0
         s.upstream_ready = None
+        s.spatial_order = None
         s.densify_grad_accum = s.densify_denom = s.max_radii2D = None
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.last_num_rendered = None
+        # screen-coherent processing orders of the scatter kernel (gsr_scene.spatial_order), one per key (a window unit);
+        # built by calibrate() for maps too large for the cooperative preprocess + scatter kernel
+        self.spatial_orders = {}
+        self.order_key = 0
+        self.use_spatial_order = (not os.environ.get("GSR_NO_SPATIAL_ORDER")) and not _L.gsr_forward_nosync_fuses_scatter(P, W, H)
         # step(): the compositing backward overlaps the tail of the compositing forward (GSR_NO_OVERLAP=1: plain order)
         self.overlap = not os.environ.get("GSR_NO_OVERLAP")
 
@@ -153,6 +159,17 @@ class RasterEngine:
             self.scene.tile_row_begin, self.scene.tile_row_end = int(tile_row_begin), int(tile_row_end)
             self.graph_fwd = self.graph_bwd = self.graph_all = None
 
+    def use_order(self, key):
+        """Select the spatial order built for `key` (e.g. the index of a window unit: every view / band has its own); a key
+        without an order yet runs the plain scatter until calibrate() builds one.  The captured graphs belong to the
+        previous order."""
+        self.order_key = key
+        t = self.spatial_orders.get(key)
+        ptr = None if t is None else t.data_ptr()
+        if ptr != self.scene.spatial_order:
+            self.scene.spatial_order = ptr
+            self.graph_fwd = self.graph_bwd = self.graph_all = None
+
     # ---- capacity -------------------------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -166,8 +183,9 @@ class RasterEngine:
             self.graph_fwd = self.graph_bwd = self.graph_all = None   # pointers changed
         return self.capacity
 
-    def calibrate(self):
-        """One exact (synchronising) forward plan at the current camera to size the binning workspace."""
+    def calibrate(self, build_order=True):
+        """One exact (synchronising) forward plan at the current camera to size the binning workspace (and, for maps beyond
+        the cooperative preprocess + scatter kernel, to build the scatter's spatial order for the current order key)."""
         with torch.cuda.device(self.dev):
             _cabi.check(_L.gsr_forward_plan(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(self.radii),
                                             _p(self.n_touched), self._stream()), "forward_plan")
@@ -179,6 +197,15 @@ class RasterEngine:
             self.max_tile_hint = hint
             self.graph_fwd = self.graph_bwd = self.graph_all = None
         self.ensure_capacity(R.value)
+        if self.use_spatial_order and build_order:
+            # Gaussians bucketed by the tile at the centre of their rectangle AT THIS CAMERA; later poses reuse it (any
+            # permutation gives the same lists, a stale one only loses locality)
+            t = self.spatial_orders.get(self.order_key)
+            if t is None:
+                t = self.spatial_orders[self.order_key] = torch.empty((self.P,), dtype=torch.int32, device=self.dev)
+            with torch.cuda.device(self.dev):
+                _cabi.check(_L.gsr_spatial_order(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(t), self._stream()), "spatial_order")
+            self.use_order(self.order_key)
         return int(R.value)
 
     # ---- un-synchronised launches ---------------------------------------------------------------------

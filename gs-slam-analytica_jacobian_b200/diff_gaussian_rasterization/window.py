@@ -216,10 +216,11 @@ class KeyframeWindow:
     def calibrate(self):
         """Size the binning workspaces for the largest local unit (one exact plan per unit and engine)."""
         for e in self.engines:
-            for (v, y0, y1) in self.units:
+            for i, (v, y0, y1) in enumerate(self.units):
                 e.set_camera(self.cameras[v])
                 e.set_band(y0, y1)
-                e.calibrate()
+                e.use_order(i)
+                e.calibrate(build_order=e is self.engine_of(i))      # the scatter's spatial order: on the engine that runs the unit
 
     def iteration(self, upstream, reduce=True, on_view=None, upstream_precomputed=False, fused_loss=None):
         """One window iteration.  Returns engine.grad_flat (summed over all units of all ranks when reduce=True; its tail
@@ -239,6 +240,7 @@ class KeyframeWindow:
             for i, (v, y0, y1) in enumerate(self.units):
                 eng.set_camera(self.cameras[v])
                 eng.set_band(y0, y1)
+                eng.use_order(i)
                 if fused_loss is not None:
                     eng.launch_forward(fused_loss=fused_loss(i, v))
                     eng.launch_backward(accumulate=(i > 0), overlap_forward=True, tau_out=eng.tau_block[v])
@@ -262,6 +264,7 @@ class KeyframeWindow:
                 with torch.cuda.stream(self.streams[k]):
                     e.set_camera(self.cameras[v])
                     e.set_band(y0, y1)
+                    e.use_order(i)
                     if fused_loss is not None:
                         e.launch_forward(fused_loss=fused_loss(i, v))
                         e.launch_backward(accumulate="atomic", overlap_forward=True, tau_out=eng.tau_block[v])

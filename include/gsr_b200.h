@@ -133,6 +133,15 @@ typedef struct gsr_scene {
 	                                band are not written; n_touched, every per-Gaussian gradient and dL_dtau are the band's
 	                                share -- the bands of a view sum to the whole view (a view of a mapping window split over
 	                                several GPUs, window.py).  Pass the same values to the backward of the same workspaces. */
+	const unsigned int* spatial_order; /* forward only, optional (null = off): a device PERMUTATION of [0, P) that lists the
+	                                Gaussians so that neighbours in the list are neighbours on the screen (gsr_spatial_order).
+	                                The scatter of the two-kernel path (maps too large for the cooperative preprocess) then
+	                                walks the Gaussians in this order: the 256 Gaussians of a CTA touch a small box of tiles
+	                                with dozens of instances each instead of every tile with about one, so that a CTA counts
+	                                in a box-sized shared-memory histogram, claims one slice per box tile and its pairs land
+	                                in runs.  ANY permutation gives the same lists (the order inside a segment is fixed later,
+	                                by depth and id); a stale one -- built for an earlier pose -- only costs speed.  The caller
+	                                guarantees that it IS a permutation. */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */
@@ -250,6 +259,12 @@ int gsr_debug_pointers(int P, int W, int H, void* geom, void* binning, long long
  * bit-exact list tests compare); < 0: query only.  Sets the process-wide DEFAULT (used by calls whose
  * gsr_scene.sort_on_demand is 0); returns the previous value.  Default 256 (environment: GSR_LAZY_MIN). */
 int gsr_sort_on_demand(int min_list_length);
+
+/* Builds gsr_scene.spatial_order for the view last planned / rendered into `geom` (gsr_forward_plan, gsr_forward_nosync or
+ * gsr_rasterize_gaussians with the same scene): Gaussians bucketed by the tile at the centre of their tile rectangle, culled
+ * ones first.  order_out: device unsigned int[P].  Overwrites the tile counters of `geom` (scratch of the forward's binning:
+ * the next forward rebuilds them, the backward does not read them). */
+int gsr_spatial_order(const gsr_scene* scene, void* geom, size_t geom_bytes, unsigned int* order_out, void* stream);
 
 /* ---- keyframe-window gradient reduction over the GPUs of one NVSwitch domain ----
  * Sums, in place, the packed per-Gaussian gradient buffer every rank accumulated for its share of the window (the sum

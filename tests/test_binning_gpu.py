@@ -93,3 +93,62 @@ def test_sparse_tiles(ref):
     n = r["ranges"][:, 1].astype(np.int64) - r["ranges"][:, 0]
     assert (n == 0).sum() > 0 and (n == 1).sum() > 0
     _check(o, r)
+
+
+def _order_for(sc, device="cuda"):
+    """gsr_spatial_order for scene `sc` through the C-ABI (plan first), as a numpy permutation."""
+    import ctypes as C
+
+    import torch
+
+    import diff_gaussian_rasterization as dgr
+    import scenes as S
+    from common import settings_from_scene
+
+    t = S.to_torch(sc, device)
+    e = torch.empty(0)
+    call = dgr._Call(settings_from_scene(t), t["means3D"], t["shs"], e, t["opacities"], t["scales"], t["rotations"], e)
+    P = call.P
+    gb = dgr._L.gsr_geometry_bytes(P, call.W, call.H)
+    geom = torch.empty(gb, dtype=torch.uint8, device=device)
+    radii = torch.empty(P, dtype=torch.int32, device=device)
+    nt = torch.empty(P, dtype=torch.int32, device=device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    dgr._cabi.check(dgr._L.gsr_forward_plan(C.byref(call.scene), p(geom), gb, p(radii), p(nt), st), "plan")
+    order = torch.empty(P, dtype=torch.int32, device=device)
+    dgr._cabi.check(dgr._L.gsr_spatial_order(C.byref(call.scene), p(geom), gb, p(order), st), "order")
+    torch.cuda.synchronize()
+    return order, radii.cpu().numpy()
+
+
+@pytest.mark.parametrize("W,H,big", [(640, 480, False), (1208, 680, True)])
+def test_scatter_in_spatial_order(ref, W, H, big):
+    """gsr_scene.spatial_order (the scatter walks the Gaussians bucketed by home tile, box-local histogram): ranges and
+    complete lists bit-exact against the reference kernels -- with the order of THIS view, with the order of another pose (stale:
+    only locality suffers) and with an arbitrary permutation; a few Gaussians scaled up 25x make some CTAs' boxes exceed the
+    shared-memory box (per-instance path inside the same launch)."""
+    import torch
+
+    sc = _identity_scene(W, H, 20000, seed=11, f=0.8 * W)
+    rng = np.random.default_rng(12)
+    s = sc["scales"].copy()
+    if big:
+        s[rng.random(20000) < 0.02] *= 25.0
+    s[rng.random(20000) < 0.3] *= 0.15
+    sc["scales"] = s.astype(np.float32)
+    r = ref.forward(sc)
+    order, radii = _order_for(sc)
+    o_np = order.cpu().numpy()
+    assert np.array_equal(np.sort(o_np), np.arange(20000))                    # a permutation
+    vis = radii[o_np] > 0
+    # culled ones share the first bucket with the few visible Gaussians whose home is tile 0
+    assert np.flatnonzero(~vis).max() < int((~vis).sum()) + 200
+    other = _identity_scene(W, H, 20000, seed=11, f=0.8 * W)
+    other["scales"] = sc["scales"]
+    other["means3D"] = (sc["means3D"] + np.array([0.3, -0.2, 0.1], np.float32)).astype(np.float32)
+    stale, _ = _order_for(other)
+    perm = torch.from_numpy(rng.permutation(20000).astype(np.int32)).cuda()
+    for name, od in (("own", order), ("stale", stale), ("random", perm)):
+        o = run_ours(sc, spatial_order=od)
+        _check(o, r)
