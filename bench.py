@@ -492,10 +492,10 @@ def run_window(args, rank, world, device):
     cams_pin = torch.from_numpy(cams).pin_memory()
     gc_dev, gd_dev = torch.from_numpy(dc).to(device), torch.from_numpy(dd).to(device)      # ONE resident copy, read by every view
     # further engines over the same Gaussians: units overlap on separate streams, all add into ONE gradient buffer (REDs)
-    n_units_max = -(-V // plan_world) + 1
+    n_units_max = (-(-V // plan_world)) * max(1, args.whole_bands) + 1
     extra = [mk(grad_flat=eng.grad_flat) for _ in range(min(max(args.engines, 1), n_units_max) - 1)]
     win = KeyframeWindow(eng, cams_dev, rank=plan_rank, world_size=plan_world, extra_engines=extra, split=not args.no_split,
-                         reducer=reducer)
+                         reducer=reducer, whole_bands=args.whole_bands)
     win.calibrate()
     Rs = []
     for (v, y0, y1) in win.units:
@@ -514,9 +514,16 @@ def run_window(args, rank, world, device):
     win.iteration(up, reduce=reduce, upstream_precomputed=True)
     torch.cuda.synchronize(device)
     launches_per_step = int(L.gsr_kernel_launch_count() - l0)
+    # the whole iteration -- every unit on every engine stream + the reduction -- as ONE CUDA graph (--no-graph: eager launches)
+    if args.no_graph:
+        step_value = lambda: win.iteration(up, reduce=reduce, upstream_precomputed=True)
+    else:
+        barrier()
+        graph_value = win.capture(up, reduce=reduce, upstream_precomputed=True)
+        step_value = graph_value.replay
     for _ in range(Wm):
         flush()
-        win.iteration(up, reduce=reduce, upstream_precomputed=True)
+        step_value()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(torch.cuda.current_device())
     barrier()
@@ -524,7 +531,7 @@ def run_window(args, rank, world, device):
     for i in range(K):
         flush()
         ev[i][0].record(stream)
-        win.iteration(up, reduce=reduce, upstream_precomputed=True)
+        step_value()
         ev[i][1].record(stream)
     barrier()
     clocks = sampler.stop()
@@ -577,9 +584,18 @@ def run_window(args, rank, world, device):
         norm_pin = torch.empty(1, dtype=torch.float32).pin_memory()
         body = eng.grad_flat[:eng.grad_flat.numel() - 8 * eng.tau_slots]
 
+        mw.iteration(reduce=True)
+        if args.no_graph:
+            step_e2e = lambda: mw.iteration(reduce=True)
+        else:
+            barrier()
+            graph_e2e = mw.capture(reduce=True)
+            step_e2e = graph_e2e.replay
+        sums = mw.view_sums
+
         def e2e_step():
             cams_dev.copy_(cams_pin, non_blocking=True)
-            flat, sums, _ = mw.iteration(reduce=True)
+            step_e2e()
             sums_pin.copy_(sums, non_blocking=True)
             tau_pin.copy_(win.tau_all, non_blocking=True)
             norm_pin.copy_(body.norm().reshape(1), non_blocking=True)
@@ -591,7 +607,7 @@ def run_window(args, rank, world, device):
 
         def e2e_step():
             cams_dev.copy_(cams_pin, non_blocking=True)
-            win.iteration(up, reduce=False, upstream_precomputed=True)
+            step_value()
             tau_pin.copy_(win.tau_all, non_blocking=True)
             stream.synchronize()
 
@@ -659,14 +675,15 @@ def run_window(args, rank, world, device):
                                       if reducer is not None else "dist.all_reduce (NCCL)", coll_ms, nccl_ms)) if reduce else "none",
                     "parallelism": "keyframe-parallel x%d (left-over views split into bands of tile rows), %d engine(s) / stream(s) per GPU"
                                    % (world, len(win.engines)),
-                    "path": "KeyframeWindow over RasterEngine(s), no host sync; per-tile lists ordered " + sort_path(eng)},
+                    "path": "KeyframeWindow over RasterEngine(s), %s, no host sync; per-tile lists ordered %s"
+                            % ("eager launches" if args.no_graph else "one CUDA graph per window iteration (all units, all engine streams, the reduction)", sort_path(eng))},
         "e2e": {"value": K / emax, "unit": WINDOW_UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": emax / K * 1e3,
                 "what": ("slam_ops.MappingWindow.iteration: pinned camera blocks H2D, mapping loss of every view fused into its forward "
                          "(ground truth resident), backward, all-reduce, per-view loss + dL/dtau + gradient norm D2H; host sync every step")
                         if reduce else "KeyframeWindow.iteration(reduce=False): pinned candidate poses H2D, dL/dtau of every pose D2H"},
         "gpu_launches": launches_per_step * K,
-        "launches_per_step": {"kernels": launches_per_step},
+        "launches_per_step": {"kernels": launches_per_step, "graph_launches": 0 if args.no_graph else 1},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
@@ -956,6 +973,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-split", action="store_true", help="window workloads: whole views only (round robin), no bands of tile rows")
     ap.add_argument("--no-also-c1", action="store_true", help="skip the nested C1 tracking record of the default run at N = 1")
+    ap.add_argument("--no-graph", action="store_true", help="window workloads: eager launches instead of one CUDA graph per window iteration")
+    ap.add_argument("--whole-bands", type=int, default=1, help="window workloads: cut every whole view of a rank into this many bands of tile rows (window.plan_units)")
     ap.add_argument("--nccl-reduce", action="store_true", help="window workloads at N > 1: sum the gradients with dist.all_reduce instead of the library's NVSwitch kernel")
     ap.add_argument("--as-rank-of", type=int, default=0, help="tuning aid (N = 1 only): time rank 0's share of a window sharded over this many ranks, without the collective")
     args = ap.parse_args()

@@ -215,8 +215,22 @@ class MappingWindow:
                 self.fused.append(FusedLoss(slot, gt_colors[v], None if gt_depths is None else gt_depths[v], None, expo, tracking=False,
                                             **self.kw))
 
+    def capture(self, reduce=True):
+        """The iteration as ONE CUDA graph (KeyframeWindow.capture); results land where iteration() leaves them
+        (window.engine.grad_flat, self.view_sums, window.tau_all).  Run iteration() once before."""
+        dev = self.eng.dev
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch(reduce, None)
+        return g
+
     def iteration(self, reduce=True, on_view=None):
         """Returns (grad_flat summed over all views of all ranks, per-local-view sums [n,4], per-local-view dL/dtau [n,6])."""
+        flat = self._launch(reduce, on_view)
+        return flat, self.view_sums, self.win.tau
+
+    def _launch(self, reduce, on_view):
         eng, local = self.eng, {v: i for i, v in enumerate(self.win.views)}
 
         def upstream(v, e=None):
@@ -231,6 +245,5 @@ class MappingWindow:
         if self.fused is None:
             assert all(y1 == 0 for (_, _, y1) in self.win.units) and len(self.win.engines) == 1, \
                 "the stand-alone loss kernel needs whole views on one engine; use fused=True"
-        flat = self.win.iteration(upstream, reduce=reduce, on_view=on_view,
+        return self.win.iteration(upstream, reduce=reduce, on_view=on_view,
                                   fused_loss=None if self.fused is None else (lambda i, v: self.fused[i].struct))
-        return flat, self.view_sums, self.win.tau

@@ -222,6 +222,18 @@ def test_window_with_two_engines_on_two_streams_matches_one_engine():
         torch.cuda.synchronize()
         assert rel_err(flat2.cpu().numpy(), flat1.cpu().numpy()) <= 1e-5
         assert rel_err(w2.tau.cpu().numpy(), tau1.cpu().numpy()) <= 1e-5
+    # the same iteration as ONE CUDA graph (both engine streams forked and joined inside the capture); new poses at replay
+    graph = w2.capture((gc, gd))
+    for shift in (0, 1):
+        packed_new = torch.roll(packed, shift, 0)
+        w1.cameras.copy_(packed_new); w2.cameras.copy_(packed_new)
+        ref = w1.iteration((gc, gd)).clone()
+        ref_tau = w1.tau.clone()
+        w2.engine.grad_flat.fill_(7.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(w2.engine.grad_flat.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+        assert rel_err(w2.tau.cpu().numpy(), ref_tau.cpu().numpy()) <= 1e-5
 
 
 def test_bands_of_a_view_sum_to_the_view():
