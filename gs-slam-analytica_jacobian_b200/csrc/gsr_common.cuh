@@ -46,7 +46,7 @@ struct GeomHeader {
 	unsigned int bwd_blocks_done;
 	unsigned int max_tile_count; // longest per-tile list
 	unsigned int num_long_tiles; // tiles queued for the long-list sort kernel (> GSR_SORT_CHUNK entries)
-	unsigned int spin_timeout;   // a compositing-backward CTA gave up waiting: 1 = tile flag of the forward, 2 = upstream_ready word
+	unsigned int spin_timeout;   // a bounded wait gave up: 1 = tile flag of the forward, 2 = upstream_ready word (compositing backward), 3 = a bulk copy of input rows (preprocess)
 	unsigned int pad[64 - 8];
 };
 static_assert(sizeof(GeomHeader) == 256, "header must be 256 B");
@@ -168,6 +168,38 @@ __device__ __forceinline__ float warp_sum(float v)
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
+}
+
+// ---- bulk asynchronous copies (TMA unit, cp.async.bulk) with transaction-counting mbarriers ----
+// One elected thread programs the copy of a CONTIGUOUS block (16-byte aligned on both sides, a multiple of 16 bytes); the TMA
+// unit moves it while the CTA does something else and signals the mbarrier with the byte count.  Used where a CTA's input
+// really is one contiguous block (the rows of 256 consecutive Gaussians in the per-Gaussian kernels); the compositing kernels
+// gather 48-byte records through an index list, which the TMA unit does no better than LDGSTS.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // visible to the async proxy before the first copy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+	             : "memory");
+}
+// true once the phase with the given parity has completed; bounded polling is the caller's business
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity)
+{
+	unsigned ok;
+	asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+	             : "=r"(ok)
+	             : "r"(smem_addr(bar)), "r"(parity)
+	             : "memory");
+	return ok != 0;
 }
 
 // Row index i / w inside a tile rectangle without a per-instance integer division and without special cases in the walk

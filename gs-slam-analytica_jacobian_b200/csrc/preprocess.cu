@@ -119,11 +119,34 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 		s_view[threadIdx.x] = s.viewmatrix[threadIdx.x];
 		s_proj[threadIdx.x] = s.projmatrix[threadIdx.x];
 	}
-	load_rows3(s.means3D, row0, s.P, s_mean, vec_mask & 1);
-	if (s.scales) load_rows3(s.scales, row0, s.P, s_scale, vec_mask & 2);
 	const bool dc_only = (s.colors_precomp != nullptr) || (s.M == 1);
-	if (dc_only) load_rows3(s.colors_precomp ? s.colors_precomp : s.shs, row0, s.P, s_col, vec_mask & 4);
+	// The rows of this CTA's 256 Gaussians are ONE contiguous block per input array: a full CTA with 16-byte aligned arrays
+	// has them fetched by the TMA unit (one elected thread, cp.async.bulk, completion on an mbarrier); the ragged last CTA and
+	// unaligned arrays take the vector / scalar loads (vec_mask bit 3: bulk copies allowed)
+	__shared__ __align__(8) uint64_t s_bar;
+	const bool bulk = (vec_mask & 8) && row0 + 256 <= s.P && (vec_mask & 1) && (!s.scales || (vec_mask & 2)) && (!dc_only || (vec_mask & 4));
+	if (bulk) {
+		if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+	} else {
+		load_rows3(s.means3D, row0, s.P, s_mean, vec_mask & 1);
+		if (s.scales) load_rows3(s.scales, row0, s.P, s_scale, vec_mask & 2);
+		if (dc_only) load_rows3(s.colors_precomp ? s.colors_precomp : s.shs, row0, s.P, s_col, vec_mask & 4);
+	}
 	__syncthreads();
+	if (bulk) {
+		if (threadIdx.x == 0) {
+			constexpr unsigned kBytes = 256 * 3 * sizeof(float);
+			mbar_arrive_expect_tx(&s_bar, kBytes * (1u + (s.scales ? 1u : 0u) + (dc_only ? 1u : 0u)));
+			bulk_copy_g2s(s_mean, s.means3D + (size_t)row0 * 3, kBytes, &s_bar);
+			if (s.scales) bulk_copy_g2s(s_scale, s.scales + (size_t)row0 * 3, kBytes, &s_bar);
+			if (dc_only) bulk_copy_g2s(s_col, (s.colors_precomp ? s.colors_precomp : s.shs) + (size_t)row0 * 3, kBytes, &s_bar);
+		}
+		// every thread polls the barrier's phase 0 (bounded: a copy that never lands must not hang the GPU)
+		unsigned spins = 0;
+		while (!mbar_try_wait(&s_bar, 0u)) {
+			if (++spins > (1u << 22)) { g.hdr->spin_timeout = 3; break; }
+		}
+	}
 	GSR_PROBE(0, 1);
 
 	unsigned my_tiles = 0, my_vis = 0, rect_lo = 0, rect_hi = 0, depth_bits = 0;
@@ -464,8 +487,9 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 		cudaMemsetAsync(g.ranges, 0, (size_t)tiles * sizeof(uint2), stream);
 		return false;
 	}
+	static const bool no_tma = getenv("GSR_NO_TMA") != nullptr;      // A/B switch for measurements
 	int vec_mask = (aligned16(s.means3D) ? 1 : 0) | (aligned16(s.scales) ? 2 : 0) |
-	               (aligned16(s.colors_precomp ? s.colors_precomp : s.shs) ? 4 : 0);
+	               (aligned16(s.colors_precomp ? s.colors_precomp : s.shs) ? 4 : 0) | (no_tma ? 0 : 8);
 	// CTA-private tile histogram in shared memory while it fits next to the static arrays (<= 8192 tiles, e.g. 1920x1080)
 	const int hist_smem = tiles <= 8192 ? 1 : 0;
 	const int grid = (s.P + 255) / 256;

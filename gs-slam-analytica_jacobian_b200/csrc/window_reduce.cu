@@ -15,8 +15,6 @@
 // No NCCL, no host involvement, graph-capturable; the flags reset themselves (compare-and-swap 0 -> 1 by the sender,
 // 1 -> 0 by the receiver), one flag per (CTA, peer).  Waits are bounded (%globaltimer): a peer that never arrives sets
 // status[0] = 1 instead of hanging the GPU.
-#include <cstdlib>
-
 #include "gsr_params.h"
 
 namespace gsr {
@@ -105,12 +103,11 @@ window_allreduce_kernel(float4* mc, uint32_t* const* pads, int rank, int world, 
 void launch_window_allreduce(float* multicast, const void* signal_pads, int rank, int world, size_t n_float4, int ctas, int* status,
                              cudaStream_t stream)
 {
-	static const int unroll = getenv("GSR_REDUCE_UNROLL") ? atoi(getenv("GSR_REDUCE_UNROLL")) : 4;      // experiments
-	float4* mc = reinterpret_cast<float4*>(multicast);
-	uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads);
-	if (unroll >= 8) window_allreduce_kernel<8><<<ctas, kReduceThreads, 0, stream>>>(mc, pads, rank, world, n_float4, status);
-	else if (unroll <= 2) window_allreduce_kernel<2><<<ctas, kReduceThreads, 0, stream>>>(mc, pads, rank, world, n_float4, status);
-	else window_allreduce_kernel<4><<<ctas, kReduceThreads, 0, stream>>>(mc, pads, rank, world, n_float4, status);
+	// (2, 4 and 8 loads in flight per thread and 16 .. 148 CTAs per rank were measured on 8 GPUs: 0.101 .. 0.113 ms for 28 MB,
+	// 0.431 .. 0.473 ms for 168 MB -- the switch, not the issue rate, sets the pace; profiles/r2_switch_reduce_n8.jsonl)
+	window_allreduce_kernel<4><<<ctas, kReduceThreads, 0, stream>>>(reinterpret_cast<float4*>(multicast),
+	                                                                reinterpret_cast<uint32_t* const*>(signal_pads), rank, world,
+	                                                                n_float4, status);
 }
 
 }  // namespace gsr
