@@ -23,10 +23,10 @@ fi
 if [ -z "$SKIP_NCU" ]; then
 for WL in C1_tum_tracking C2_replica_mapping; do
 S=${WL:0:2}
-python tools/profile_step.py $WL 3 > $O/plain_${S}_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 5 -c 10 --csv --log-file $O/launches_${S}_$TAG.csv python tools/profile_step.py $WL 3 > $O/ncu_launch_${S}_$TAG.log 2>&1
+python tools/profile_step.py $WL 4 > $O/plain_${S}_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(preprocess|render|scatter|tile_sort|mark|home|bucket)' -s 5 -c 10 --csv --log-file $O/launches_${S}_$TAG.csv python tools/profile_step.py $WL 4 > $O/ncu_launch_${S}_$TAG.log 2>&1
 echo "$S launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark)' -s 10 -c 5 -f -o $O/prof_${S}_$TAG python tools/profile_step.py $WL 3 > $O/ncu_full_${S}_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|render|scatter|tile_sort|mark|home|bucket)' -s 12 -c 6 -f -o $O/prof_${S}_$TAG python tools/profile_step.py $WL 4 > $O/ncu_full_${S}_$TAG.log 2>&1
 echo "$S full capture rc=$?"
 done
 fi
