@@ -396,10 +396,11 @@ def run_ours(args, rank, world, device):
     tau_last = [float(x) for x in eng.g_tau.cpu().numpy()]
     stages = {n: {"ms": round(float(ms), 4), "alg_bytes": int(rb[n]), "GB/s": round(rb[n] / (ms * 1e-3) / 1e9, 1) if (ms > 0 and rb[n] > 0) else None}
               for n, ms in zip(names, stage)}
-    traffic = None
+    traffic, issue_pct = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(names[dom])
+        tj = json.load(open(tp))
+        traffic, issue_pct = tj.get(names[dom]), tj.get("issue_pct_" + names[dom])
 
     # ---------------- reductions over ranks ----------------
     tmax, emax = dev_ms, e2e_s
@@ -424,7 +425,7 @@ def run_ours(args, rank, world, device):
         "gpu_launches": launches_per_step * K,
         "launches_per_step": {"kernels": launches_per_step, "graph_launches": 1},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src, "issue_slot_pct_ncu": issue_pct,
                      "alg_bytes_per_launch": int(rb[names[dom]]), "kernel_ms": round(float(stage[dom]), 4),
                      "byte_model": "gather terms on consumed instances (R_consumed = %.0f of R = %.0f)" % (R_cons, R_mean),
                      "frac_whole_list_model": round(rb_full[names[dom]] / (stage[dom] * 1e-3) / 1e9 / peak, 4),
@@ -519,8 +520,14 @@ def run_window(args, rank, world, device):
         step_value = lambda: win.iteration(up, reduce=reduce, upstream_precomputed=True)
     else:
         barrier()
-        graph_value = win.capture(up, reduce=reduce, upstream_precomputed=True)
-        step_value = graph_value.replay
+        try:
+            graph_value = win.capture(up, reduce=reduce, upstream_precomputed=True)
+            step_value = graph_value.replay
+        except Exception as ex:      # e.g. a collective that cannot be captured: eager launches, same work
+            log("window graph capture failed (%s): eager launches" % ex)
+            args.no_graph = True
+            torch.cuda.synchronize(device)
+            step_value = lambda: win.iteration(up, reduce=reduce, upstream_precomputed=True)
     for _ in range(Wm):
         flush()
         step_value()
@@ -698,7 +705,12 @@ def run_window(args, rank, world, device):
     }
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        line["roofline"]["traffic"] = json.load(open(tp)).get(name[:2] + "_" + names[dom])
+        tj = json.load(open(tp))
+        line["roofline"]["traffic"] = tj.get(name[:2] + "_" + names[dom])
+        # the compositing kernels are bound by instruction issue, not by bytes: issue-slot utilisation of the
+        # dominant kernel in the committed ncu capture of this shape
+        line["roofline"]["issue_slot_pct_ncu"] = tj.get(name[:2] + "_issue_pct_" + names[dom])
+        line["roofline"]["traffic_source"] = tj.get(name[:2] + "__source")
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_iters_per_s(S.with_camera(sc, S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], S.arc_poses(V, radius=0.5, seed=2)[0])),
                                                   dc, dd, views_per_iter=V)

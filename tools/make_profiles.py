@@ -64,6 +64,10 @@ for S in ("C1", "C2"):
         else:
             binb += a + b
     traffic[pre + "binning"] = int(binb)
+    icol = col("smsp__issue_active.avg.pct_of_peak_sustained_active")
+    for j, n in enumerate(names):      # issue-slot utilisation of the same launches (what actually bounds the compositing kernels)
+        if n in key:
+            traffic[pre + "issue_pct_" + key[n]] = float(rows[2 + j][icol].replace(",", ""))
     traffic[pre + "_source" if pre else "_source"] = "profiles/%s_ncu_full_%s.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % (prefix, S)
     with open(os.path.join(P, "%s_ncu_full_%s.md" % (prefix, S)), "w") as out:
         out.write("# ncu --set full, %s, one un-graphed forward+backward step, B200\n\n" % SHAPES[S])
