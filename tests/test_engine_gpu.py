@@ -1,5 +1,7 @@
 """GPU tests of RasterEngine (persistent workspaces, no host sync, CUDA graphs) and KeyframeWindow
 (per-view accumulation into one flat gradient buffer) against the plain per-call path."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -315,3 +317,55 @@ def test_window_plan_splits_leftover_views_and_matches_unsplit_window():
         torch.cuda.synchronize()
     assert rel_err(total.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
     assert rel_err(total[-8 * e.tau_slots:].cpu().numpy(), ref[-8 * e.tau_slots:].cpu().numpy()) <= 2e-5     # every view's dL/dtau
+
+
+def test_bands_and_spatial_orders_on_the_two_kernel_path_in_a_fresh_process():
+    """The window of three ranks emulated on one GPU with the cooperative preprocess + scatter kernel switched off
+    (GSR_NO_FUSED_SCATTER=1, read when the library loads): every unit -- whole views and bands of tile rows -- then runs the
+    two-kernel path with ITS spatial order (RasterEngine.use_order / gsr_spatial_order).  The ranks' gradient buffers must sum
+    to the unsplit, unordered window."""
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path[:0] = [%r, %r, %r]\n"
+        "import scenes as S\n"
+        "from common import rel_err\n"
+        "from diff_gaussian_rasterization.engine import RasterEngine\n"
+        "from diff_gaussian_rasterization.window import KeyframeWindow\n"
+        "cfg = dict(W=320, H=240, fx=290.0, fy=290.0, cx=159.5, cy=119.5, P=20000, sh_degree=0)\n"
+        "sc = S.make_scene(cfg, seed=5); sc['scales'] = sc['scales'] * 1.5\n"
+        "t = S.to_torch(sc, 'cuda')\n"
+        "mk = lambda **kw: RasterEngine(dict(means3D=t['means3D'], opacities=t['opacities'], shs=t['shs'], scales=t['scales'], rotations=t['rotations']),\n"
+        "                               cfg['W'], cfg['H'], sc['tanfovx'], sc['tanfovy'], sc['bg'], sh_degree=0, **kw)\n"
+        "V = 4\n"
+        "cams = [S.make_camera(cfg['W'], cfg['H'], cfg['fx'], cfg['fy'], cfg['cx'], cfg['cy'], w2c) for w2c in S.arc_poses(V, radius=0.3)]\n"
+        "pack = lambda c: RasterEngine.pack_camera(*(torch.from_numpy(c[k]) for k in ('viewmatrix', 'projmatrix', 'projmatrix_raw', 'campos'))).cuda()\n"
+        "packed = torch.stack([pack(c) for c in cams])\n"
+        "grads = [S.make_pixel_grads(cfg['W'], cfg['H'], seed=30 + v) for v in range(V)]\n"
+        "gc = torch.stack([torch.from_numpy(g[0]) for g in grads]).cuda(); gd = torch.stack([torch.from_numpy(g[1]) for g in grads]).cuda()\n"
+        "e0 = mk(); e0.use_spatial_order = False\n"
+        "w0 = KeyframeWindow(e0, packed); w0.calibrate()\n"
+        "ref = w0.iteration((gc, gd)).clone(); ref_tau = w0.tau_all.clone()\n"
+        "total = torch.zeros_like(ref); orders = 0\n"
+        "for r in range(3):\n"
+        "    ea = mk(); eb = mk(grad_flat=ea.grad_flat)\n"
+        "    assert ea.use_spatial_order      # two-kernel path: the engine builds orders\n"
+        "    w = KeyframeWindow(ea, packed, rank=r, world_size=3, extra_engines=[eb]); w.calibrate()\n"
+        "    orders += len(ea.spatial_orders) + len(eb.spatial_orders)\n"
+        "    assert any(u[2] > 0 for u in w.units)      # a band among the rank's units\n"
+        "    total += w.iteration((gc, gd), reduce=False)\n"
+        "    for e in (ea, eb):\n"
+        "        assert not e.header()[1]\n"
+        "assert orders >= 4\n"
+        "n = ref.numel() - 8 * e0.tau_slots\n"
+        "assert rel_err(total[:n].cpu().numpy(), ref[:n].cpu().numpy()) <= 1e-5\n"
+        "assert rel_err(total[n:].view(-1, 8)[:V, :6].cpu().numpy(), ref_tau.cpu().numpy()) <= 1e-5\n"
+        "print('ok')\n"
+    ) % (here, os.path.join(root, "gs-slam-analytica_jacobian_b200"), root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, GSR_NO_FUSED_SCATTER="1"))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
