@@ -174,7 +174,7 @@ int pick_cap_smem(long long max_tile_hint)
 extern "C" {
 
 const char* gsr_error_string(void) { return g_err; }
-int gsr_version(void) { return 101; }
+int gsr_version(void) { return 102; }
 
 size_t gsr_geometry_bytes(int P, int W, int H) { return gsr::geom_bytes((size_t)(P > 0 ? P : 0), tiles_of(W, H)); }
 size_t gsr_image_bytes(int W, int H) { return gsr::image_bytes((size_t)W, (size_t)H); }
