@@ -161,18 +161,20 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 }
 
 // ---- screen-coherent permutation of the Gaussians (gsr_spatial_order): counting sort by home tile ----
-__device__ __forceinline__ uint32_t home_bucket(const GaussRec* __restrict__ rec, int idx, int grid_x)
+__device__ __forceinline__ uint32_t home_bucket(const GaussRec* __restrict__ rec, int idx, int grid_x, int n_tiles)
 {
 	const float4 q2 = __ldg(&rec[idx].q2);
 	const uint32_t lo = __float_as_uint(q2.z), hi = __float_as_uint(q2.w);
 	const uint32_t x0 = lo & 0xffff, y0 = lo >> 16, x1 = hi & 0xffff, y1 = hi >> 16;
 	if (x1 <= x0 || y1 <= y0) return 0u;      // culled: first bucket
-	return ((y0 + y1 - 1) >> 1) * (uint32_t)grid_x + ((x0 + x1 - 1) >> 1);      // the tile at the centre of the rectangle
+	// the tile at the centre of the rectangle (clamped: records that no forward plan has written must not index out of bounds)
+	return min(((y0 + y1 - 1) >> 1) * (uint32_t)grid_x + ((x0 + x1 - 1) >> 1), (uint32_t)n_tiles - 1u);
 }
-__global__ void __launch_bounds__(256) home_count_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, uint32_t* __restrict__ count)
+__global__ void __launch_bounds__(256) home_count_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, int n_tiles,
+                                                         uint32_t* __restrict__ count)
 {
 	const int idx = blockIdx.x * 256 + threadIdx.x;
-	if (idx < P) atomicAdd(&count[home_bucket(rec, idx, grid_x)], 1u);
+	if (idx < P) atomicAdd(&count[home_bucket(rec, idx, grid_x, n_tiles)], 1u);
 }
 __global__ void __launch_bounds__(256) bucket_scan_kernel(uint32_t* __restrict__ count, int tiles)      // one CTA: exclusive scan in place
 {
@@ -197,11 +199,11 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(uint32_t* __restrict__
 		run += c;
 	}
 }
-__global__ void __launch_bounds__(256) home_order_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, uint32_t* __restrict__ cursor,
-                                                         uint32_t* __restrict__ order)
+__global__ void __launch_bounds__(256) home_order_kernel(int P, const GaussRec* __restrict__ rec, int grid_x, int n_tiles,
+                                                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ order)
 {
 	const int idx = blockIdx.x * 256 + threadIdx.x;
-	if (idx < P) order[atomicAdd(&cursor[home_bucket(rec, idx, grid_x)], 1u)] = (uint32_t)idx;
+	if (idx < P) order[atomicAdd(&cursor[home_bucket(rec, idx, grid_x, n_tiles)], 1u)] = (uint32_t)idx;
 }
 
 // one CTA per tile; lists queued for the long-list kernel (use_long) are skipped here
@@ -280,9 +282,9 @@ void launch_spatial_order(const Scene& s, const GeomView& g, uint32_t* order_out
 {
 	const int tiles = s.grid_x * s.grid_y, grid = (s.P + 255) / 256;
 	cudaMemsetAsync(g.tile_cursor, 0, (size_t)tiles * sizeof(uint32_t), stream);
-	home_count_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, g.tile_cursor);
+	home_count_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, tiles, g.tile_cursor);
 	bucket_scan_kernel<<<1, 256, 0, stream>>>(g.tile_cursor, tiles);
-	home_order_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, g.tile_cursor, order_out);
+	home_order_kernel<<<grid, 256, 0, stream>>>(s.P, g.rec, s.grid_x, tiles, g.tile_cursor, order_out);
 }
 
 GSR_PROBE_READER(probe_read_scatter)

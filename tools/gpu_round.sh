@@ -30,3 +30,4 @@ ncu --set full --clock-control none --import-source on -k 'regex:^(preprocess|re
 echo "$S full capture rc=$?"
 done
 fi
+if [ -n "$WITH_SMOKE" ]; then python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke_$TAG.log; fi
