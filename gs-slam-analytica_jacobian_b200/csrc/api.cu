@@ -218,7 +218,7 @@ int gsr_forward_num_rendered(void* geom, void* stream, long long* out, long long
 static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* geom, void* binning, size_t binning_bytes,
                                long long capacity, long long R_host, long long max_tile_hint, void* image, size_t image_bytes,
                                float* out_color, float* out_depth, float* out_opacity, int* n_touched, cudaStream_t st,
-                               bool scatter_done)
+                               bool scatter_done, bool preprocess_just_launched = false)
 {
 	if (capacity < 0) return fail(GSR_ERR_ARG, "negative binning capacity");
 	if (R_host > capacity) return fail(GSR_ERR_WORKSPACE, "binning capacity below num_rendered");
@@ -239,14 +239,17 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	if (max_tile_hint > 0 && max_tile_hint <= lazy_min) lazy_min = 0;
 	const bool fuse_sort = !g_no_fused_sort && (lazy_min > 0 || (max_tile_hint > 0 && max_tile_hint <= GSR_SORT_CHUNK));
 	nvtxRangePushA("gsr: binning");
-	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done);
+	const bool pdl_ok = !g_timing.load() && !a->debug && !g_no_pdl && !g_no_pdl_fwd;
+	g_launches += gsr::launch_binning(s, g, b, (size_t)capacity, pick_cap_smem(max_tile_hint), max_tile_hint, fuse_sort, st, scatter_done,
+	                                  preprocess_just_launched && pdl_ok);
 	stage_mark(2, st);
 	nvtxRangePop();
 	int rc = debug_sync(a, st, "binning");
 	if (rc) return rc;
 	NvtxRange nvtx_render("gsr: render forward");
 	// directly behind the cooperative preprocess + scatter (no kernel in between): start inside its tail
-	const bool behind_preprocess = scatter_done && fuse_sort && !g_timing.load() && !a->debug && !g_no_pdl && !g_no_pdl_fwd;
+	// (cooperative preprocess + scatter, or the stand-alone scatter: either way the kernel in front built the segments)
+	const bool behind_preprocess = fuse_sort && pdl_ok && s.P > 0 && capacity > 0;
 	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st,
 	                           behind_preprocess);
 	stage_mark(3, st);
@@ -288,7 +291,7 @@ int gsr_forward_nosync(const gsr_scene* a, void* geom, size_t geom_bytes, void* 
 	rc = debug_sync(a, st, "preprocess");
 	if (rc) return rc;
 	return forward_render_impl(a, s, geom, binning, binning_bytes, capacity, -1, max_tile_hint, image, image_bytes, out_color,
-	                           out_depth, out_opacity, n_touched, st, scatter_done);
+	                           out_depth, out_opacity, n_touched, st, scatter_done, !scatter_done && s.P > 0 && !a->debug);
 }
 
 int gsr_forward_nosync_fuses_scatter(int P, int W, int H) { return gsr::fused_scatter_fits(P, (int)tiles_of(W, H)) ? 1 : 0; }

@@ -72,6 +72,8 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
                int n_tiles, int use_smem, const uint32_t* __restrict__ order)
 {
 	GSR_PROBE(1, 0);
+	pdl_launch_dependents();      // the forward compositing kernel may take the slots this grid frees (it waits for the segments itself)
+	pdl_wait();                   // launched as programmatic dependent of the preprocess: records, ranges and cursors are complete from here
 	const int sub = threadIdx.x & (kScatterLanes - 1);
 	const int slot = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
 	int idx = slot;
@@ -244,7 +246,7 @@ size_t tile_sort_smem_bytes(int cap_smem) { return sort_smem_bytes(cap_smem, kSm
 // R_capacity: instance capacity of the binning workspace.  cap_smem: longest tile list sorted in shared memory by the
 // 256-thread kernel; max_tile_hint: longest list expected (<= 0: unknown).
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
-                   bool fuse_sort, cudaStream_t stream, bool scatter_done)
+                   bool fuse_sort, cudaStream_t stream, bool scatter_done, bool behind_preprocess)
 {
 	if (s.P == 0 || R_capacity == 0) return 0;
 	const int tiles = s.grid_x * s.grid_y;
@@ -254,12 +256,25 @@ int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R
 	if (scatter_smem > 48 * 1024) ensure_dynamic_smem(scatter_kernel<false>, scatter_smem, scatter_attr);
 	static const bool no_order = getenv("GSR_NO_SPATIAL_ORDER") != nullptr;      // A/B switch for measurements
 	if (!scatter_done) {
-		if (s.spatial_order && !no_order)
-			scatter_kernel<true><<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, 2 * kBoxMax * sizeof(uint32_t), stream>>>(
-			s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, 1, s.spatial_order);
-		else
-			scatter_kernel<false><<<(s.P + kScatterGauss - 1) / kScatterGauss, kScatterThreads, scatter_smem, stream>>>(
-			s.P, g.rec, s.grid_x, g.tile_cursor, b.pairs, (unsigned)R_capacity, g.hdr, tiles, use_smem, nullptr);
+		// behind_preprocess: the preprocess kernel was launched just before on this stream and releases its dependents at once:
+		// the scatter's CTAs are resident when it ends (programmatic dependent launch; they wait for its results themselves)
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((s.P + kScatterGauss - 1) / kScatterGauss); cfg.blockDim = dim3(kScatterThreads); cfg.stream = stream;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at;
+		cfg.numAttrs = behind_preprocess ? 1 : 0;
+		const unsigned cap = (unsigned)R_capacity;
+		if (s.spatial_order && !no_order) {
+			cfg.dynamicSmemBytes = 2 * kBoxMax * sizeof(uint32_t);
+			cudaLaunchKernelEx(&cfg, scatter_kernel<true>, s.P, (const GaussRec*)g.rec, s.grid_x, g.tile_cursor, b.pairs, cap, g.hdr, tiles, 1,
+			                   (const uint32_t*)s.spatial_order);
+		} else {
+			cfg.dynamicSmemBytes = scatter_smem;
+			cudaLaunchKernelEx(&cfg, scatter_kernel<false>, s.P, (const GaussRec*)g.rec, s.grid_x, g.tile_cursor, b.pairs, cap, g.hdr, tiles,
+			                   use_smem, (const uint32_t*)nullptr);
+		}
 	}
 	if (fuse_sort) return scatter_done ? 0 : 1;      // the forward compositing kernel sorts its own tile
 	int id_bits = 1;

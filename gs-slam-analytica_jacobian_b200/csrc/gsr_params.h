@@ -93,7 +93,7 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 // max_tile_hint = longest list expected (<= 0: unknown)
 // fuse_sort: launch only the scatter; the per-tile sort then runs inside the forward compositing kernel
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
-                   bool fuse_sort, cudaStream_t stream, bool scatter_done = false);
+                   bool fuse_sort, cudaStream_t stream, bool scatter_done = false, bool behind_preprocess = false);
 size_t tile_sort_smem_bytes(int cap_smem);
 // permutation of [0, P) by home tile from the records of the last forward plan (clobbers g.tile_count / g.tile_cursor)
 void launch_spatial_order(const Scene& s, const GeomView& g, uint32_t* order_out, cudaStream_t stream);

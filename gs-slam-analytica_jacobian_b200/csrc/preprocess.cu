@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(Scene s, GeomVi
 	extern __shared__ uint32_t s_hist[];   // [tiles] CTA-private tile histogram (hist_smem != 0)
 
 	GSR_PROBE(0, 0);
+	if (!FUSED_SCATTER) pdl_launch_dependents();      // two-kernel path: the scatter (launched as programmatic dependent) moves into this grid's tail
 	const int row0 = blockIdx.x * 256;
 	const int idx = row0 + threadIdx.x;
 	const int n_tiles = s.grid_x * s.grid_y;
