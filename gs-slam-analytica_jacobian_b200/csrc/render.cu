@@ -107,7 +107,10 @@ struct FusedSortArgs {
 constexpr int kFusedIdsOffset = 40960;    // bytes: behind the FwdSmem overlay, inside the sort's counter scratch
 constexpr int kFusedIdsCap = GSR_SORT_CHUNK;
 constexpr int kLazyBins = 1024;           // depth bins over the tile's key range: four per thread
-constexpr int kLazyTarget = 512;          // entries a slab should hold at least: two compositing batches
+#ifndef GSR_LAZY_TARGET
+#define GSR_LAZY_TARGET 512
+#endif
+constexpr int kLazyTarget = GSR_LAZY_TARGET;   // entries a slab should hold at least: two compositing batches (experiments: -DGSR_LAZY_TARGET=n)
 constexpr int kRankMax = 256;             // longest depth bin ordered by all-pairs ranking
 struct LazySmem {                         // lives behind the sort scratch: survives sorts and compositing
 	uint32_t excl[kLazyBins + 1];         // list position at which bin b starts
