@@ -92,3 +92,41 @@ def test_shard_map():
     for parts in (2, 3, 5):
         b = band_rows(43, parts, list(range(43)))
         assert b[0][0] == 0 and b[-1][1] == 43 and all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(y1 > y0 for y0, y1 in b)
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diff_gaussian_rasterization.window import SwitchReducer      # needs libgsr_b200.so (built in-tree)
+
+        red = SwitchReducer.create(1024, "cpu")      # no multicast memory on the CPU: every rank must agree on "unavailable"
+        ok = red is None and SwitchReducer.last_error is not None
+    except ImportError:
+        ok = True      # library not built here: nothing to check
+    np.save(os.path.join(out_dir, "s%d.npy" % rank), np.array([1 if ok else 0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_switch_reducer_reports_unavailable_consistently_without_multicast_memory(tmp_path):
+    """SwitchReducer.create is a collective that must return None on EVERY rank (the caller then uses dist.all_reduce) when the
+    symmetric / multicast allocation cannot be made -- here: CPU tensors under gloo."""
+    mp.spawn(_reducer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert int(np.load(tmp_path / ("s%d.npy" % r))[0]) == 1
+
+
+def test_plan_units_whole_bands():
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    from diff_gaussian_rasterization.window import band_rows, plan_units
+
+    plan = plan_units(10, 8, 43, whole_bands=2)
+    assert plan[0][:2] == [(0,) + band_rows(43, 2)[0], (0,) + band_rows(43, 2)[1]] and len(plan[0]) == 3
+    rows = np.zeros((10, 43), np.int64)
+    for units in plan:
+        for v, y0, y1 in units:
+            rows[v, (y0 if y1 else 0):(y1 if y1 else 43)] += 1
+    assert (rows == 1).all()
