@@ -12,7 +12,8 @@
 // of the entries) in list order into a warp-private shared-memory queue.  The pixel threads then run a
 // branch-free, two-way unrolled loop over the queue with the reference's per-pair decisions:
 //   * every record is three broadcast LDS.128 at immediate offsets (no per-entry bit scan / address math),
-//   * the exponent keeps the reference's expression tree (bit-identical power), exp is one ex2.approx.ftz,
+//   * the exponent keeps the reference's expression tree (bit-identical power); exp is the reference's own expf by default
+//     (EXACT: alpha, T and every threshold decision bit-identical to the reference's) or one ex2.approx.ftz (gsr_scene.exact_exp < 0),
 //   * "done" is carried in the sign of T (T < 0 <=> this pixel stopped; |T| is its final transmittance), so the
 //     three per-pair tests of the reference collapse into compares whose results are used as predicates,
 //   * n_touched (pixels whose transmittance after the blend is still > 0.5, forward.cu:511-514) costs one vote +
