@@ -64,6 +64,13 @@ __device__ __forceinline__ void for_each_tile_quad(uint32_t n, uint32_t lo, uint
 // global atomics per CTA instead of ~2000) and its pairs land in runs of dozens instead of isolated 8-byte stores.  A box
 // above kBoxMax tiles (an oversized Gaussian among the 256) sends the CTA down the per-instance path.
 constexpr int kBoxMax = 2048;
+// -DGSR_DEBUG_CHECKS (never the product; compute-sanitizer is closed on this pool): index checks of the ordered scatter that
+// trap instead of writing out of bounds -- run the binning / config-scale tests with such a build (tools/debug_checks.sh)
+#ifdef GSR_DEBUG_CHECKS
+#define GSR_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define GSR_CHECK(cond) do { } while (0)
+#endif
 
 template <bool ORDERED>
 __global__ void __launch_bounds__(kScatterThreads, 4)
@@ -78,6 +85,7 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 	const int slot = blockIdx.x * kScatterGauss + (threadIdx.x / kScatterLanes);
 	int idx = slot;
 	if (ORDERED) idx = slot < P ? (int)__ldg(&order[slot]) : P;
+	GSR_CHECK(!ORDERED || (idx >= 0 && idx <= P));
 	uint32_t n = 0, lo = 0, hi = 0, key = 0;
 	if (idx < P) {
 		// one round trip: the rectangle (all zero for a culled Gaussian) gives the tile count itself
@@ -133,7 +141,10 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 		for (int t = threadIdx.x; t < span; t += kScatterThreads) s_cnt[t] = 0;
 		__syncthreads();
 		GSR_PROBE(1, 1);
-		for_each_tile_quad(n, lo, hi, gx, 0u, 0u, sub, [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(&s_cnt[tile], 1u); });
+		for_each_tile_quad(n, lo, hi, gx, 0u, 0u, sub, [&](uint32_t tile, uint32_t, uint32_t) {
+			GSR_CHECK(tile < (uint32_t)span);
+			atomicAdd(&s_cnt[tile], 1u);
+		});
 		__syncthreads();
 		GSR_PROBE(1, 2);
 		for (int t = threadIdx.x; t < span; t += kScatterThreads) {
@@ -144,6 +155,7 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 					const uint32_t ty = (uint32_t)t / (uint32_t)gx;
 					gt = (by0 + ty) * (uint32_t)grid_x + bx0 + ((uint32_t)t - ty * (uint32_t)gx);
 				}
+				GSR_CHECK(gt < (uint32_t)n_tiles);
 				s_base[t] = atomicAdd(&cursor[gt], c);
 			}
 			s_cnt[t] = 0;
@@ -154,6 +166,7 @@ scatter_kernel(int P, const GaussRec* __restrict__ rec, int grid_x,
 	bool overflow = false;
 	// pass 2: claim a slot per (Gaussian, tile) inside the CTA's slice and store the pair
 	for_each_tile_quad(n, lo, hi, gx, key, (uint32_t)idx, sub, [&](uint32_t tile, uint32_t g_key, uint32_t g_id) {
+		GSR_CHECK(tile < (uint32_t)(use_smem ? span : n_tiles));
 		const uint32_t pos = use_smem ? s_base[tile] + atomicAdd(&s_cnt[tile], 1u) : atomicAdd(&cursor[tile], 1u);
 		if (pos < capacity) pairs[pos] = make_uint2(g_key, g_id);
 		else overflow = true;
