@@ -37,8 +37,14 @@ namespace {
 // two lanes halve the chain (the largest rectangle among the warp's Gaussians) and double the warps in flight; four
 // lanes are more than one wave of CTAs at P = 100 k.  One thread per Gaussian with the balanced walk for every
 // rectangle was measured too: 5-8 % slower here (the kernel is bound by its partial-sector stores).
-constexpr int kScatterLanes = 2;
-constexpr int kScatterGauss = 256;                           // Gaussians per CTA
+#ifndef GSR_SCATTER_LANES
+#define GSR_SCATTER_LANES 2
+#endif
+constexpr int kScatterLanes = GSR_SCATTER_LANES;      // (experiments: -DGSR_SCATTER_LANES=1|4)
+#ifndef GSR_SCATTER_GAUSS
+#define GSR_SCATTER_GAUSS 256
+#endif
+constexpr int kScatterGauss = GSR_SCATTER_GAUSS;             // Gaussians per CTA
 constexpr int kScatterThreads = kScatterGauss * kScatterLanes;
 
 // visit the tiles of this thread's share of its Gaussian's rectangle: steps sub, sub + kScatterLanes, ... of a row-major
