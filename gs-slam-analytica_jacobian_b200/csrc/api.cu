@@ -17,6 +17,7 @@ int probe_read_preprocess(unsigned long long*);
 int probe_read_scatter(unsigned long long*);
 int probe_read_preprocess_backward(unsigned long long*);
 int probe_read_render(unsigned long long*);
+int probe_read_render_backward(unsigned long long*);
 }
 
 namespace {
@@ -397,6 +398,8 @@ int gsr_debug_probe(unsigned long long* out, size_t bytes)
 	const size_t one = 4096 * 8;
 	if (!out || bytes < 3 * one * sizeof(unsigned long long)) return fail(GSR_ERR_ARG, "probe buffer too small");
 	if (bytes >= 4 * one * sizeof(unsigned long long) && gsr::probe_read_render(out + 3 * one))
+		return fail(GSR_ERR_ARG, "library built without GSR_PHASE_PROBE");
+	if (bytes >= 5 * one * sizeof(unsigned long long) && gsr::probe_read_render_backward(out + 4 * one))
 		return fail(GSR_ERR_ARG, "library built without GSR_PHASE_PROBE");
 	if (cudaDeviceSynchronize() != cudaSuccess) return fail(GSR_ERR_CUDA, "sync failed");
 	if (gsr::probe_read_preprocess(out) || gsr::probe_read_scatter(out + one) || gsr::probe_read_preprocess_backward(out + 2 * one))

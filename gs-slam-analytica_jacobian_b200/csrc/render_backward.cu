@@ -166,6 +166,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
 	const int tile = tile0 + (int)blockIdx.x;      // tile0: first tile of the band this launch covers
+	GSR_PROBE(4, 0);
 	pdl_launch_dependents();      // the per-Gaussian backward may move in (and fetch its inputs) during this kernel's tail
 	// Launched as a programmatic dependent of the forward compositing kernel (RasterEngine.step) this CTA may be running
 	// while forward CTAs of other tiles still are: wait for ITS tile (a flag the forward CTA releases behind its last
@@ -191,6 +192,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		sm.wmax[0] = v ? v - 1u : 0u;
 	}
 	__syncthreads();
+	GSR_PROBE(4, 1);      // the tile's flag (and the upstream word) are in
 	const uint32_t top = sm.wmax[0];
 	const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +263,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		}
 		cp_async_wait<1>();
 		__syncthreads();
+		if (b == 0) GSR_PROBE(4, 2);      // per-pixel state loaded, first batch of records staged: the prologue a fused kernel would not have
 		for (int c0 = 0; c0 < cnt; c0 += 32) {
 			// lane L <-> slot c0 + L <-> position p = hi - 1 - c0 - L = 32 g + (31 - L)
 			const uint32_t fm = __shfl_sync(kFull, fetched, c0 >> 5);
@@ -304,6 +307,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 		flush_panel(panel, sm.dpix[warp], qn, lane, wq + head, bx0, by0, ddelx_dx, ddely_dy, acc);
 	}
 	cp_async_wait<0>();
+	GSR_PROBE(4, 3);
 }
 
 }  // namespace
@@ -331,5 +335,7 @@ void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b,
 	                   (const uint32_t*)b.cull_masks, (const uint32_t*)g.tile_done, (const uint32_t*)s.upstream_ready, g.hdr,
 	                   band ? s.band_y0 * s.grid_x : 0);
 }
+
+GSR_PROBE_READER(probe_read_render_backward)
 
 }  // namespace gsr

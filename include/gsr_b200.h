@@ -291,7 +291,7 @@ unsigned long long gsr_kernel_launch_count(void);
  * programmatic dependent launches (the event records sit between the kernels). */
 int gsr_stage_timing(int enable);
 int gsr_stage_times_ms(float* out5);
-/* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3 or 4][4096][8] %globaltimer table
+/* phase probe of a -DGSR_PHASE_PROBE build (tools/phase_probe.py): copies the u64[3, 4 or 5][4096][8] %globaltimer table
  * (kernel, CTA, phase) to the host; returns an error in the product build, which carries no probes */
 int gsr_debug_probe(unsigned long long* out, size_t bytes);
 

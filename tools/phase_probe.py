@@ -32,7 +32,7 @@ for _ in range(5):
     eng.step()
 torch.cuda.synchronize()
 L = _cabi.load()
-buf = np.zeros((4, 4096, 8), np.uint64)
+buf = np.zeros((5, 4096, 8), np.uint64)
 _cabi.check(L.gsr_debug_probe(buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.nbytes), "probe")
 tiles = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
 for k, (kname, nph) in enumerate((("preprocess_forward", 8), ("scatter", 5), ("preprocess_backward", 4), ("render_forward", 5))):
@@ -56,6 +56,18 @@ d04 = (tb[ok, 4] - tb[ok, 0]) / 1e3
 more = (tb[ok, 3] > tb[ok, 0]).mean()
 print("render_forward per CTA [us]: list ready med %.2f p90 %.2f | first run of batches med %.2f p90 %.2f | whole CTA med %.2f p90 %.2f | CTAs that ordered a further slab: %.1f %%"
       % (np.median(d01), np.percentile(d01, 90), np.median(d12), np.percentile(d12, 90), np.median(d04), np.percentile(d04, 90), 100 * more))
+
+# render backward: 0 start, 1 tile flag acquired, 2 per-pixel state loaded + first batch of records staged (the prologue a
+# compositing CTA that ran the backward right behind its own forward would not have), 3 end
+tbb = buf[4, :min(4096, tiles), :4].astype(np.int64)
+okb = tbb[:, 0] > 0
+if okb.any():
+    w01 = (tbb[okb, 1] - tbb[okb, 0]) / 1e3
+    w12 = (tbb[okb, 2] - tbb[okb, 1]) / 1e3
+    w03 = (tbb[okb, 3] - tbb[okb, 0]) / 1e3
+    print("render_backward per CTA [us]: flag wait med %.2f p90 %.2f | loads + first gather med %.2f p90 %.2f | whole CTA med %.2f p90 %.2f | prologue share of the CTA time: %.1f %%"
+          % (np.median(w01), np.percentile(w01, 90), np.median(w12), np.percentile(w12, 90), np.median(w03), np.percentile(w03, 90),
+             100 * (w01.sum() + w12.sum()) / w03.sum()))
 
 # scheduling headroom of the compositing kernel: greedy list scheduling of the measured CTA durations on the resident slots
 import heapq
