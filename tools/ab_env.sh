@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of one environment switch on the default bench line:  VAR=GSR_NO_PDL_FWD bash tools/quick_ab2.sh
+# A/B of one environment switch on the default bench line:  VAR=GSR_NO_PDL_FWD bash tools/ab_env.sh
 O=gpurun_out
 VAR=${VAR:-GSR_NO_PDL_FWD}
 python -m pytest tests -m gpu -x -q > $O/pytest_ab2.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_ab2.log
