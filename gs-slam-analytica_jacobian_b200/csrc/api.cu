@@ -140,6 +140,7 @@ int make_scene(const gsr_scene* a, gsr::Scene& s)
 	s.exact_exp = exact > 0 ? 1 : 0;
 	s.exact_exp_bwd = exact > 1 ? 1 : 0;
 	s.spatial_order = a->spatial_order;
+	s.depth_cut = a->depth_cut;
 	s.band_y0 = s.band_y1 = 0;
 	if (a->tile_row_end != 0 || a->tile_row_begin != 0) {
 		if (a->tile_row_begin < 0 || a->tile_row_end <= a->tile_row_begin || a->tile_row_end > s.grid_y)
@@ -251,8 +252,9 @@ static int forward_render_impl(const gsr_scene* a, const gsr::Scene& s, void* ge
 	// directly behind the cooperative preprocess + scatter (no kernel in between): start inside its tail
 	// (cooperative preprocess + scatter, or the stand-alone scatter: either way the kernel in front built the segments)
 	const bool behind_preprocess = fuse_sort && pdl_ok && s.P > 0 && capacity > 0;
+	// (the stand-alone scatter in spatial order partitions the segments by depth when the caller keeps a depth_cut array)
 	gsr::launch_render_forward(s, g, b, im, out_color, out_depth, out_opacity, n_touched, fuse_sort, lazy_min, (size_t)capacity, st,
-	                           behind_preprocess);
+	                           behind_preprocess, !scatter_done && gsr::depth_partition_active(s));
 	stage_mark(3, st);
 	g_launches += 1;
 	return debug_sync(a, st, "render");

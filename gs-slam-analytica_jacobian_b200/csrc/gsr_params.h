@@ -45,6 +45,7 @@ struct Scene {
 	int exact_exp;                // forward: alpha from the reference's expf instead of ex2.approx (bit-identical T, n_contrib, n_touched)
 	int band_y0, band_y1;         // tile rows [band_y0, band_y1) this call renders (a band of the view); band_y1 == 0: the whole image
 	const uint32_t* spatial_order; // optional permutation of [0, P): screen-coherent processing order of the scatter kernel
+	uint32_t* depth_cut;           // optional [tiles] in/out: per-tile depth-key hint that splits a tile's segment into front / back (binning.cu)
 	float* densify_grad_accum;    // [P] or null
 	float* densify_denom;         // [P] or null
 	float* max_radii2D;           // [P] or null
@@ -95,13 +96,14 @@ bool launch_preprocess_forward(const Scene& s, const GeomView& g, int* radii, in
 int launch_binning(const Scene& s, const GeomView& g, const BinView& b, size_t R_capacity, int cap_smem, long long max_tile_hint,
                    bool fuse_sort, cudaStream_t stream, bool scatter_done = false, bool behind_preprocess = false);
 size_t tile_sort_smem_bytes(int cap_smem);
+bool depth_partition_active(const Scene& s);
 // permutation of [0, P) by home tile from the records of the last forward plan (clobbers g.tile_count / g.tile_cursor)
 void launch_spatial_order(const Scene& s, const GeomView& g, uint32_t* order_out, cudaStream_t stream);
 // fused_sort: the forward kernel sorts each tile's segment itself (launch_binning was called with fuse_sort = true);
 // lazy_min > 0: lists longer than lazy_min are ordered on demand, slab by slab, as far as the compositing gets (render.cu)
 void launch_render_forward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im, float* out_color,
                            float* out_depth, float* out_opacity, int* n_touched, bool fused_sort, int lazy_min, size_t R_capacity,
-                           cudaStream_t stream, bool behind_preprocess = false);
+                           cudaStream_t stream, bool behind_preprocess = false, bool front_partition = false);
 void launch_render_backward(const Scene& s, const GeomView& g, const BinView& b, const ImageView& im,
                             const float* dL_dpix, const float* dL_dpix_depth, bool overlap_forward, cudaStream_t stream);
 void launch_preprocess_backward(const Scene& s, const GeomView& g, const int* radii, float* dL_dmeans3D,

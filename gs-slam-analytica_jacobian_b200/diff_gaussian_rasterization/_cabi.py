@@ -42,7 +42,7 @@ class GsrScene(C.Structure):
         ("prefiltered", C.c_int), ("debug", C.c_int), ("accumulate_grads", C.c_int),
         ("densify_grad_accum", C.c_void_p), ("densify_denom", C.c_void_p), ("max_radii2D", C.c_void_p),
         ("overlap_forward", C.c_int), ("upstream_ready", C.c_void_p), ("fused_loss", C.POINTER(GsrFusedLoss)),
-        ("sort_on_demand", C.c_int), ("exact_exp", C.c_int), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int), ("spatial_order", C.c_void_p),
+        ("sort_on_demand", C.c_int), ("exact_exp", C.c_int), ("tile_row_begin", C.c_int), ("tile_row_end", C.c_int), ("spatial_order", C.c_void_p), ("depth_cut", C.c_void_p),
     ]
 
 

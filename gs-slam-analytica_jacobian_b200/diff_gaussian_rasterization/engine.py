@@ -116,6 +116,7 @@ class RasterEngine:
         s.prefiltered, s.debug, s.accumulate_grads, s.overlap_forward = 0, 0, 0, 0
         s.upstream_ready = None
         s.spatial_order = None
+        s.depth_cut = None
         s.densify_grad_accum = s.densify_denom = s.max_radii2D = None
         self.scene = s
         self.graph_fwd = self.graph_bwd = self.graph_all = None
@@ -123,6 +124,8 @@ class RasterEngine:
         # screen-coherent processing orders of the scatter kernel (gsr_scene.spatial_order), one per key (a window unit);
         # built by calibrate() for maps too large for the cooperative preprocess + scatter kernel
         self.spatial_orders = {}
+        self.depth_cuts = {}      # per key: the per-tile depth hints that go with the order (gsr_scene.depth_cut)
+        self.depth_cut_min_list = 4096
         self.order_key = 0
         self.use_spatial_order = (not os.environ.get("GSR_NO_SPATIAL_ORDER")) and not _L.gsr_forward_nosync_fuses_scatter(P, W, H)
         # step(): the compositing backward overlaps the tail of the compositing forward (GSR_NO_OVERLAP=1: plain order)
@@ -166,8 +169,11 @@ class RasterEngine:
         self.order_key = key
         t = self.spatial_orders.get(key)
         ptr = None if t is None else t.data_ptr()
-        if ptr != self.scene.spatial_order:
+        c = self.depth_cuts.get(key) if t is not None else None
+        cptr = None if c is None else c.data_ptr()
+        if ptr != self.scene.spatial_order or cptr != self.scene.depth_cut:
             self.scene.spatial_order = ptr
+            self.scene.depth_cut = cptr
             self.graph_fwd = self.graph_bwd = self.graph_all = None
 
     # ---- capacity -------------------------------------------------------------------------------------
@@ -192,6 +198,7 @@ class RasterEngine:
             R, mt = C.c_longlong(0), C.c_longlong(0)
             _cabi.check(_L.gsr_forward_num_rendered(_p(self.geom), self._stream(), C.byref(R), C.byref(mt)), "num_rendered")
         self.last_num_rendered = int(R.value)
+        self.longest_list = max(getattr(self, "longest_list", 0), int(mt.value))
         hint = int(mt.value * self.headroom) + 64      # longest per-tile list -> smem capacity of the tile sort
         if hint > self.max_tile_hint:
             self.max_tile_hint = hint
@@ -205,6 +212,12 @@ class RasterEngine:
                 t = self.spatial_orders[self.order_key] = torch.empty((self.P,), dtype=torch.int32, device=self.dev)
             with torch.cuda.device(self.dev):
                 _cabi.check(_L.gsr_spatial_order(C.byref(self.scene), _p(self.geom), self.geom_bytes, _p(t), self._stream()), "spatial_order")
+            # per-tile depth hints (gsr_scene.depth_cut) pay where the forward sweeps lists too long for its registers (> 4096
+            # entries: C4 view 2.41 -> 2.20 ms); at 2-3 k entries per tile the partition costs the scatter what it saves the
+            # forward (C2: +0.2 %), so shorter lists run without
+            if self.order_key not in self.depth_cuts and self.longest_list > self.depth_cut_min_list and not os.environ.get("GSR_NO_DEPTH_CUT"):
+                tiles = ((self.W + 15) // 16) * ((self.H + 15) // 16)
+                self.depth_cuts[self.order_key] = torch.full((tiles,), 0x7f800000, dtype=torch.int32, device=self.dev)      # +inf: no cut yet
             self.use_order(self.order_key)
         return int(R.value)
 

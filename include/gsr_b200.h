@@ -142,6 +142,15 @@ typedef struct gsr_scene {
 	                                in runs.  ANY permutation gives the same lists (the order inside a segment is fixed later,
 	                                by depth and id); a stale one -- built for an earlier pose -- only costs speed.  The caller
 	                                guarantees that it IS a permutation. */
+	unsigned int* depth_cut;     /* forward only, optional (null = off), used together with spatial_order: device unsigned int[tiles],
+	                                in/out, initialised by the caller to 0x7f800000 (+inf) and then left alone.  A per-tile depth HINT
+	                                carried from one forward of a view to the next: the scatter puts the pairs with depth <= the
+	                                tile's value at the front of the tile's segment and the others at its back (same segment, same
+	                                count), the compositing forward orders the front part first and touches the back part only if
+	                                the tile is still open behind it, and writes the value for the next call (the depth a little
+	                                behind the tile's deepest contributor).  SLAM loops render the same views again and again, and
+	                                compositing reads 2-40 % of a list: the forward then skips its sweeps over the rest.  Results do
+	                                not depend on the values (sorted front ++ sorted back is the sorted list). */
 } gsr_scene;
 
 /* device allocator callback: must return a device pointer to >= bytes, aligned to 256 B, or null */

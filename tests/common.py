@@ -44,7 +44,7 @@ def settings_from_scene(sc_t):
         prefiltered=False, debug=bool(sc_t.get("debug", False)))
 
 
-def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, on_demand=0, exact_exp=0, lean=False, spatial_order=None):
+def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, on_demand=0, exact_exp=0, lean=False, spatial_order=None, depth_cut=None):
     """Run the product path through its C-ABI on `device`; returns outputs, internals and gradients
     as numpy arrays.  sc: numpy scene dict (tests/scenes.py).
     on_demand: per-call threshold (gsr_scene.sort_on_demand) -- 0 (default here): every per-tile list is sorted completely,
@@ -52,10 +52,10 @@ def run_ours(sc, dL_dcolor=None, dL_ddepth=None, device="cuda", capacity=None, o
     None: the library default (on demand, 256).
     exact_exp: gsr_scene.exact_exp (0 = library default = exact, -1 = ex2.approx).
     lean: skip the host copies of the per-Gaussian records (large scenes)."""
-    return _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand, exact_exp, lean, spatial_order)
+    return _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand, exact_exp, lean, spatial_order, depth_cut)
 
 
-def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand=0, exact_exp=0, lean=False, spatial_order=None):
+def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand=0, exact_exp=0, lean=False, spatial_order=None, depth_cut=None):
     import diff_gaussian_rasterization as dgr
     import scenes as S
 
@@ -70,6 +70,7 @@ def _run_ours(sc, dL_dcolor, dL_ddepth, device, capacity, on_demand=0, exact_exp
     call.scene.sort_on_demand = 0 if on_demand is None else (-1 if int(on_demand) == 0 else int(on_demand))
     call.scene.exact_exp = int(exact_exp)
     call.scene.spatial_order = None if spatial_order is None else spatial_order.data_ptr()      # device int32 permutation
+    call.scene.depth_cut = None if depth_cut is None else depth_cut.data_ptr()                  # device int32[tiles], in/out
     R, cap, color, radii, geom, binning, img, depth, opacity, n_touched = dgr._forward_impl(call, capacity)
     torch.cuda.synchronize()
     P, W, H = call.P, call.W, call.H

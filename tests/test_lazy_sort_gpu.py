@@ -141,3 +141,81 @@ def test_engine_default_is_on_demand_and_matches():
         assert np.array_equal(eng.n_touched.cpu().numpy(), full["n_touched"])
         assert rel_err(eng.g_tau.cpu().numpy(), full["dL_dtau"]) <= 1e-5
         assert rel_err(eng.g_means3D.cpu().numpy(), full["dL_dmeans3D"]) <= 1e-5
+
+
+# ---- depth partition of the segments (gsr_scene.depth_cut; binning.cu scatter_kernel<true>, render.cu two-part lists) ----
+def _check_partition(sc, ref, threshold, cuts):
+    """Scatter in spatial order with per-tile depth hints `cuts` (device int32[tiles], in/out): every output, n_contrib,
+    final_T, n_touched bit-identical to the run without hints, point_list bit-exact against the reference on the consumed prefix,
+    gradients within 1e-5 of the run without hints.  Returns the updated hints."""
+    import scenes as S
+    from test_binning_gpu import _order_for
+
+    W, H = int(sc["image_width"]), int(sc["image_height"])
+    dc, dd = S.make_pixel_grads(W, H, seed=11)
+    order, _ = _order_for(sc)
+    plain = run_ours(sc, dc, dd, on_demand=threshold)
+    part = run_ours(sc, dc, dd, on_demand=threshold, spatial_order=order, depth_cut=cuts)
+    r = ref.forward(sc)
+    assert part["overflow"] == 0 and part["num_rendered"] == r["num_rendered"]
+    np.testing.assert_array_equal(part["ranges"], r["ranges"])
+    for k in ("color", "depth", "opacity", "final_T", "n_contrib", "n_touched", "radii"):
+        np.testing.assert_array_equal(part[k], plain[k], err_msg=k)
+    top = _tile_top(part, W, H)
+    start = r["ranges"][:, 0].astype(np.int64)
+    bad = [t for t in range(start.size)
+           if not np.array_equal(part["point_list"][start[t]:start[t] + top[t]], r["point_list"][start[t]:start[t] + top[t]])]
+    assert not bad, "tiles whose consumed list prefix differs from the reference: %s" % bad[:8]
+    for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dtau", "dL_dmean2D"):
+        assert rel_err(part[k], plain[k]) <= 1e-5, k
+    return cuts
+
+
+@pytest.mark.parametrize("kind", ["inf", "random", "zero", "iterated"])
+def test_depth_partition_gives_the_same_results_for_any_hint(ref, kind):
+    """The hint only moves pairs between the two ends of a tile's segment: +inf (everything in front: the plain path), random
+    depths (front parts of every size, many tiles must go on into their back part), 0 (everything behind), and the hints the
+    forward itself writes, fed back three times (the steady state of a SLAM loop)."""
+    import torch
+
+    sc = _identity_scene(160, 128, 15000, seed=6, f=120.0)
+    sc["scales"] = (sc["scales"] * 5.0).astype(np.float32)
+    sc["opacities"] = np.maximum(sc["opacities"], np.float32(0.6))
+    tiles = 10 * 8
+    if kind == "inf":
+        cuts = torch.full((tiles,), 0x7f800000, dtype=torch.int32, device="cuda")
+    elif kind == "zero":
+        cuts = torch.zeros((tiles,), dtype=torch.int32, device="cuda")
+    else:
+        g = torch.Generator().manual_seed(3)
+        depth = (torch.rand(tiles, generator=g) * 6.0).float()
+        cuts = depth.view(torch.int32).cuda() if kind == "random" else torch.full((tiles,), 0x7f800000, dtype=torch.int32, device="cuda")
+    before = cuts.clone()
+    for rep in range(3 if kind == "iterated" else 1):
+        _check_partition(sc, ref, 300, cuts)
+    after = cuts.cpu().numpy()
+    # the forward wrote next iteration's hints: finite depths for tiles that closed, +inf for tiles with an open pixel
+    assert (after != before.cpu().numpy()).any() or kind == "inf"
+    assert ((after == 0x7f800000) | ((after.view(np.float32) > 0.2) & (after.view(np.float32) < 50.0))).all()
+    if kind == "iterated":
+        assert (after != 0x7f800000).mean() > 0.5      # an opaque scene: most tiles close and carry a cut
+
+
+def test_depth_partition_transparent_scene_and_depth_ties(ref):
+    """No pixel ever closes (every tile reads front AND back part to the end); and exact depth ties across the cut."""
+    import torch
+
+    sc = _identity_scene(96, 80, 6000, seed=8, f=120.0)
+    sc["scales"] = (sc["scales"] * 4.0).astype(np.float32)
+    sc["opacities"] = np.minimum(sc["opacities"], np.float32(0.02))
+    tiles = 6 * 5
+    cuts = torch.tensor(np.full(tiles, 2.5, np.float32)).view(torch.int32).cuda()
+    _check_partition(sc, ref, 64, cuts)
+    assert (cuts.cpu().numpy() == 0x7f800000).all()          # open tiles: no cut for the next iteration
+    sc = _identity_scene(160, 128, 6000, seed=3)
+    z = sc["means3D"][:, 2]
+    q = np.float32(5.5 / 40)
+    sc["means3D"][:, 2] = np.where(z > 0.3, np.round(z / q) * q, z).astype(np.float32)
+    sc["scales"] = (sc["scales"] * 3.0).astype(np.float32)
+    cuts = torch.tensor(np.full(10 * 8, float(q * 12), np.float32)).view(torch.int32).cuda()      # exactly ON a depth level
+    _check_partition(sc, ref, 64, cuts)
