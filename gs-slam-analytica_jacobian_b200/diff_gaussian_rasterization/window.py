@@ -92,6 +92,23 @@ def plan_units(num_views, world_size, grid_y, split=True, row_weights=None, whol
     return units
 
 
+def tau_rows(units, num_views):
+    """Row of the [tau_slots, 8] pose-gradient block every local unit writes its dL/dtau into (the backward kernel STORES its
+    six sums): the first unit of a view on this rank takes row `view`, every further band of the same view (whole_bands > 1)
+    a spare row behind the window's views; `merges` = [(spare row, view), ...] are added into the view's row before the
+    reduction.  Returns (rows, merges)."""
+    rows, merges, seen, spare = [], [], set(), int(num_views)
+    for (v, _, _) in units:
+        if v in seen:
+            rows.append(spare)
+            merges.append((spare, v))
+            spare += 1
+        else:
+            seen.add(v)
+            rows.append(v)
+    return rows, merges
+
+
 def allreduce_window_gradients(grad_flat, group=None):
     """Sum the packed per-Gaussian gradient buffer over all ranks, in place (one collective per window
     iteration).  No-op without an initialised process group (single GPU)."""
@@ -205,6 +222,8 @@ class KeyframeWindow:
         self.units = self.plan[rank]
         self.views = [u[0] for u in self.units]
         n = len(self.units)
+        self.tau_row, self.tau_merges = tau_rows(self.units, self.num_views)
+        assert self.num_views + len(self.tau_merges) <= engine.tau_slots, "tau_slots too small for the bands of this rank"
         self.num_rendered = [0] * n
         self.streams = [torch.cuda.Stream(engine.dev) for _ in self.engines] if len(self.engines) > 1 else None
         # dL/dtau of EVERY view of the window (complete after the all-reduce; rows of other ranks' whole views are theirs)
@@ -265,14 +284,14 @@ class KeyframeWindow:
                 eng.use_order(i)
                 if fused_loss is not None:
                     eng.launch_forward(fused_loss=fused_loss(i, v))
-                    eng.launch_backward(accumulate=(i > 0), overlap_forward=True, tau_out=eng.tau_block[v])
+                    eng.launch_backward(accumulate=(i > 0), overlap_forward=True, tau_out=eng.tau_block[self.tau_row[i]])
                 else:
                     eng.launch_forward()
                     if callable(upstream):
                         gc, gd = upstream(v)
                     else:
                         gc, gd = upstream[0][v], upstream[1][v]
-                    eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed, tau_out=eng.tau_block[v])
+                    eng.launch_backward(gc, gd, accumulate=(i > 0), overlap_forward=upstream_precomputed, tau_out=eng.tau_block[self.tau_row[i]])
                 if on_view is not None:
                     on_view(i, v)
         else:
@@ -289,18 +308,20 @@ class KeyframeWindow:
                     e.use_order(i)
                     if fused_loss is not None:
                         e.launch_forward(fused_loss=fused_loss(i, v))
-                        e.launch_backward(accumulate="atomic", overlap_forward=True, tau_out=eng.tau_block[v])
+                        e.launch_backward(accumulate="atomic", overlap_forward=True, tau_out=eng.tau_block[self.tau_row[i]])
                     else:
                         e.launch_forward()
                         if callable(upstream):
                             gc, gd = upstream(v, e)
                         else:
                             gc, gd = upstream[0][v], upstream[1][v]
-                        e.launch_backward(gc, gd, accumulate="atomic", overlap_forward=upstream_precomputed, tau_out=eng.tau_block[v])
+                        e.launch_backward(gc, gd, accumulate="atomic", overlap_forward=upstream_precomputed, tau_out=eng.tau_block[self.tau_row[i]])
                     if on_view is not None:
                         on_view(i, v)
             for st in self.streams:
                 main.wait_stream(st)
+        for (spare, v) in self.tau_merges:       # several bands of one view on this rank: their dL/dtau add up
+            eng.tau_block[v] += eng.tau_block[spare]
         if reduce:
             if self.reducer is not None:
                 self.reducer.all_reduce()

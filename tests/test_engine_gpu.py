@@ -238,6 +238,35 @@ def test_window_with_two_engines_on_two_streams_matches_one_engine():
         assert rel_err(w2.tau.cpu().numpy(), ref_tau.cpu().numpy()) <= 1e-5
 
 
+def test_several_bands_of_one_view_on_one_rank_sum_their_pose_gradient():
+    """plan_units(whole_bands=2) puts both bands of every view on the SAME rank: the backward kernel stores its dL/dtau, so the
+    second band must not overwrite the first (window.tau_rows: spare rows merged before the reduction)."""
+    import scenes as S
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    V = 3
+    cfg, sc, cams = _scene_and_cams(V=V)
+    packed = torch.stack([_pack(c) for c in cams])
+    grads = [S.make_pixel_grads(cfg["W"], cfg["H"], seed=40 + v) for v in range(V)]
+    gc = torch.stack([torch.from_numpy(g[0]) for g in grads]).cuda()
+    gd = torch.stack([torch.from_numpy(g[1]) for g in grads]).cuda()
+    w1 = KeyframeWindow(_engine(sc, cfg), packed)
+    w1.calibrate()
+    flat1 = w1.iteration((gc, gd)).clone()
+    tau1 = w1.tau_all.clone()
+    n = flat1.numel() - 8 * w1.engine.tau_slots
+    ea = _engine(sc, cfg)
+    for extra in ([], [_engine(sc, cfg, grad_flat=ea.grad_flat)]):      # one stream, then two engines on two streams
+        w2 = KeyframeWindow(ea, packed, extra_engines=extra, whole_bands=2)
+        assert len(w2.units) == 2 * V and len(w2.tau_merges) == V
+        w2.calibrate()
+        for _ in range(2):
+            flat2 = w2.iteration((gc, gd))
+            torch.cuda.synchronize()
+            assert rel_err(flat2[:n].cpu().numpy(), flat1[:n].cpu().numpy()) <= 1e-5
+            assert rel_err(w2.tau_all.cpu().numpy(), tau1.cpu().numpy()) <= 1e-5
+
+
 def test_bands_of_a_view_sum_to_the_view():
     """gsr_scene.tile_row_begin / tile_row_end: the bands of a view partition its pixels, and per-Gaussian gradients, dL/dtau
     and n_touched are linear in the pixels (window.py splits left-over keyframes over the ranks this way)."""

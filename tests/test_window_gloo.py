@@ -130,3 +130,47 @@ def test_plan_units_whole_bands():
         for v, y0, y1 in units:
             rows[v, (y0 if y1 else 0):(y1 if y1 else 43)] += 1
     assert (rows == 1).all()
+
+
+def test_tau_rows_give_every_band_of_a_view_on_one_rank_its_own_row():
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    from diff_gaussian_rasterization.window import plan_units, tau_rows
+
+    # default plan (10 keyframes on 8 ranks): every unit of a rank is a different view -> row = view, nothing to merge
+    for units in plan_units(10, 8, 43):
+        rows, merges = tau_rows(units, 10)
+        assert rows == [u[0] for u in units] and merges == []
+    # both bands of a whole view on the same rank: the second one writes a spare row behind the window's views
+    units = plan_units(10, 8, 43, whole_bands=2)[0]
+    rows, merges = tau_rows(units, 10)
+    assert rows[:2] == [0, 10] and merges[0] == (10, 0)
+    assert len(set(rows)) == len(rows) and all(r >= 10 for r, _ in merges)
+    assert sorted(v for _, v in merges) == sorted(u[0] for u in units[1::2] if u[0] < 8)
+
+
+def test_plans_cover_every_tile_row_of_every_view_exactly_once_randomised():
+    """Property of plan_units / band_rows over random window sizes, rank counts, image heights and row weights: the units of all
+    ranks partition (view, tile row); bands are consecutive and, while there are enough rows, non-empty."""
+    import random
+
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    from diff_gaussian_rasterization.window import band_rows, plan_units, tau_rows
+
+    rnd = random.Random(7)
+    for _ in range(3000):
+        gy, parts = rnd.randint(1, 80), rnd.randint(1, 12)
+        wts = rnd.choice([None, [0.0] * gy, [rnd.choice([0, 0, 0, 5.0]) for _ in range(gy)], [rnd.random() ** 4 * 100 for _ in range(gy)]])
+        b = band_rows(gy, parts, wts)
+        assert len(b) == parts and b[0][0] == 0 and b[-1][1] == gy
+        assert all(b[i][1] == b[i + 1][0] for i in range(parts - 1)) and all(y1 >= y0 for y0, y1 in b)
+        assert gy < parts or all(y1 > y0 for y0, y1 in b)
+    for _ in range(1500):
+        V, N, gy, wb = rnd.randint(0, 40), rnd.randint(1, 9), rnd.randint(1, 70), rnd.randint(1, 3)
+        plan = plan_units(V, N, gy, split=rnd.random() < 0.8, whole_bands=wb)
+        cover = np.zeros((V, gy), np.int64)
+        for units in plan:
+            rows, merges = tau_rows(units, V)
+            assert len(set(rows)) == len(rows) and all(0 <= v < V <= s for s, v in merges)
+            for v, y0, y1 in units:
+                cover[v, (y0 if y1 else 0):(y1 if y1 else gy)] += 1
+        assert (cover == 1).all()
