@@ -28,11 +28,11 @@ std::atomic<unsigned long long> g_launches{0};   // kernels launched by this lib
 std::atomic<bool> g_timing{false};
 const bool g_no_fused_sort = getenv("GSR_NO_FUSED_SORT") != nullptr;   // A/B switch for measurements
 const bool g_no_pdl = getenv("GSR_NO_PDL") != nullptr;                 // A/B switch: no programmatic dependent launches
-const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;
+const bool g_no_pdl_fwd = getenv("GSR_NO_PDL_FWD") != nullptr;         // A/B switch: forward not a programmatic dependent of the preprocess
 // what gsr_scene.exact_exp == 0 means: 2 = exact forward + backward (built-in), 1 = exact forward only, <= 0 = ex2.approx
 // (environment GSR_EXACT_EXP overrides the built-in default: A/B switch for measurements)
 const int g_exact_exp_default = getenv("GSR_EXACT_EXP") ? (atoi(getenv("GSR_EXACT_EXP")) > 0 ? atoi(getenv("GSR_EXACT_EXP")) : -1)
-                                                        : GSR_EXACT_EXP_DEFAULT;         // A/B switch: forward not a programmatic dependent of the preprocess
+                                                        : GSR_EXACT_EXP_DEFAULT;
 // lists longer than this are ordered on demand inside the forward compositing kernel (gsr_sort_on_demand); 0 = every list
 // is sorted completely
 std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")) : GSR_LAZY_MIN_DEFAULT};
@@ -41,7 +41,7 @@ std::atomic<int> g_lazy_min{getenv("GSR_LAZY_MIN") ? atoi(getenv("GSR_LAZY_MIN")
 constexpr int kMaxDevices = 64;
 struct StageEvents {
 	cudaEvent_t ev[7];
-	bool made = false;
+	std::atomic<bool> made{false};      // set (release) once all seven events exist; read without the mutex
 };
 StageEvents g_stage[kMaxDevices];
 std::mutex g_stage_mutex;
@@ -50,13 +50,13 @@ StageEvents* stage_events(bool create)
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
 	StageEvents& se = g_stage[dev];
-	if (!se.made) {
+	if (!se.made.load(std::memory_order_acquire)) {
 		if (!create) return nullptr;
 		std::lock_guard<std::mutex> lock(g_stage_mutex);
-		if (!se.made) {
+		if (!se.made.load(std::memory_order_relaxed)) {
 			for (int i = 0; i < 7; i++)
 				if (cudaEventCreate(&se.ev[i]) != cudaSuccess) return nullptr;
-			se.made = true;
+			se.made.store(true, std::memory_order_release);
 		}
 	}
 	return &se;
@@ -362,6 +362,7 @@ int gsr_rasterize_gaussians_backward(const gsr_scene* a, const int* radii, void*
 		return check_cuda("backward(P=0)");
 	}
 	if (!geom || !binning || !image || !radii) return fail(GSR_ERR_ARG, "null workspace");
+	if (capacity < 0 || capacity >= (1ll << 31)) return fail(GSR_ERR_ARG, "binning capacity out of range (pass the forward's)");
 	if (!dL_dout_color || !dL_dout_depth) return fail(GSR_ERR_ARG, "null upstream gradient");
 	if (!s.projmatrix_raw) return fail(GSR_ERR_ARG, "projmatrix_raw is required by the backward");
 	if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacity) return fail(GSR_ERR_ARG, "null gradient output");
