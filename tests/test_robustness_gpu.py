@@ -67,6 +67,23 @@ def test_nosync_forward_with_a_tiny_workspace_overflows_cleanly_and_recovers(cap
     assert torch.equal(eng.color, want_color) and rel_err(eng.g_tau.cpu().numpy(), want_tau.cpu().numpy()) <= 1e-5
 
 
+def test_backward_rejects_a_binning_capacity_out_of_range():
+    """The capacity handed to the backward carves up the binning workspace: a negative one must not turn into a huge offset."""
+    cfg, sc, eng = _small()
+    eng.calibrate()
+    eng.step(use_graph=False)
+    cap = eng.capacity
+    try:
+        eng.capacity = -1
+        with pytest.raises(Exception, match="capacity out of range"):
+            eng.launch_backward()
+    finally:
+        eng.capacity = cap
+    eng.launch_backward()
+    torch.cuda.synchronize()
+    assert not eng.header()[1]
+
+
 def test_backward_spin_timeout_is_reported_as_an_error_not_as_overflow():
     """upstream_ready that never arrives: the compositing backward gives up after its bounded spin, flags the header's
     spin_timeout word (not the capacity-overflow word) and the host sees GSR_ERR_TIMEOUT."""
