@@ -9,8 +9,9 @@ mapping, 1200x680, 500 000 Gaussians, 10-keyframe window.  A *step* is one windo
 forward + backward incl. dL/dtau of all 10 views through one replicated map, per-Gaussian gradients summed over the views;
 the loss is excluded from `value` (dL/dpixel tensors are pre-generated, seed 1).  The views are sharded over the N ranks
 (whole keyframes round robin, left-over keyframes split into bands of tile rows, window.py) and the packed gradient buffer
-is summed by ONE NCCL all-reduce inside the timed region: strong scaling, value = window iterations/s of the whole job
-(max-over-ranks device time).  At N = 1 the line also carries `also_C1`: the C1 tracking step (640x480, 100 k Gaussians,
+is summed by ONE collective inside the timed region -- the library's own NVSwitch kernel (csrc/window_reduce.cu; multimem.ld_reduce +
+multimem.st over symmetric memory), dist.all_reduce / NCCL with --nccl-reduce or without multicast memory: strong scaling, value =
+window iterations/s of the whole job (max-over-ranks device time).  At N = 1 the line also carries `also_C1`: the C1 tracking step (640x480, 100 k Gaussians,
 one view, pose perturbed every step), last round's headline.
 
   value     device-timed (CUDA events per step, L2 flushed between steps) with everything resident in HBM
