@@ -680,7 +680,8 @@ def run_window(args, rank, world, device):
                     "collective": ("all_reduce(sum) of %d B (packed per-Gaussian gradients + every view's dL/dtau) per step, inside the timed region, by %s; "
                                    "alone %.3f ms (dist.all_reduce / NCCL on the same buffer: %.3f ms)"
                                    % (grad_bytes, "the library's NVSwitch kernel (gsr_window_allreduce: multimem.ld_reduce + multimem.st over symmetric memory)"
-                                      if reducer is not None else "dist.all_reduce (NCCL)", coll_ms, nccl_ms)) if reduce else "none",
+                                      if reducer is not None else "dist.all_reduce (NCCL)", coll_ms, nccl_ms)) if (reduce and world > 1)
+                                  else ("none (one rank: the views of the window add up in the gradient buffer of this GPU, %d B)" % grad_bytes if reduce else "none"),
                     "parallelism": "keyframe-parallel x%d (left-over views split into bands of tile rows), %d engine(s) / stream(s) per GPU"
                                    % (world, len(win.engines)),
                     "path": "KeyframeWindow over RasterEngine(s), %s, no host sync; per-tile lists ordered %s"
