@@ -716,7 +716,8 @@ def run_window(args, rank, world, device):
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_iters_per_s(S.with_camera(sc, S.make_camera(W, H, cfg["fx"], cfg["fy"], cfg["cx"], cfg["cy"], S.arc_poses(V, radius=0.5, seed=2)[0])),
                                                   dc, dd, views_per_iter=V)
-        line["cpu_baseline"] = {"value": v, "unit": WINDOW_UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": WINDOW_UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "script_C0": script_c0_baseline()}      # BASELINE.json configs[0], the reference's own CPU script
     return line
 
 
