@@ -13,8 +13,10 @@
  * gso_cov2d_pose_jacobian / gso_mean2d_pose_jacobian (tests/test_oracle_kat.py),
  * (ii) torch-autograd through SE3_exp(tau)*T_cw (utils/pose_utils.py:61-93), and
  * (iii) on the GPU box the unmodified reference kernels themselves (oracle/_ref/libgsref.so,
- * tests/test_parity_reference.py) plus committed fixtures generated from them
- * (tests/golden/make_ref_golden.py).
+ * tests/test_parity_gpu.py, tests/test_config_scale_gpu.py at the BASELINE shapes) plus committed fixtures generated
+ * from them (tests/golden/make_ref_golden.py -> tests/test_golden_reference.py, on the CPU), and (iv) the reference's
+ * analytic-Jacobian script chain executed on C0 (tests/golden/make_script_chain_golden.py -> tests/test_script_chain.py;
+ * gso_set_math_mode selects the script's dense formulation).
  *
  * Stages (each takes/returns plain arrays so a test can substitute the CUDA intermediates):
  *   gso_preprocess   CR/forward.cu:157-401  (+ auxiliary.h:41-56,139-164)

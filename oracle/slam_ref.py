@@ -1,5 +1,7 @@
 """TEST INFRASTRUCTURE (oracle) -- NOT product code: plain-torch restatement of the reference code around the rasterizer, used to check the fused
-slam_ops kernels.  Each function follows the reference lines it cites (repo root = /root/reference)."""
+slam_ops kernels.  Each function follows the reference lines it cites (repo root = /root/reference).
+Parity pinning: tests/golden/slam_golden.npz is produced by IMPORTING the reference's own utils/slam_utils.py, utils/pose_utils.py and
+utils/camera_utils.py (tests/golden/make_slam_golden.py); tests/test_slam_golden.py checks this restatement against it on the CPU."""
 import torch
 
 
