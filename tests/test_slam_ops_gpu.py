@@ -1,5 +1,5 @@
 """GPU parity of the fused callers of the rasterizer (slam_ops: loss + gradients, Adam + pose update + camera tensors)
-against a plain-torch restatement of the reference (tests/slam_ref.py) with torch autograd / torch.optim.Adam, and an
+against a plain-torch restatement of the reference (oracle/slam_ref.py, pinned to the reference modules by tests/test_slam_golden.py) with torch autograd / torch.optim.Adam, and an
 end-to-end check of the graph-captured tracking loop."""
 import numpy as np
 import pytest
