@@ -53,7 +53,7 @@ struct PixelState {
 };
 
 // One thread per pixel: entries grp[0 .. cnt) (cnt even, a padding record with opacity 0 at the end if needed)
-// EXACT: G from the reference's expf (backward.cu:779), so that alpha -- and with it every skip decision -- is bit-identical to
+// EXACT: G from the reference's expf (backward.cu:772), so that alpha -- and with it every skip decision -- is bit-identical to
 // the (exact) forward's and T = T / (1 - alpha) retraces the forward's transmittances to an ulp or two per step (the quotient
 // itself as T * rcp.approx(1 - alpha): a correctly rounded division, -DGSR_BWD_DIV=1, was measured -- gradients 4e-7 instead
 // of 7e-7 from the reference at 300 k Gaussians, compositing backward 126 -> 157 us at C1 -- and is not worth it).

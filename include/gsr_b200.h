@@ -119,7 +119,7 @@ typedef struct gsr_scene {
 	                                longer than this are ordered on demand; < 0: every list of this call is sorted completely */
 	int exact_exp;               /* forward + backward: how alpha = min(0.99, o * exp(power)) is evaluated by the compositing kernels.
 	                                0 = the library default (2; environment GSR_EXACT_EXP overrides);
-	                                2: the reference's own expf (forward.cu:496, backward.cu:779) in forward and backward -- T, every
+	                                2: the reference's own expf (forward.cu:496, backward.cu:772) in forward and backward -- T, every
 	                                   threshold decision, n_contrib, n_touched and final_T are bit-identical to the reference's and
 	                                   the gradients agree with it to ~1e-6 (its own run-to-run spread is ~1e-7);
 	                                1: exact in the forward only (bit-identical integer outputs; gradients to ~1e-4);
