@@ -56,6 +56,24 @@ def test_reference_render_call_sites_fit_this_package():
     assert all('"%s"' % k in src for k in ref_keys)
 
 
+def test_sh_to_rgb_matches_the_reference_eval_sh_golden():
+    """pipe.convert_SHs_python: sh_to_rgb against colours computed by the reference's own eval_sh + render() expression
+    (tests/golden/make_sh_golden.py imports gaussian_splatting/utils/sh_utils.py), every degree, float64; plus autograd."""
+    import gaussian_renderer as gr
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sh_eval_golden.npz"))
+    f, xyz, c = (torch.from_numpy(g[k]) for k in ("features", "xyz", "camera_center"))
+    for deg in range(4):
+        got = gr.sh_to_rgb(f, deg, xyz, c).numpy()
+        assert got.shape == g["rgb_deg%d" % deg].shape
+        np.testing.assert_allclose(got, g["rgb_deg%d" % deg], rtol=0, atol=1e-13)
+        assert (got == 0).any() and (got > 0).any()      # the clamp at zero is exercised
+    with pytest.raises(NotImplementedError):
+        gr.sh_basis(4, xyz)
+    f8, x8 = f[:8].clone().requires_grad_(True), xyz[:8].clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a, b: gr.sh_to_rgb(a, 3, b, c), (f8, x8), eps=1e-6, atol=1e-6)
+
+
 def _stand_ins(sc, device):
     import scenes as S
 
@@ -110,3 +128,32 @@ def test_render_glue_outputs_and_gradients(masked):
     # an empty model renders nothing (reference :38-39)
     empty = types.SimpleNamespace(get_xyz=torch.zeros((0, 3), device="cuda"))
     assert gr.render(cam, empty, pipe, t["bg"]) is None
+
+
+@pytest.mark.gpu
+def test_render_glue_with_python_sh_conversion_matches_the_kernel_sh_path():
+    """pipe.convert_SHs_python=True (colours from sh_to_rgb, handed over as colors_precomp) renders what the kernel's own SH
+    evaluation renders; SH coefficients and positions receive the same gradients (autograd through sh_to_rgb against
+    backward.cu:21-145).  The pose gradient differs on purpose: only the kernel path carries the colours' camera-centre term."""
+    import gaussian_renderer as gr
+    import scenes as S
+    from common import rel_err
+
+    cfg = dict(W=200, H=136, fx=180.0, fy=182.0, cx=100.0, cy=68.0, P=3000, sh_degree=3)
+    sc = S.make_scene(cfg, seed=6)
+    sc["scales"] = sc["scales"] * 2.0
+    dc, dd = S.make_pixel_grads(cfg["W"], cfg["H"])
+    res = []
+    for python_sh in (False, True):
+        t, pc, cam = _stand_ins(sc, "cuda")
+        pipe = types.SimpleNamespace(compute_cov3D_python=False, convert_SHs_python=python_sh)
+        pkg = gr.render(cam, pc, pipe, t["bg"])
+        ((pkg["render"] * torch.from_numpy(dc).cuda()).sum() + (pkg["depth"] * torch.from_numpy(dd).cuda()).sum()).backward()
+        res.append((pkg, pc))
+    (a, pa), (b, pb) = res
+    np.testing.assert_array_equal(a["radii"].cpu().numpy(), b["radii"].cpu().numpy())
+    np.testing.assert_array_equal(a["n_touched"].cpu().numpy(), b["n_touched"].cpu().numpy())
+    assert rel_err(b["render"].detach().cpu().numpy(), a["render"].detach().cpu().numpy()) <= 1e-5
+    assert rel_err(pb.get_features.grad.cpu().numpy(), pa.get_features.grad.cpu().numpy()) <= 1e-4
+    assert rel_err(pb.get_xyz.grad.cpu().numpy(), pa.get_xyz.grad.cpu().numpy()) <= 1e-4
+    assert rel_err(pb.get_opacity.grad.cpu().numpy(), pa.get_opacity.grad.cpu().numpy()) <= 1e-4
