@@ -174,3 +174,80 @@ def test_plans_cover_every_tile_row_of_every_view_exactly_once_randomised():
             for v, y0, y1 in units:
                 cover[v, (y0 if y1 else 0):(y1 if y1 else gy)] += 1
         assert (cover == 1).all()
+
+
+class _StandInEngine:
+    """The part of RasterEngine a KeyframeWindow drives, on the CPU, with the kernels' write semantics: per-Gaussian gradients
+    are overwritten unless `accumulate`, dL/dtau is STORED into tau_out; a band contributes its rows' share of the view."""
+
+    def __init__(self, n, tau_slots=64):
+        self.dev, self.H, self.tau_slots, self.n = torch.device("cpu"), GRID_Y * 16, tau_slots, n
+        self.grad_flat = torch.full((n + 8 * tau_slots,), 7.0)      # stale contents: the window must not rely on zeros
+        self.tau_block = self.grad_flat[n:].view(tau_slots, 8)
+        self.view, self.band, self.calls = -1, (0, 0), 0
+
+    def set_camera(self, cam):
+        self.view = int(cam[0])
+
+    def set_band(self, y0=0, y1=0):
+        self.band = (int(y0), int(y1))
+
+    def use_order(self, key):
+        pass
+
+    def calibrate(self, build_order=True):
+        return 0
+
+    def launch_forward(self, fused_loss=None):
+        pass
+
+    def launch_backward(self, dL_dcolor=None, dL_ddepth=None, accumulate=False, overlap_forward=False, upstream_ready=None, tau_out=None):
+        share = 1.0 if self.band[1] == 0 else (self.band[1] - self.band[0]) / GRID_Y
+        g = share * _view_grad(self.view, self.n)
+        if accumulate:
+            self.grad_flat[:self.n] += g
+        else:
+            self.grad_flat[:self.n] = g
+        tau_out[:6] = share * _view_grad(100 + self.view, 6)
+        self.calls += 1
+
+
+def _window_worker(rank, world, port, V, n, whole_bands, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    from diff_gaussian_rasterization.window import KeyframeWindow
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _StandInEngine(n)
+    cams = torch.zeros(V, 52)
+    cams[:, 0] = torch.arange(V, dtype=torch.float32)
+    win = KeyframeWindow(eng, cams, rank=rank, world_size=world, whole_bands=whole_bands)
+    win.calibrate()
+    up = (torch.zeros(V, 1), torch.zeros(V, 1))
+    for _ in range(2):      # twice: nothing of the first iteration may leak into the second
+        flat = win.iteration(up)
+    assert eng.calls == 2 * len(win.units)
+    np.save(os.path.join(out_dir, "w%d.npy" % rank), torch.cat([flat[:n], win.tau_all.reshape(-1)]).numpy())
+    np.save(os.path.join(out_dir, "t%d.npy" % rank), win.tau.numpy())
+    np.save(os.path.join(out_dir, "v%d.npy" % rank), np.asarray(win.views, np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,V,whole_bands", [(2, 5, 1), (2, 4, 2), (3, 7, 3)])
+def test_keyframe_window_iteration_over_gloo(tmp_path, world, V, whole_bands):
+    """The real KeyframeWindow (plan, per-unit launches, dL/dtau rows, the one all-reduce) over a stand-in engine on world_size-2 / 3
+    gloo groups: every rank ends with the window gradient and every view's dL/dtau, also when a rank holds several bands of a view."""
+    n = 1031
+    mp.spawn(_window_worker, args=(world, _free_port(), V, n, whole_bands, str(tmp_path)), nprocs=world, join=True)
+    want_g = sum(_view_grad(v, n) for v in range(V)).numpy()
+    want_tau = np.zeros((V, 8), np.float32)
+    for v in range(V):
+        want_tau[v, :6] = _view_grad(100 + v, 6).numpy()
+    for r in range(world):
+        got = np.load(tmp_path / ("w%d.npy" % r))
+        np.testing.assert_allclose(got[:n], want_g, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(got[n:].reshape(V, 6), want_tau[:, :6], rtol=1e-5, atol=1e-6)
+        views = np.load(tmp_path / ("v%d.npy" % r))
+        np.testing.assert_allclose(np.load(tmp_path / ("t%d.npy" % r)), want_tau[views, :6], rtol=1e-5, atol=1e-6)
