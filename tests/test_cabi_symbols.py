@@ -83,3 +83,49 @@ def test_python_api_surface_matches_reference():
         r.forward(x, x, x)
     with pytest.raises(Exception, match="exactly one of either scale/rotation"):
         r.forward(x, x, x, shs=x)
+
+
+def test_argument_errors_of_the_round_2_entry_points():
+    """Validation that returns before any CUDA work: bands of tile rows, SH degree / coefficient count, image limits, the
+    backward's binning capacity, the switch reduction's rank / alignment / signal-pad checks."""
+    from diff_gaussian_rasterization import _cabi
+    from diff_gaussian_rasterization._cabi import GsrScene
+
+    lib = _cabi.load()
+    fake = 0x1000      # never dereferenced
+    err = lambda: lib.gsr_error_string().decode()
+
+    def scene(**kw):
+        s = GsrScene()
+        s.P, s.W, s.H, s.M, s.D = 10, 64, 48, 1, 0
+        for f in ("means3D", "opacities", "viewmatrix", "projmatrix", "projmatrix_raw", "background", "campos", "shs", "scales", "rotations"):
+            setattr(s, f, fake)
+        for k, v in kw.items():
+            setattr(s, k, v)
+        return s
+
+    plan = lambda s: lib.gsr_forward_plan(C.byref(s), None, 0, None, None, None)
+    assert plan(scene()) == _cabi.GSR_ERR_WORKSPACE                                  # a valid scene gets as far as the workspace check
+    assert plan(scene(tile_row_begin=2, tile_row_end=2)) == _cabi.GSR_ERR_ARG and "tile_row_begin" in err()
+    assert plan(scene(tile_row_begin=0, tile_row_end=4)) == _cabi.GSR_ERR_ARG        # 48 rows of pixels = 3 tile rows
+    assert plan(scene(tile_row_begin=1, tile_row_end=3)) == _cabi.GSR_ERR_WORKSPACE
+    assert plan(scene(tile_row_begin=1, tile_row_end=3, densify_denom=fake)) == _cabi.GSR_ERR_ARG and "per view" in err()
+    assert plan(scene(D=2, M=4)) == _cabi.GSR_ERR_ARG and "SH degree" in err()       # degree 2 needs 9 coefficients
+    assert plan(scene(D=3, M=16)) == _cabi.GSR_ERR_WORKSPACE
+    assert plan(scene(M=17)) == _cabi.GSR_ERR_ARG
+    assert plan(scene(W=16 * 65535 + 1)) == _cabi.GSR_ERR_ARG and "too large" in err()
+    assert plan(scene(W=0)) == _cabi.GSR_ERR_ARG and plan(scene(P=-1)) == _cabi.GSR_ERR_ARG
+    assert plan(scene(rotations=fake + 4)) == _cabi.GSR_ERR_ARG and "16-byte" in err()
+    vp = C.c_void_p
+    bwd = lambda cap: lib.gsr_rasterize_gaussians_backward(C.byref(scene()), vp(fake), vp(fake), vp(fake), cap, vp(fake), vp(fake), vp(fake),
+                                                           *([vp(fake)] * 9), None)
+    assert bwd(-1) == _cabi.GSR_ERR_ARG and "capacity out of range" in err()
+    assert bwd(1 << 31) == _cabi.GSR_ERR_ARG
+    red = lambda mc, rank, world, n, pad: lib.gsr_window_allreduce(vp(mc), vp(fake), rank, world, n, 64, pad, vp(fake), None)
+    assert red(0x10000, 0, 1, 1024, 4096) == _cabi.GSR_ERR_ARG and "world size" in err()
+    assert red(0x10000, 8, 8, 1024, 4096) == _cabi.GSR_ERR_ARG
+    assert red(0x10004, 0, 8, 1024, 4096) == _cabi.GSR_ERR_ARG and "16-byte aligned" in err()
+    assert red(0x10000, 0, 8, 1022, 4096) == _cabi.GSR_ERR_ARG
+    assert red(0x10000, 0, 8, 1024, 16) == _cabi.GSR_ERR_WORKSPACE and "signal pad" in err()
+    assert lib.gsr_mark_visible(-1, None, None, None, None, None) == _cabi.GSR_ERR_ARG
+    assert lib.gsr_sort_on_demand(-1) == lib.gsr_sort_on_demand(-1) > 0              # query leaves the threshold alone
