@@ -35,6 +35,21 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found at %s and %s is missing/stale" % (NVCC, OUT))
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    # several ranks of one job may find the library stale at the same moment (torchrun on a box whose snapshot lost the mtimes):
+    # one of them builds, the others wait for the lock and find the fresh library
+    import fcntl
+
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return OUT
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir, verbose):
     extra = ["-Xptxas", "-v"] if verbose else []
     extra += os.environ.get("GSR_EXTRA_NVCC_FLAGS", "").split()      # experiments, e.g. -DGSR_BWD_SLOTS=8
     if os.environ.get("GSR_PHASE_PROBE"):      # diagnostic build (tools/phase_probe.py), never the product
@@ -52,10 +67,14 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart"]
+    tmp = OUT + ".tmp%d" % os.getpid()      # link beside the target, then rename: a process loading the library never sees half of it
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, OUT)
     return OUT
 
 
