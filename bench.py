@@ -121,8 +121,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------
 def build_workload(name, steps_total, rank, device):
-    import scenes as S
-    from diff_gaussian_rasterization.engine import RasterEngine
+    import scenes as S      # (nothing of the product package: the reference arm builds its inputs here too)
 
     cfg = S.CONFIGS[name]
     sc = S.make_scene(name, seed=0)
