@@ -100,3 +100,17 @@ def test_product_arm_refuses_to_run_without_a_cuda_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout) and r.stdout.strip() == ""
+
+
+def test_reference_arm_builds_its_inputs_without_the_product_library():
+    """`--impl reference` must not map libgsr_b200.so.  Its input builders (shared with the product arm) are run
+    in a fresh process whose memory map is then searched for the library."""
+    code = (
+        "import sys; sys.argv = ['bench.py']; sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "bench.build_workload('C1_tum_tracking', 4, 0, 'cpu')\n"
+        "bench.window_inputs('C3_batched_tracking', 2)\n"
+        "bench.workload_config('C2_replica_mapping')\n"
+        "print('MAPPED' if any('libgsr_b200' in l for l in open('/proc/self/maps')) else 'CLEAN')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("CLEAN"), r.stderr[-2000:]
