@@ -119,6 +119,23 @@ def allreduce_window_gradients(grad_flat, group=None):
     return grad_flat
 
 
+def allreduce_densification_stats(xyz_gradient_accum=None, denom=None, max_radii2D=None, group=None):
+    """The densification statistics of a keyframe-sharded window: every rank's engines accumulate
+    xyz_gradient_accum += ||dL/dmeans2D||, denom += 1 and max_radii2D = max(., radii) for the views THEY render
+    (RasterEngine.attach_densification_stats; gaussian_model.py:767-771, utils/slam_backend.py:115-121), so a replicated optimiser
+    needs the sum / sum / maximum over the ranks before it densifies -- every `gaussian_update_every` iterations, not per
+    iteration.  Call with per-rank DELTAS for the two sums (tensors zeroed at the last call) or reset them afterwards.
+    The statistics are per whole view (a norm is not linear in the pixels): run the iterations that feed them with
+    KeyframeWindow(split=False).  In place; no-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    for t, op in ((xyz_gradient_accum, dist.ReduceOp.SUM), (denom, dist.ReduceOp.SUM), (max_radii2D, dist.ReduceOp.MAX)):
+        if t is not None:
+            dist.all_reduce(t, op=op, group=group)
+
+
 class SwitchReducer:
     """The window's gradient buffer in a symmetric allocation + its sum over the ranks by ONE kernel over NVSwitch multicast
     memory (gsr_window_allreduce: multimem.ld_reduce / multimem.st, no NCCL on the data path).

@@ -251,3 +251,39 @@ def test_keyframe_window_iteration_over_gloo(tmp_path, world, V, whole_bands):
         np.testing.assert_allclose(got[n:].reshape(V, 6), want_tau[:, :6], rtol=1e-5, atol=1e-6)
         views = np.load(tmp_path / ("v%d.npy" % r))
         np.testing.assert_allclose(np.load(tmp_path / ("t%d.npy" % r)), want_tau[views, :6], rtol=1e-5, atol=1e-6)
+
+
+def _densify_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "gs-slam-analytica_jacobian_b200"))
+    from diff_gaussian_rasterization.window import allreduce_densification_stats, shard_views
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, V = 257, 5
+    accum, denom, radii = torch.zeros(P), torch.zeros(P), torch.zeros(P)
+    for v in shard_views(V, world, rank):      # what the backward epilogue of every local view does (gaussian_model.py:767-771)
+        g = _view_grad(v, P).abs()
+        vis = _view_grad(50 + v, P) > 0
+        accum[vis] += g[vis]
+        denom[vis] += 1
+        radii[vis] = torch.maximum(radii[vis], (10 * _view_grad(70 + v, P).abs())[vis])
+    allreduce_densification_stats(accum, denom, radii)
+    allreduce_densification_stats(None, None, None)      # nothing attached: nothing to do
+    np.save(os.path.join(out_dir, "d%d.npy" % rank), torch.stack([accum, denom, radii]).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_densification_stats_reduce_over_the_ranks(tmp_path):
+    mp.spawn(_densify_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    P, V = 257, 5
+    accum, denom, radii = torch.zeros(P), torch.zeros(P), torch.zeros(P)
+    for v in range(V):
+        g, vis = _view_grad(v, P).abs(), _view_grad(50 + v, P) > 0
+        accum[vis] += g[vis]
+        denom[vis] += 1
+        radii[vis] = torch.maximum(radii[vis], (10 * _view_grad(70 + v, P).abs())[vis])
+    want = torch.stack([accum, denom, radii]).numpy()
+    for r in range(2):
+        np.testing.assert_allclose(np.load(tmp_path / ("d%d.npy" % r)), want, rtol=1e-6, atol=1e-6)
